@@ -1,0 +1,24 @@
+// Error state, version and launch accounting of the C ABI (include/gd_b200.h).
+#include "common.cuh"
+#include "../../include/gd_b200.h"
+#include <stdarg.h>
+
+namespace gd {
+namespace {
+thread_local char g_err[512] = "";
+thread_local int64_t g_launches = 0;
+}  // namespace
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches += n; }
+}  // namespace gd
+
+extern "C" const char* gd_last_error(void) { return gd::g_err; }
+extern "C" int gd_version(void) { return GD_B200_ABI_VERSION; }
+extern "C" int64_t gd_launch_count(void) { return gd::g_launches; }
+extern "C" void gd_launch_count_reset(void) { gd::g_launches = 0; }

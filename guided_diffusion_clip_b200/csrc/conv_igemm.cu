@@ -1,0 +1,466 @@
+// Implicit-GEMM convolution (3x3 pad 1 / 1x1) on tcgen05 tensor cores for sm_100a.
+//
+// Replaces every nn.Conv2d / nn.Conv1d(k=1) call site of the reference torso
+// (guided_diffusion/unet.py:185,211,222,286,294,483,616 via nn.py:22-32) and, with flipped/transposed
+// packed weights, their data-gradient (conv backward-data) used by the guidance gradient.
+//
+// Formulation:  D[m, n] = sum_k A[m, k] * B[n, k]
+//   m  : output pixel.  One CTA tile = 128 pixels = a BI x BH x BW patch (images x rows x cols).
+//   k  : (tap, channel) of source 0, followed by the channels of an optional 1x1 "skip" source 1
+//        (this fuses ResBlock.skip_connection + out_layers conv into one accumulation, unet.py:256).
+//   n  : output channel.
+// Activations are NHWC fp16 "channel views" (pointer, C, ld) so concatenations are free: producers
+// write straight into channel slices of the concat buffer.  For a K block (tap, 64 channels) the A tile
+// is ONE 4-D TMA box {64ch, BW, BH, BI} at (c, x0+dx, y0+dy, n0): the conv halo and the image border are
+// the TMA's out-of-bounds zero fill, and the box lands in shared memory exactly as the 128-row x 128-byte
+// K-major SWIZZLE_128B tile tcgen05.mma wants.  Weights are a plain 2-D TMA box {64, BN}.
+//
+// Warp roles (192 threads, 1 CTA/SM, persistent over tiles):
+//   warp 0   : TMA producer (one lane)           smem ring: full[s]/empty[s] mbarriers
+//   warp 1   : TMEM alloc + tcgen05.mma issuer   accumulators: 2 x 256 TMEM columns (double buffered)
+//   warps 2-5: epilogue (tcgen05.ld -> bias/residual -> fp16 NHWC or fp32 NCHW stores)
+#include "common.cuh"
+#include "../../include/gd_b200.h"
+
+namespace gd {
+void count_launch(int n = 1);
+
+namespace {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kATileBytes = kBM * kBK * 2;  // 16 KiB
+constexpr int kMaxStages = 8;
+constexpr int kThreads = 192;
+constexpr int kSmemBudget = 227 * 1024;
+constexpr int kBarrierBytes = 1024;
+
+struct ConvArgs {
+  // geometry
+  int n_img, h, w;
+  int bi, bh, bw;              // patch
+  int patches_x, patches_y;    // per image (group)
+  int m_tiles, n_tiles;
+  int bn;                      // N tile
+  int stages;
+  // K blocks
+  int kb0_per_tap;             // C0 / 64
+  int taps;                    // 9 or 1
+  int kb0;                     // taps * C0/64
+  int kb_total;                // kb0 + C1/64
+  // epilogue
+  int cout;
+  const float* bias;
+  const __half* res;
+  int ld_res;
+  int res_mode;
+  void* out;
+  int ld_out;
+  int out_mode;
+  float out_scale;
+};
+
+__device__ __forceinline__ void tile_coords(const ConvArgs& p, int m_tile, int& n0, int& y0, int& x0) {
+  const int px = m_tile % p.patches_x;
+  const int t = m_tile / p.patches_x;
+  const int py = t % p.patches_y;
+  const int ig = t / p.patches_y;
+  n0 = ig * p.bi;
+  y0 = py * p.bh;
+  x0 = px * p.bw;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+                  const __grid_constant__ CUtensorMap map_b, const ConvArgs p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [barriers 1 KiB][stage 0: A | B][stage 1] ...   (stage bases are 1024-aligned)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full = empty_bar + kMaxStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint8_t* stage_base = smem + kBarrierBytes;
+  const int b_tile_bytes = p.bn * kBK * 2;
+  const int stage_bytes = kATileBytes + b_tile_bytes;  // multiple of 1024 since bn % 16 == 0 -> bn*128 % 2048 == 0
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a0);
+    tma_prefetch_desc(&map_a1);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_base_slot, 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        const int m_tile = tile / p.n_tiles;
+        int n0, y0, x0;
+        tile_coords(p, m_tile, n0, y0, x0);
+        int tap = 0, cc = 0;
+        for (int kb = 0; kb < p.kb_total; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = stage_base + stage * stage_bytes;
+          uint8_t* sb = sa + kATileBytes;
+          mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
+          if (kb < p.kb0) {
+            int dy = 0, dx = 0;
+            if (p.taps == 9) {
+              dy = tap / 3 - 1;
+              dx = tap % 3 - 1;
+            }
+            tma_load_4d(sa, &map_a0, &full_bar[stage], cc * kBK, x0 + dx, y0 + dy, n0);
+            if (++cc == p.kb0_per_tap) {
+              cc = 0;
+              ++tap;
+            }
+          } else {
+            tma_load_4d(sa, &map_a1, &full_bar[stage], (kb - p.kb0) * kBK, x0, y0, n0);
+          }
+          tma_load_2d(sb, &map_b, &full_bar[stage], kb * kBK, n_tile * p.bn);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(kBM, static_cast<uint32_t>(p.bn));
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
+        for (int kb = 0; kb < p.kb_total; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stage_base + stage * stage_bytes);
+          const uint64_t a_desc = umma_smem_desc_sw128(sa);
+          const uint64_t b_desc = umma_smem_desc_sw128(sa + kATileBytes);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            // advance 16 fp16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in (addr >> 4) units
+            umma_f16(d_tmem, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
+                     static_cast<uint32_t>((kb | k) != 0));
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int quarter = warp & 3;          // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;   // row of the 128-row tile == pixel within the patch
+    const int patch_px = p.bh * p.bw;
+    const int i_local = row / patch_px;
+    const int rem = row - i_local * patch_px;
+    const int y_local = rem / p.bw;
+    const int x_local = rem - y_local * p.bw;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = tile / p.n_tiles;
+      int n0, y0, x0;
+      tile_coords(p, m_tile, n0, y0, x0);
+      const int img = n0 + i_local, y = y0 + y_local, x = x0 + x_local;
+      const bool valid = (img < p.n_img) && (y < p.h) && (x < p.w);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * 256);
+      const int col_base = n_tile * p.bn;
+      const size_t pix = (static_cast<size_t>(img) * p.h + y) * p.w + x;
+
+      for (int c0 = 0; c0 < p.bn; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(t_row + static_cast<uint32_t>(c0), v);
+        tmem_ld_wait();
+        if (valid) {
+          const int col = col_base + c0;
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            f[j] = __uint_as_float(v[j]);
+            if (p.bias != nullptr && col + j < p.cout) f[j] += __ldg(p.bias + col + j);
+          }
+          if (p.res_mode != GD_RES_NONE && col + 16 <= p.cout) {
+            float r[16];
+            if (p.res_mode == GD_RES_SAME) {
+              const __half* rp = p.res + pix * p.ld_res + col;
+              half8_to_float(ld_half8(rp), *reinterpret_cast<float(*)[8]>(&r[0]));
+              half8_to_float(ld_half8(rp + 8), *reinterpret_cast<float(*)[8]>(&r[8]));
+            } else if (p.res_mode == GD_RES_UPSAMPLE2) {
+              // residual lives at half resolution: nearest-neighbour x2 (unet.py:107,241)
+              const size_t rpix = (static_cast<size_t>(img) * (p.h >> 1) + (y >> 1)) * (p.w >> 1) + (x >> 1);
+              const __half* rp = p.res + rpix * p.ld_res + col;
+              half8_to_float(ld_half8(rp), *reinterpret_cast<float(*)[8]>(&r[0]));
+              half8_to_float(ld_half8(rp + 8), *reinterpret_cast<float(*)[8]>(&r[8]));
+            } else {  // GD_RES_AVGPOOL2: residual lives at double resolution (unet.py:136,241)
+#pragma unroll
+              for (int j = 0; j < 16; ++j) r[j] = 0.f;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const size_t rpix =
+                    (static_cast<size_t>(img) * (p.h * 2) + (2 * y + (q >> 1))) * (p.w * 2) + (2 * x + (q & 1));
+                const __half* rp = p.res + rpix * p.ld_res + col;
+                float t[8];
+                half8_to_float(ld_half8(rp), t);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) r[j] += t[j];
+                half8_to_float(ld_half8(rp + 8), t);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) r[8 + j] += t[j];
+              }
+#pragma unroll
+              for (int j = 0; j < 16; ++j) r[j] *= 0.25f;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] += r[j];
+          }
+          if (p.out_scale != 1.0f) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] *= p.out_scale;
+          }
+          if (p.out_mode == GD_OUT_NHWC_F16) {
+            __half* op = reinterpret_cast<__half*>(p.out) + pix * p.ld_out + col;
+            if (col + 16 <= p.cout) {
+              st_half8(op, float_to_half8(*reinterpret_cast<float(*)[8]>(&f[0])));
+              st_half8(op + 8, float_to_half8(*reinterpret_cast<float(*)[8]>(&f[8])));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (col + j < p.cout) op[j] = __float2half_rn(f[j]);
+            }
+          } else {  // GD_OUT_NCHW_F32: adjacent threads are adjacent x -> coalesced per channel plane
+            float* op = reinterpret_cast<float*>(p.out);
+            const size_t plane = static_cast<size_t>(p.h) * p.w;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (col + j < p.cout)
+                op[(static_cast<size_t>(img) * p.cout + col + j) * plane + static_cast<size_t>(y) * p.w + x] = f[j];
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// host side
+// --------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || sym == nullptr) return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(sym);
+  return fn;
+}
+
+int encode_act_map(CUtensorMap* m, const void* base, int c, int ld, int n, int h, int w, int bi, int bh, int bw) {
+  EncodeTiledFn enc = get_encode_fn();
+  GD_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled driver entry point unavailable");
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)w * ld * 2, (cuuint64_t)h * w * ld * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bi};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation) failed: %d (c=%d ld=%d n=%d h=%d w=%d)", (int)r, c,
+             ld, n, h, w);
+  return 0;
+}
+
+int encode_weight_map(CUtensorMap* m, const void* base, int k_total, int n_pad, int bn) {
+  EncodeTiledFn enc = get_encode_fn();
+  GD_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled driver entry point unavailable");
+  cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)n_pad};
+  cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)bn};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights) failed: %d (k=%d n=%d bn=%d)", (int)r, k_total, n_pad,
+             bn);
+  return 0;
+}
+
+int g_num_sms = 0;
+
+}  // namespace
+
+int conv_pick_bn(int n_pad) {
+  if (n_pad <= 256) return n_pad;
+  for (int bn = 256; bn >= 16; bn -= 16)
+    if (n_pad % bn == 0) return bn;
+  return 16;
+}
+
+}  // namespace gd
+
+extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
+  using namespace gd;
+  GD_REQUIRE(d != nullptr, "gd_conv_igemm: null descriptor");
+  GD_REQUIRE(d->a0 != nullptr && d->wpack != nullptr && d->out != nullptr, "gd_conv_igemm: null tensor pointer");
+  GD_REQUIRE(d->taps == 9 || d->taps == 1, "gd_conv_igemm: taps must be 9 or 1, got %d", d->taps);
+  GD_REQUIRE(d->c0 > 0 && d->c0 % 64 == 0, "gd_conv_igemm: C0 must be a positive multiple of 64, got %d", d->c0);
+  GD_REQUIRE(d->ld0 >= d->c0 && d->ld0 % 8 == 0, "gd_conv_igemm: bad ld0 %d", d->ld0);
+  const int c1 = d->a1 ? d->c1 : 0;
+  GD_REQUIRE(c1 % 64 == 0, "gd_conv_igemm: C1 must be a multiple of 64, got %d", c1);
+  if (d->a1) GD_REQUIRE(d->ld1 >= c1 && d->ld1 % 8 == 0, "gd_conv_igemm: bad ld1 %d", d->ld1);
+  GD_REQUIRE(d->n > 0 && d->h > 0 && d->w > 0, "gd_conv_igemm: bad geometry");
+  const int k_total = d->taps * d->c0 + c1;
+  GD_REQUIRE(d->k_total == k_total, "gd_conv_igemm: k_total %d != taps*C0+C1 = %d", d->k_total, k_total);
+  GD_REQUIRE(d->n_pad % 16 == 0 && d->n_pad >= d->cout && d->cout > 0, "gd_conv_igemm: n_pad %d / cout %d invalid",
+             d->n_pad, d->cout);
+  int bn = d->bn > 0 ? d->bn : conv_pick_bn(d->n_pad);
+  GD_REQUIRE(bn % 16 == 0 && bn >= 16 && bn <= 256 && d->n_pad % bn == 0, "gd_conv_igemm: bad N tile %d for n_pad %d", bn,
+             d->n_pad);
+  GD_REQUIRE(d->out_mode == GD_OUT_NHWC_F16 || d->out_mode == GD_OUT_NCHW_F32, "gd_conv_igemm: bad out_mode");
+  if (d->out_mode == GD_OUT_NHWC_F16)
+    GD_REQUIRE(d->ld_out >= d->cout && (d->ld_out % 8 == 0 || d->cout % 16 != 0), "gd_conv_igemm: bad ld_out %d", d->ld_out);
+  GD_REQUIRE(d->res_mode >= GD_RES_NONE && d->res_mode <= GD_RES_AVGPOOL2, "gd_conv_igemm: bad res_mode");
+  if (d->res_mode != GD_RES_NONE) {
+    GD_REQUIRE(d->res != nullptr && d->ld_res % 8 == 0 && d->cout % 16 == 0,
+               "gd_conv_igemm: residual needs a pointer, ld%%8==0 and cout%%16==0");
+    if (d->res_mode == GD_RES_UPSAMPLE2) GD_REQUIRE(d->h % 2 == 0 && d->w % 2 == 0, "gd_conv_igemm: odd upsample target");
+  }
+
+  // patch shape: BW x BH x BI == 128 pixels
+  int bw = d->w < 16 ? d->w : 16;
+  // round bw down to a power of two so 128 % bw == 0
+  int p2 = 1;
+  while (p2 * 2 <= bw) p2 *= 2;
+  bw = p2;
+  int bh = 128 / bw;
+  if (bh > d->h) {
+    int q = 1;
+    while (q * 2 <= d->h) q *= 2;
+    bh = q;
+  }
+  int bi = 128 / (bw * bh);
+  GD_REQUIRE(bi >= 1 && bi <= 256 && bw * bh * bi == 128, "gd_conv_igemm: cannot tile %dx%d into 128-pixel patches", d->h,
+             d->w);
+
+  ConvArgs p;
+  p.n_img = d->n;
+  p.h = d->h;
+  p.w = d->w;
+  p.bi = bi;
+  p.bh = bh;
+  p.bw = bw;
+  p.patches_x = (d->w + bw - 1) / bw;
+  p.patches_y = (d->h + bh - 1) / bh;
+  p.m_tiles = p.patches_x * p.patches_y * ((d->n + bi - 1) / bi);
+  p.n_tiles = d->n_pad / bn;
+  p.bn = bn;
+  const int stage_bytes = kATileBytes + bn * kBK * 2;
+  int stages = (kSmemBudget - kBarrierBytes - 1024) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  GD_REQUIRE(stages >= 2, "gd_conv_igemm: not enough shared memory for 2 stages");
+  p.stages = stages;
+  p.kb0_per_tap = d->c0 / 64;
+  p.taps = d->taps;
+  p.kb0 = d->taps * p.kb0_per_tap;
+  p.kb_total = p.kb0 + c1 / 64;
+  p.cout = d->cout;
+  p.bias = d->bias;
+  p.res = reinterpret_cast<const __half*>(d->res);
+  p.ld_res = d->ld_res;
+  p.res_mode = d->res_mode;
+  p.out = d->out;
+  p.ld_out = d->ld_out;
+  p.out_mode = d->out_mode;
+  p.out_scale = d->out_scale == 0.0f ? 1.0f : d->out_scale;
+
+  CUtensorMap ma0, ma1, mb;
+  int rc = encode_act_map(&ma0, d->a0, d->c0, d->ld0, d->n, d->h, d->w, bi, bh, bw);
+  if (rc) return rc;
+  if (d->a1) {
+    rc = encode_act_map(&ma1, d->a1, c1, d->ld1, d->n, d->h, d->w, bi, bh, bw);
+    if (rc) return rc;
+  } else {
+    ma1 = ma0;
+  }
+  rc = encode_weight_map(&mb, d->wpack, k_total, d->n_pad, bn);
+  if (rc) return rc;
+
+  if (g_num_sms == 0) {
+    int dev = 0;
+    GD_CHECK_CUDA(cudaGetDevice(&dev));
+    GD_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  // Always request (almost) the full shared memory so exactly one CTA owns an SM and its 512 TMEM columns.
+  const int smem_bytes = kSmemBudget;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    attr_set = true;
+  }
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int grid = total_tiles < g_num_sms ? total_tiles : g_num_sms;
+  conv_igemm_kernel<<<grid, kThreads, smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(ma0, ma1, mb, p);
+  GD_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}

@@ -1,0 +1,450 @@
+// Small fp32 / bandwidth-bound kernels of the sampling step: the fused posterior + noise update, the
+// timestep-embedding MLP pieces, the tiny-C_in first conv, uint8 packing and layout helpers.
+#include "common.cuh"
+#include "../../include/gd_b200.h"
+
+namespace gd {
+void count_launch(int n = 1);
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// Posterior / noise update.  Mirrors the reference op by op in fp32 (each product and sum rounded
+// separately, like the chain of ATen pointwise ops in gaussian_diffusion.py:262-326,356-393,430-438,
+// 575-593), so only expf/sqrtf implementations separate it from the PyTorch result.
+// ---------------------------------------------------------------------------------------------
+struct PostArgs {
+  const float* x;
+  const float* model_out;
+  const float* grad;
+  const float* noise;
+  float* sample;
+  float* pred_xstart;
+  const float* coef;
+  const int32_t* step_idx;
+  int n, c, hw;
+  int var_type, mean_type, clip, ddim;
+  float eta;
+};
+
+__device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+
+__global__ void posterior_kernel(const PostArgs p) {
+  const float* co = p.coef + static_cast<size_t>(*p.step_idx) * GD_COEF_STRIDE;
+  const float sr = co[GD_COEF_SQRT_RECIP_ACP], srm1 = co[GD_COEF_SQRT_RECIPM1_ACP];
+  const float c1 = co[GD_COEF_POST_MEAN1], c2 = co[GD_COEF_POST_MEAN2];
+  const float max_log = co[GD_COEF_LOG_BETA], min_log = co[GD_COEF_POST_LOGVAR];
+  const float acp = co[GD_COEF_ACP], acp_prev = co[GD_COEF_ACP_PREV];
+  const float nonzero = co[GD_COEF_NONZERO];
+  const size_t chw = static_cast<size_t>(p.c) * p.hw;
+  const size_t total = static_cast<size_t>(p.n) * chw;
+  const int out_c = (p.var_type == GD_VAR_FIXED) ? p.c : 2 * p.c;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t b = i / chw, r = i - b * chw;
+    const size_t mo = b * static_cast<size_t>(out_c) * p.hw + r;
+    const float x = p.x[i];
+    const float m_out = p.model_out[mo];
+    float var, logvar;
+    if (p.var_type == GD_VAR_LEARNED_RANGE) {
+      const float v = p.model_out[mo + chw];
+      const float frac = mul(add(v, 1.0f), 0.5f);  // (v + 1) / 2
+      logvar = add(mul(frac, max_log), mul(sub(1.0f, frac), min_log));
+      var = expf(logvar);
+    } else if (p.var_type == GD_VAR_LEARNED) {
+      logvar = p.model_out[mo + chw];
+      var = expf(logvar);
+    } else {
+      var = co[GD_COEF_FIXED_VAR];
+      logvar = co[GD_COEF_FIXED_LOGVAR];
+    }
+    float x0;
+    if (p.mean_type == GD_MEAN_EPSILON) {
+      x0 = sub(mul(sr, x), mul(srm1, m_out));
+    } else {
+      x0 = m_out;
+    }
+    if (p.clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+    float out;
+    if (!p.ddim) {
+      float mean = add(mul(c1, x0), mul(c2, x));
+      if (p.grad != nullptr) mean = add(mean, mul(var, p.grad[i]));
+      const float z = p.noise[i];
+      out = add(mean, mul(mul(nonzero, expf(mul(0.5f, logvar))), z));
+    } else {
+      if (p.grad != nullptr) {
+        float e = __fdiv_rn(sub(mul(sr, x), x0), srm1);
+        e = sub(e, mul(sqrtf(sub(1.0f, acp)), p.grad[i]));
+        x0 = sub(mul(sr, x), mul(srm1, e));
+      }
+      const float e2 = __fdiv_rn(sub(mul(sr, x), x0), srm1);
+      const float sigma = mul(mul(p.eta, sqrtf(__fdiv_rn(sub(1.0f, acp_prev), sub(1.0f, acp)))),
+                              sqrtf(sub(1.0f, __fdiv_rn(acp, acp_prev))));
+      const float mean_pred =
+          add(mul(x0, sqrtf(acp_prev)), mul(sqrtf(sub(sub(1.0f, acp_prev), mul(sigma, sigma))), e2));
+      const float z = p.noise[i];
+      out = add(mean_pred, mul(mul(nonzero, sigma), z));
+    }
+    p.sample[i] = out;
+    if (p.pred_xstart != nullptr) p.pred_xstart[i] = x0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __restrict__ out, int n, int dim) {
+  const int half = dim / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * half) return;
+  const int b = i / half, k = i - b * half;
+  // freqs = exp(-ln(10000) * k / half) computed in fp32 like nn.py:113-116
+  const float freq = expf(__fdiv_rn(__fmul_rn(-9.210340371976184f, static_cast<float>(k)), static_cast<float>(half)));
+  const float arg = __fmul_rn(t[b], freq);
+  out[static_cast<size_t>(b) * dim + k] = cosf(arg);
+  out[static_cast<size_t>(b) * dim + half + k] = sinf(arg);
+  if ((dim & 1) && k == 0) out[static_cast<size_t>(b) * dim + dim - 1] = 0.f;
+}
+
+// y[m][n] = act_out( sum_k act_in(x[m][k]) W[n][k] + b[n] + add[m][n] ); one warp per output column,
+// rows processed in blocks of 8 so each weight row is streamed once per row block (weights dominate).
+template <bool kSiluIn>
+__global__ void linear_f32_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w,
+                                  const float* __restrict__ b, const float* __restrict__ addp, int ld_add,
+                                  float* __restrict__ y, int ldy, int m, int k, int n, int silu_out) {
+  const int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (col >= n) return;
+  const float* wr = w + static_cast<size_t>(col) * k;
+  for (int m0 = 0; m0 < m; m0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+    for (int kk = lane; kk < k; kk += 32) {
+      const float wv = __ldg(wr + kk);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        if (m0 + r < m) {
+          float xv = x[static_cast<size_t>(m0 + r) * ldx + kk];
+          if (kSiluIn) xv = xv / (1.0f + expf(-xv));
+          acc[r] = fmaf(xv, wv, acc[r]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc[r] = warp_sum(acc[r]);
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        if (m0 + r < m) {
+          float v = acc[r] + (b ? b[col] : 0.f);
+          if (addp) v += addp[static_cast<size_t>(m0 + r) * ld_add + col];
+          if (silu_out) v = v / (1.0f + expf(-v));
+          y[static_cast<size_t>(m0 + r) * ldy + col] = v;
+        }
+      }
+    }
+  }
+}
+
+__global__ void embedding_gather_kernel(const float* __restrict__ table, const int64_t* __restrict__ idx,
+                                        float* __restrict__ out, int n, int dim, int num_rows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * dim) return;
+  const int b = i / dim, j = i - b * dim;
+  long long r = idx[b];
+  if (r < 0) r = 0;
+  if (r >= num_rows) r = num_rows - 1;
+  out[i] = table[static_cast<size_t>(r) * dim + j];
+}
+
+// ---------------------------------------------------------------------------------------------
+// First conv: fp32 NCHW input with 3 or 6 channels -> fp16 NHWC.  CUDA-core direct conv (K = 27/54
+// is too thin for a tensor-core tile and is <0.1 % of the FLOPs).
+// ---------------------------------------------------------------------------------------------
+__global__ void conv3x3_small_cin_kernel(const float* __restrict__ x, const float* __restrict__ wgt,
+                                         const float* __restrict__ bias, __half* __restrict__ out, int ld_out, int n,
+                                         int cin, int h, int w, int cout, int c8, int rep) {
+  extern __shared__ float s_w[];  // [cin*9][cout]
+  const int kdim = cin * 9;
+  for (int i = threadIdx.x; i < kdim * cout; i += blockDim.x) {
+    const int co = i % cout, kk = i / cout;
+    s_w[i] = wgt[static_cast<size_t>(co) * kdim + kk];
+  }
+  __syncthreads();
+  const int cch = threadIdx.x % c8, pl = threadIdx.x / c8;
+  float bsum[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bsum[j] = bias ? bias[cch * 8 + j] : 0.f;
+  const size_t hw = static_cast<size_t>(h) * w;
+  const size_t total = static_cast<size_t>(n) * hw;
+  for (size_t p = static_cast<size_t>(blockIdx.x) * rep + pl; p < total; p += static_cast<size_t>(gridDim.x) * rep) {
+    const int img = static_cast<int>(p / hw);
+    const int rem = static_cast<int>(p - static_cast<size_t>(img) * hw);
+    const int y = rem / w, xx = rem - y * w;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = bsum[j];
+    for (int ci = 0; ci < cin; ++ci) {
+      const float* xp = x + (static_cast<size_t>(img) * cin + ci) * hw;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int yy = y + ky - 1;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int xc = xx + kx - 1;
+          float v = 0.f;
+          if (yy >= 0 && yy < h && xc >= 0 && xc < w) v = __ldg(xp + static_cast<size_t>(yy) * w + xc);
+          // the reference casts the input to fp16 before the conv (unet.py:655)
+          v = __half2float(__float2half_rn(v));
+          const float* wr = s_w + (ci * 9 + ky * 3 + kx) * cout + cch * 8;
+          const float4 w0 = *reinterpret_cast<const float4*>(wr);
+          const float4 w1 = *reinterpret_cast<const float4*>(wr + 4);
+          acc[0] = fmaf(v, w0.x, acc[0]);
+          acc[1] = fmaf(v, w0.y, acc[1]);
+          acc[2] = fmaf(v, w0.z, acc[2]);
+          acc[3] = fmaf(v, w0.w, acc[3]);
+          acc[4] = fmaf(v, w1.x, acc[4]);
+          acc[5] = fmaf(v, w1.y, acc[5]);
+          acc[6] = fmaf(v, w1.z, acc[6]);
+          acc[7] = fmaf(v, w1.w, acc[7]);
+        }
+      }
+    }
+    st_half8(out + p * ld_out + cch * 8, float_to_half8(acc));
+  }
+}
+
+__global__ void to_uint8_nhwc_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, int n, int c, int h, int w) {
+  const size_t hw = static_cast<size_t>(h) * w;
+  const size_t total = static_cast<size_t>(n) * c * hw;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    // i indexes the OUTPUT (NHWC) so the stores are coalesced
+    const size_t pix = i / c;
+    const int ch = static_cast<int>(i - pix * c);
+    const size_t b = pix / hw, r = pix - b * hw;
+    float v = __fmul_rn(__fadd_rn(x[(b * c + ch) * hw + r], 1.0f), 127.5f);
+    v = fminf(fmaxf(v, 0.0f), 255.0f);
+    out[i] = static_cast<uint8_t>(v);  // truncation, like .to(th.uint8)
+  }
+}
+
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __half* __restrict__ out, int ld_out, int n, int c,
+                                    int hw) {
+  const size_t total = static_cast<size_t>(n) * hw * c;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t pix = i / c;
+    const int ch = static_cast<int>(i - pix * c);
+    const size_t b = pix / hw, r = pix - b * hw;
+    out[pix * ld_out + ch] = __float2half_rn(x[(b * c + ch) * hw + r]);
+  }
+}
+__global__ void nhwc_to_nchw_kernel(const __half* __restrict__ x, int ld, float* __restrict__ out, int n, int c, int hw) {
+  const size_t total = static_cast<size_t>(n) * hw * c;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    // i indexes the OUTPUT (NCHW)
+    const size_t r = i % hw;
+    const size_t bc = i / hw;
+    const int ch = static_cast<int>(bc % c);
+    const size_t b = bc / c;
+    out[i] = __half2float(x[(b * hw + r) * ld + ch]);
+  }
+}
+
+// F.interpolate(mode="bilinear", align_corners=False) as used by SuperResModel.forward (unet.py:679)
+__global__ void bilinear_kernel(const float* __restrict__ x, float* __restrict__ out, int n, int c, int hi, int wi,
+                                int ho, int wo, int out_c_total, int out_c_offset) {
+  const size_t total = static_cast<size_t>(n) * c * ho * wo;
+  const float sy = static_cast<float>(hi) / static_cast<float>(ho);
+  const float sx = static_cast<float>(wi) / static_cast<float>(wo);
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int ox = static_cast<int>(i % wo);
+    const int oy = static_cast<int>((i / wo) % ho);
+    const int ch = static_cast<int>((i / (static_cast<size_t>(wo) * ho)) % c);
+    const int b = static_cast<int>(i / (static_cast<size_t>(wo) * ho * c));
+    float fy = (oy + 0.5f) * sy - 0.5f;
+    float fx = (ox + 0.5f) * sx - 0.5f;
+    if (fy < 0.f) fy = 0.f;
+    if (fx < 0.f) fx = 0.f;
+    int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+    const int y1 = y0 + (y0 < hi - 1 ? 1 : 0), x1 = x0 + (x0 < wi - 1 ? 1 : 0);
+    const float ly = fy - y0, lx = fx - x0;
+    const float* xp = x + (static_cast<size_t>(b) * c + ch) * hi * wi;
+    const float v = (1.f - ly) * ((1.f - lx) * xp[y0 * wi + x0] + lx * xp[y0 * wi + x1]) +
+                    ly * ((1.f - lx) * xp[y1 * wi + x0] + lx * xp[y1 * wi + x1]);
+    out[((static_cast<size_t>(b) * out_c_total + out_c_offset + ch) * ho + oy) * wo + ox] = v;
+  }
+}
+
+// dlogits = scale * (onehot(y) - softmax(logits)); one warp per row
+__global__ void logsoftmax_select_bwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__ y,
+                                             float* __restrict__ dlogits, int n, int classes, float scale) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float* l = logits + static_cast<size_t>(row) * classes;
+  float mx = -INFINITY;
+  for (int j = lane; j < classes; j += 32) mx = fmaxf(mx, l[j]);
+  mx = warp_max(mx);
+  float s = 0.f;
+  for (int j = lane; j < classes; j += 32) s += expf(l[j] - mx);
+  s = warp_sum(s);
+  const float inv = 1.0f / s;
+  const long long yy = y[row];
+  for (int j = lane; j < classes; j += 32) {
+    const float pr = expf(l[j] - mx) * inv;
+    dlogits[static_cast<size_t>(row) * classes + j] = scale * ((j == yy ? 1.0f : 0.0f) - pr);
+  }
+}
+
+inline int grid_for(size_t total, int block, int cap = 148 * 16) {
+  size_t g = (total + block - 1) / block;
+  if (g > static_cast<size_t>(cap)) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+}  // namespace
+}  // namespace gd
+
+using namespace gd;
+
+extern "C" int gd_posterior_step(const gd_posterior_desc* d, void* stream) {
+  GD_REQUIRE(d != nullptr, "gd_posterior_step: null descriptor");
+  GD_REQUIRE(d->x && d->model_out && d->noise && d->sample && d->coef && d->step_idx, "gd_posterior_step: null pointer");
+  GD_REQUIRE(d->n > 0 && d->c > 0 && d->hw > 0, "gd_posterior_step: bad shape");
+  GD_REQUIRE(d->var_type >= GD_VAR_LEARNED_RANGE && d->var_type <= GD_VAR_LEARNED, "gd_posterior_step: bad var_type");
+  GD_REQUIRE(d->mean_type == GD_MEAN_EPSILON || d->mean_type == GD_MEAN_START_X,
+             "gd_posterior_step: model_mean_type PREVIOUS_X is not on the sampling path built here");
+  PostArgs p;
+  p.x = d->x; p.model_out = d->model_out; p.grad = d->grad; p.noise = d->noise;
+  p.sample = d->sample; p.pred_xstart = d->pred_xstart; p.coef = d->coef; p.step_idx = d->step_idx;
+  p.n = d->n; p.c = d->c; p.hw = d->hw;
+  p.var_type = d->var_type; p.mean_type = d->mean_type; p.clip = d->clip_denoised; p.ddim = d->ddim; p.eta = d->eta;
+  const size_t total = static_cast<size_t>(d->n) * d->c * d->hw;
+  posterior_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  GD_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
+
+extern "C" int gd_timestep_embedding(const float* t, float* out, int32_t n, int32_t dim, void* stream) {
+  GD_REQUIRE(t && out && n > 0 && dim >= 2, "gd_timestep_embedding: bad arguments");
+  const int total = n * (dim / 2);
+  timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(t, out, n, dim);
+  GD_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
+
+extern "C" int gd_linear_f32(const float* x, int32_t ldx, const float* w, const float* b, const float* add,
+                             int32_t ld_add, float* y, int32_t ldy, int32_t m, int32_t k, int32_t n, int32_t silu_in,
+                             int32_t silu_out, void* stream) {
+  GD_REQUIRE(x && w && y && m > 0 && k > 0 && n > 0, "gd_linear_f32: bad arguments");
+  GD_REQUIRE(ldx >= k && ldy >= n, "gd_linear_f32: bad leading dimensions");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int warps = 8;
+  const int grid = (n + warps - 1) / warps;
+  if (silu_in)
+    linear_f32_kernel<true><<<grid, warps * 32, 0, st>>>(x, ldx, w, b, add, ld_add, y, ldy, m, k, n, silu_out);
+  else
+    linear_f32_kernel<false><<<grid, warps * 32, 0, st>>>(x, ldx, w, b, add, ld_add, y, ldy, m, k, n, silu_out);
+  GD_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
+
+extern "C" int gd_embedding_gather(const float* table, const int64_t* idx, float* out, int32_t n, int32_t dim,
+                                   int32_t num_rows, void* stream) {
+  GD_REQUIRE(table && idx && out && n > 0 && dim > 0 && num_rows > 0, "gd_embedding_gather: bad arguments");
+  const int total = n * dim;
+  embedding_gather_kernel<<<(total + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(table, idx, out, n,
+                                                                                                 dim, num_rows);
+  GD_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
+
+extern "C" int gd_conv3x3_small_cin(const float* x, const float* w, const float* bias, void* out, int32_t ld_out,
+                                    int32_t n, int32_t cin, int32_t h, int32_t w_, int32_t cout, void* stream) {
+  GD_REQUIRE(x && w && out, "gd_conv3x3_small_cin: null pointer");
+  GD_REQUIRE(cin >= 1 && cin <= 8, "gd_conv3x3_small_cin: cin must be <= 8, got %d", cin);
+  GD_REQUIRE(cout % 8 == 0 && cout <= 1024 && ld_out % 8 == 0 && ld_out >= cout, "gd_conv3x3_small_cin: bad cout/ld_out");
+  const int c8 = cout / 8;
+  int rep = 256 / c8;
+  if (rep < 1) rep = 1;
+  const int threads = c8 * rep;
+  const size_t smem = static_cast<size_t>(cin) * 9 * cout * sizeof(float);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    GD_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_small_cin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+    smem_set = smem;
+  }
+  const size_t total_px = static_cast<size_t>(n) * h * w_;
+  size_t grid = (total_px + rep * 8 - 1) / (rep * 8);
+  if (grid > 148 * 8) grid = 148 * 8;
+  if (grid < 1) grid = 1;
+  conv3x3_small_cin_kernel<<<static_cast<int>(grid), threads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, w, bias, reinterpret_cast<__half*>(out), ld_out, n, cin, h, w_, cout, c8, rep);
+  GD_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
+
+extern "C" int gd_to_uint8_nhwc(const float* x, uint8_t* out, int32_t n, int32_t c, int32_t h, int32_t w, void* stream) {
+  GD_REQUIRE(x && out && n > 0 && c > 0 && h > 0 && w > 0, "gd_to_uint8_nhwc: bad arguments");
+  const size_t total = static_cast<size_t>(n) * c * h * w;
+  to_uint8_nhwc_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, out, n, c, h, w);
+  GD_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
+
+extern "C" int gd_nchw_f32_to_nhwc_f16(const float* x, void* out, int32_t ld_out, int32_t n, int32_t c, int32_t h,
+                                       int32_t w, void* stream) {
+  GD_REQUIRE(x && out && ld_out >= c, "gd_nchw_f32_to_nhwc_f16: bad arguments");
+  const size_t total = static_cast<size_t>(n) * c * h * w;
+  nchw_to_nhwc_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, reinterpret_cast<__half*>(out), ld_out, n, c, h * w);
+  GD_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
+
+extern "C" int gd_nhwc_f16_to_nchw_f32(const void* x, int32_t ld, float* out, int32_t n, int32_t c, int32_t h, int32_t w,
+                                       void* stream) {
+  GD_REQUIRE(x && out && ld >= c, "gd_nhwc_f16_to_nchw_f32: bad arguments");
+  const size_t total = static_cast<size_t>(n) * c * h * w;
+  nhwc_to_nchw_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half*>(x), ld, out, n, c, h * w);
+  GD_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
+
+extern "C" int gd_bilinear_upsample_nchw(const float* x, float* out, int32_t n, int32_t c, int32_t h_in, int32_t w_in,
+                                         int32_t h_out, int32_t w_out, int32_t out_c_total, int32_t out_c_offset,
+                                         void* stream) {
+  GD_REQUIRE(x && out && n > 0 && c > 0 && out_c_offset + c <= out_c_total, "gd_bilinear_upsample_nchw: bad arguments");
+  const size_t total = static_cast<size_t>(n) * c * h_out * w_out;
+  bilinear_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, out, n, c, h_in, w_in, h_out, w_out, out_c_total, out_c_offset);
+  GD_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
+
+extern "C" int gd_logsoftmax_select_bwd(const float* logits, const int64_t* y, float* dlogits, int32_t n,
+                                        int32_t classes, float scale, void* stream) {
+  GD_REQUIRE(logits && y && dlogits && n > 0 && classes > 0, "gd_logsoftmax_select_bwd: bad arguments");
+  const int warps = 4;
+  logsoftmax_select_bwd_kernel<<<(n + warps - 1) / warps, warps * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      logits, y, dlogits, n, classes, scale);
+  GD_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}

@@ -1,0 +1,508 @@
+// GroupNorm32 (32 groups, biased variance, fp32 math on fp16 NHWC storage) fused with SiLU, FiLM
+// scale/shift and the 2x avg-pool / nearest-upsample of up/down ResBlocks, plus its data-gradient.
+//
+// Reference call sites: nn.py:17-19,93-100 (GroupNorm32), unet.py:184,208 (SiLU), unet.py:248-252 (FiLM:
+// out_norm(h)*(1+scale)+shift, scale = first half of emb_out), unet.py:191-195,237-242 (h_upd),
+// unet.py:285,302 (attention norm, no activation), unet.py:614-615 (out head).
+//
+// Bandwidth-bound: every kernel streams 16-byte (8 x fp16) vectors with the channel chunk fixed per thread
+// (blockDim is a multiple of C/8) so per-channel affine terms live in registers; the statistics pass
+// reduces per-CTA partials deterministically (no float atomics in global memory).
+#include "common.cuh"
+#include "../../include/gd_b200.h"
+
+namespace gd {
+void count_launch(int n = 1);
+namespace {
+
+constexpr int kGroups = 32;
+constexpr int kMaxChunks = 128;
+
+struct Geo {
+  int c8;        // C / 8
+  int rep;       // pixel lanes per CTA
+  int threads;   // c8 * rep
+  int chunks;    // CTAs per image
+  int px_per_chunk;
+};
+
+Geo make_geo(int c, int hw) {
+  Geo g;
+  g.c8 = c / 8;
+  g.rep = 256 / g.c8;
+  if (g.rep < 1) g.rep = 1;
+  g.threads = g.c8 * g.rep;
+  int chunks = (hw + g.rep * 16 - 1) / (g.rep * 16);
+  if (chunks > kMaxChunks) chunks = kMaxChunks;
+  if (chunks < 1) chunks = 1;
+  g.px_per_chunk = (hw + chunks - 1) / chunks;
+  g.chunks = (hw + g.px_per_chunk - 1) / g.px_per_chunk;
+  return g;
+}
+
+// Reduce this thread's 8 per-channel values into per-group shared accumulators.
+__device__ __forceinline__ void group_accumulate(float* s_acc, const float (&v)[8], int ch0, int cpg) {
+  int g = ch0 / cpg;
+  float run = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int gj = (ch0 + j) / cpg;
+    if (gj != g) {
+      atomicAdd(&s_acc[g], run);
+      run = 0.f;
+      g = gj;
+    }
+    run += v[j];
+  }
+  atomicAdd(&s_acc[g], run);
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward statistics: partial[n][chunk][32][2] = (sum x, sum x^2) over this CTA's pixels
+// ---------------------------------------------------------------------------------------------
+__global__ void gn_stats_kernel(const __half* __restrict__ x, int ld, int hw, int c, int c8, int rep, int px_per_chunk,
+                                float* __restrict__ partial) {
+  __shared__ float s_acc[2 * kGroups];
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  if (threadIdx.x < 2 * kGroups) s_acc[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int cch = threadIdx.x % c8, pl = threadIdx.x / c8;
+  const int p0 = chunk * px_per_chunk;
+  const int p1 = min(hw, p0 + px_per_chunk);
+  const __half* base = x + static_cast<size_t>(n) * hw * ld + cch * 8;
+  float s[8], ss[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
+  int p = p0 + pl;
+  // 4 independent 16-byte loads in flight per thread
+  for (; p + 3 * rep < p1; p += 4 * rep) {
+    Half8 v0 = ld_half8(base + static_cast<size_t>(p) * ld);
+    Half8 v1 = ld_half8(base + static_cast<size_t>(p + rep) * ld);
+    Half8 v2 = ld_half8(base + static_cast<size_t>(p + 2 * rep) * ld);
+    Half8 v3 = ld_half8(base + static_cast<size_t>(p + 3 * rep) * ld);
+    float f[8];
+    half8_to_float(v0, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] += f[j] * f[j]; }
+    half8_to_float(v1, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] += f[j] * f[j]; }
+    half8_to_float(v2, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] += f[j] * f[j]; }
+    half8_to_float(v3, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] += f[j] * f[j]; }
+  }
+  for (; p < p1; p += rep) {
+    float f[8];
+    half8_to_float(ld_half8(base + static_cast<size_t>(p) * ld), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] += f[j] * f[j]; }
+  }
+  const int cpg = c / kGroups;
+  group_accumulate(s_acc, s, cch * 8, cpg);
+  group_accumulate(s_acc + kGroups, ss, cch * 8, cpg);
+  __syncthreads();
+  if (threadIdx.x < kGroups) {
+    float* o = partial + ((static_cast<size_t>(n) * gridDim.x + chunk) * kGroups + threadIdx.x) * 2;
+    o[0] = s_acc[threadIdx.x];
+    o[1] = s_acc[kGroups + threadIdx.x];
+  }
+}
+
+// mode 0: (mean, rstd); mode 1: (sum0/count, sum1/count)
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, int chunks, float inv_count, float eps, int mode,
+                                   float* __restrict__ out) {
+  const int n = blockIdx.x, g = threadIdx.x;
+  double a = 0.0, b = 0.0;
+  for (int k = 0; k < chunks; ++k) {
+    const float* pp = partial + ((static_cast<size_t>(n) * chunks + k) * kGroups + g) * 2;
+    a += pp[0];
+    b += pp[1];
+  }
+  a *= inv_count;
+  b *= inv_count;
+  float* o = out + (static_cast<size_t>(n) * kGroups + g) * 2;
+  if (mode == 0) {
+    double var = b - a * a;
+    if (var < 0.0) var = 0.0;
+    o[0] = static_cast<float>(a);
+    o[1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  } else {
+    o[0] = static_cast<float>(a);
+    o[1] = static_cast<float>(b);
+  }
+}
+
+// per-thread affine: y = x * a + b for the thread's 8 channels
+__device__ __forceinline__ void load_affine(const float* mean_rstd, const float* gamma, const float* beta,
+                                            const float* film, int film_ld, int n, int c, int ch0, float (&a)[8],
+                                            float (&b)[8]) {
+  const int cpg = c / kGroups;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = ch0 + j;
+    const int g = ch / cpg;
+    const float mean = mean_rstd[(static_cast<size_t>(n) * kGroups + g) * 2];
+    const float rstd = mean_rstd[(static_cast<size_t>(n) * kGroups + g) * 2 + 1];
+    float ga = gamma[ch], be = beta[ch];
+    float aa = rstd * ga;
+    float bb = be - mean * aa;
+    if (film != nullptr) {
+      const float sc = 1.0f + film[static_cast<size_t>(n) * film_ld + ch];
+      const float sh = film[static_cast<size_t>(n) * film_ld + c + ch];
+      aa *= sc;
+      bb = bb * sc + sh;
+    }
+    a[j] = aa;
+    b[j] = bb;
+  }
+}
+
+template <bool kSilu>
+__device__ __forceinline__ void norm_act(const Half8& v, const float (&a)[8], const float (&b)[8], float (&o)[8]) {
+  float f[8];
+  half8_to_float(v, f);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float z = fmaf(f[j], a[j], b[j]);
+    o[j] = kSilu ? silu_f(z) : z;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward apply.  Iterates over INPUT pixels for SAME / UPSAMPLE2 and over OUTPUT pixels for AVGPOOL2.
+// ---------------------------------------------------------------------------------------------
+template <bool kSilu, int kMode>
+__global__ void gn_apply_kernel(const __half* __restrict__ x, int ld, const float* __restrict__ mean_rstd,
+                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                const float* __restrict__ film, int film_ld, __half* __restrict__ out, int ld_out, int h,
+                                int w, int c, int c8, int rep, int px_per_chunk) {
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int cch = threadIdx.x % c8, pl = threadIdx.x / c8;
+  float a[8], b[8];
+  load_affine(mean_rstd, gamma, beta, film, film_ld, n, c, cch * 8, a, b);
+  const int hw_in = h * w;
+  const __half* xin = x + static_cast<size_t>(n) * hw_in * ld + cch * 8;
+  if (kMode == GD_GN_SAME) {
+    __half* o = out + static_cast<size_t>(n) * hw_in * ld_out + cch * 8;
+    const int p0 = chunk * px_per_chunk, p1 = min(hw_in, p0 + px_per_chunk);
+    int p = p0 + pl;
+    for (; p + 3 * rep < p1; p += 4 * rep) {
+      Half8 v0 = ld_half8(xin + static_cast<size_t>(p) * ld);
+      Half8 v1 = ld_half8(xin + static_cast<size_t>(p + rep) * ld);
+      Half8 v2 = ld_half8(xin + static_cast<size_t>(p + 2 * rep) * ld);
+      Half8 v3 = ld_half8(xin + static_cast<size_t>(p + 3 * rep) * ld);
+      float r[8];
+      norm_act<kSilu>(v0, a, b, r);
+      st_half8(o + static_cast<size_t>(p) * ld_out, float_to_half8(r));
+      norm_act<kSilu>(v1, a, b, r);
+      st_half8(o + static_cast<size_t>(p + rep) * ld_out, float_to_half8(r));
+      norm_act<kSilu>(v2, a, b, r);
+      st_half8(o + static_cast<size_t>(p + 2 * rep) * ld_out, float_to_half8(r));
+      norm_act<kSilu>(v3, a, b, r);
+      st_half8(o + static_cast<size_t>(p + 3 * rep) * ld_out, float_to_half8(r));
+    }
+    for (; p < p1; p += rep) {
+      float r[8];
+      norm_act<kSilu>(ld_half8(xin + static_cast<size_t>(p) * ld), a, b, r);
+      st_half8(o + static_cast<size_t>(p) * ld_out, float_to_half8(r));
+    }
+  } else if (kMode == GD_GN_AVGPOOL2) {
+    const int ho = h / 2, wo = w / 2, hw_out = ho * wo;
+    __half* o = out + static_cast<size_t>(n) * hw_out * ld_out + cch * 8;
+    const int p0 = chunk * px_per_chunk, p1 = min(hw_out, p0 + px_per_chunk);
+    for (int p = p0 + pl; p < p1; p += rep) {
+      const int oy = p / wo, ox = p - oy * wo;
+      const size_t i00 = static_cast<size_t>(2 * oy) * w + 2 * ox;
+      Half8 v0 = ld_half8(xin + i00 * ld);
+      Half8 v1 = ld_half8(xin + (i00 + 1) * ld);
+      Half8 v2 = ld_half8(xin + (i00 + w) * ld);
+      Half8 v3 = ld_half8(xin + (i00 + w + 1) * ld);
+      float r[8], acc[8];
+      norm_act<kSilu>(v0, a, b, acc);
+      norm_act<kSilu>(v1, a, b, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += r[j];
+      norm_act<kSilu>(v2, a, b, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += r[j];
+      norm_act<kSilu>(v3, a, b, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = (acc[j] + r[j]) * 0.25f;
+      st_half8(o + static_cast<size_t>(p) * ld_out, float_to_half8(acc));
+    }
+  } else {  // GD_GN_UPSAMPLE2
+    const int wo = w * 2;
+    __half* o = out + static_cast<size_t>(n) * hw_in * 4 * ld_out + cch * 8;
+    const int p0 = chunk * px_per_chunk, p1 = min(hw_in, p0 + px_per_chunk);
+    for (int p = p0 + pl; p < p1; p += rep) {
+      const int iy = p / w, ix = p - iy * w;
+      float r[8];
+      norm_act<kSilu>(ld_half8(xin + static_cast<size_t>(p) * ld), a, b, r);
+      const Half8 hv = float_to_half8(r);
+      const size_t o00 = static_cast<size_t>(2 * iy) * wo + 2 * ix;
+      st_half8(o + o00 * ld_out, hv);
+      st_half8(o + (o00 + 1) * ld_out, hv);
+      st_half8(o + (o00 + wo) * ld_out, hv);
+      st_half8(o + (o00 + wo + 1) * ld_out, hv);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward.  With xh = (x-mean)*rstd, z = xh*g' + b', y = act(z), g' = gamma*(1+scale):
+//   dz = dy_in * act'(z);  dxh = dz * g';  dx = rstd * (dxh - mean_g(dxh) - xh * mean_g(dxh*xh))
+// dy_in is dy pulled back through the spatial op (avg-pool: dy/4 at the parent; upsample: sum of 4).
+// ---------------------------------------------------------------------------------------------
+template <int kMode>
+__device__ __forceinline__ void load_dy(const __half* dy, int ld_dy, int n, int h, int w, int p, int ch0, float (&d)[8]) {
+  if (kMode == GD_GN_SAME) {
+    half8_to_float(ld_half8(dy + (static_cast<size_t>(n) * h * w + p) * ld_dy + ch0), d);
+  } else if (kMode == GD_GN_AVGPOOL2) {
+    const int iy = p / w, ix = p - iy * w;
+    const int wo = w / 2;
+    const size_t q = static_cast<size_t>(n) * (h / 2) * wo + static_cast<size_t>(iy / 2) * wo + ix / 2;
+    half8_to_float(ld_half8(dy + q * ld_dy + ch0), d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d[j] *= 0.25f;
+  } else {
+    const int iy = p / w, ix = p - iy * w;
+    const int wo = w * 2;
+    const size_t q = static_cast<size_t>(n) * h * 2 * wo + static_cast<size_t>(2 * iy) * wo + 2 * ix;
+    float t[8];
+    half8_to_float(ld_half8(dy + q * ld_dy + ch0), d);
+    half8_to_float(ld_half8(dy + (q + 1) * ld_dy + ch0), t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d[j] += t[j];
+    half8_to_float(ld_half8(dy + (q + wo) * ld_dy + ch0), t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d[j] += t[j];
+    half8_to_float(ld_half8(dy + (q + wo + 1) * ld_dy + ch0), t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d[j] += t[j];
+  }
+}
+
+template <bool kSilu>
+__device__ __forceinline__ float act_grad(float z) {
+  if (!kSilu) return 1.0f;
+  const float s = 1.0f / (1.0f + __expf(-z));
+  return s * (1.0f + z * (1.0f - s));
+}
+
+// xa/xb: xh = x*xa + xb (normalised value); ga: g'; z = xh*ga + bz
+struct BwdAffine {
+  float xa[8], xb[8], ga[8], bz[8];
+};
+__device__ __forceinline__ void load_bwd_affine(const float* mean_rstd, const float* gamma, const float* beta,
+                                                const float* film, int film_ld, int n, int c, int ch0, BwdAffine& A) {
+  const int cpg = c / kGroups;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = ch0 + j;
+    const int g = ch / cpg;
+    const float mean = mean_rstd[(static_cast<size_t>(n) * kGroups + g) * 2];
+    const float rstd = mean_rstd[(static_cast<size_t>(n) * kGroups + g) * 2 + 1];
+    A.xa[j] = rstd;
+    A.xb[j] = -mean * rstd;
+    float ga = gamma[ch], be = beta[ch];
+    if (film != nullptr) {
+      const float sc = 1.0f + film[static_cast<size_t>(n) * film_ld + ch];
+      const float sh = film[static_cast<size_t>(n) * film_ld + c + ch];
+      ga *= sc;
+      be = be * sc + sh;
+    }
+    A.ga[j] = ga;
+    A.bz[j] = be;
+  }
+}
+
+template <bool kSilu, int kMode>
+__global__ void gn_bwd_stats_kernel(const __half* __restrict__ x, int ld, const float* __restrict__ mean_rstd,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    const float* __restrict__ film, int film_ld, const __half* __restrict__ dy, int ld_dy,
+                                    int h, int w, int c, int c8, int rep, int px_per_chunk,
+                                    float* __restrict__ partial) {
+  __shared__ float s_acc[2 * kGroups];
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  if (threadIdx.x < 2 * kGroups) s_acc[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int cch = threadIdx.x % c8, pl = threadIdx.x / c8;
+  BwdAffine A;
+  load_bwd_affine(mean_rstd, gamma, beta, film, film_ld, n, c, cch * 8, A);
+  const int hw = h * w;
+  const __half* xin = x + static_cast<size_t>(n) * hw * ld + cch * 8;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  const int p0 = chunk * px_per_chunk, p1 = min(hw, p0 + px_per_chunk);
+  for (int p = p0 + pl; p < p1; p += rep) {
+    float xf[8], d[8];
+    half8_to_float(ld_half8(xin + static_cast<size_t>(p) * ld), xf);
+    load_dy<kMode>(dy, ld_dy, n, h, w, p, cch * 8, d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = fmaf(xf[j], A.xa[j], A.xb[j]);
+      const float z = fmaf(xh, A.ga[j], A.bz[j]);
+      const float dxh = d[j] * act_grad<kSilu>(z) * A.ga[j];
+      s1[j] += dxh;
+      s2[j] += dxh * xh;
+    }
+  }
+  const int cpg = c / kGroups;
+  group_accumulate(s_acc, s1, cch * 8, cpg);
+  group_accumulate(s_acc + kGroups, s2, cch * 8, cpg);
+  __syncthreads();
+  if (threadIdx.x < kGroups) {
+    float* o = partial + ((static_cast<size_t>(n) * gridDim.x + chunk) * kGroups + threadIdx.x) * 2;
+    o[0] = s_acc[threadIdx.x];
+    o[1] = s_acc[kGroups + threadIdx.x];
+  }
+}
+
+template <bool kSilu, int kMode>
+__global__ void gn_bwd_apply_kernel(const __half* __restrict__ x, int ld, const float* __restrict__ mean_rstd,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    const float* __restrict__ film, int film_ld, const __half* __restrict__ dy, int ld_dy,
+                                    const float* __restrict__ gsum, const __half* __restrict__ add, int ld_add,
+                                    __half* __restrict__ dx, int ld_dx, int h, int w, int c, int c8, int rep,
+                                    int px_per_chunk) {
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int cch = threadIdx.x % c8, pl = threadIdx.x / c8;
+  BwdAffine A;
+  load_bwd_affine(mean_rstd, gamma, beta, film, film_ld, n, c, cch * 8, A);
+  const int cpg = c / kGroups;
+  float m1[8], m2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (cch * 8 + j) / cpg;
+    m1[j] = gsum[(static_cast<size_t>(n) * kGroups + g) * 2];
+    m2[j] = gsum[(static_cast<size_t>(n) * kGroups + g) * 2 + 1];
+  }
+  const int hw = h * w;
+  const __half* xin = x + static_cast<size_t>(n) * hw * ld + cch * 8;
+  const int p0 = chunk * px_per_chunk, p1 = min(hw, p0 + px_per_chunk);
+  for (int p = p0 + pl; p < p1; p += rep) {
+    float xf[8], d[8], r[8];
+    half8_to_float(ld_half8(xin + static_cast<size_t>(p) * ld), xf);
+    load_dy<kMode>(dy, ld_dy, n, h, w, p, cch * 8, d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = fmaf(xf[j], A.xa[j], A.xb[j]);
+      const float z = fmaf(xh, A.ga[j], A.bz[j]);
+      const float dxh = d[j] * act_grad<kSilu>(z) * A.ga[j];
+      r[j] = A.xa[j] * (dxh - m1[j] - xh * m2[j]);
+    }
+    const size_t off = (static_cast<size_t>(n) * hw + p);
+    if (add != nullptr) {
+      float t[8];
+      half8_to_float(ld_half8(add + off * ld_add + cch * 8), t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] += t[j];
+    }
+    st_half8(dx + off * ld_dx + cch * 8, float_to_half8(r));
+  }
+}
+
+}  // namespace
+}  // namespace gd
+
+using namespace gd;
+
+extern "C" int64_t gd_groupnorm_ws_floats(int32_t n, int32_t hw, int32_t c) {
+  (void)hw;
+  (void)c;
+  return static_cast<int64_t>(n) * (kMaxChunks + 1) * kGroups * 2;
+}
+
+static int check_gn_common(const char* who, const void* x, int ld, int n, int hw, int c) {
+  GD_REQUIRE(x != nullptr, "%s: null input", who);
+  GD_REQUIRE(n > 0 && hw > 0, "%s: bad n/hw", who);
+  GD_REQUIRE(c > 0 && c % 32 == 0 && c <= 8192, "%s: channels must be a multiple of 32 (GroupNorm32), got %d", who, c);
+  GD_REQUIRE(ld >= c && ld % 8 == 0, "%s: bad ld %d for c %d", who, ld, c);
+  return 0;
+}
+
+extern "C" int gd_groupnorm_stats(const void* x, int32_t ld, int32_t n, int32_t hw, int32_t c, float eps,
+                                  float* partial_ws, float* mean_rstd, void* stream) {
+  if (int rc = check_gn_common("gd_groupnorm_stats", x, ld, n, hw, c)) return rc;
+  GD_REQUIRE(partial_ws != nullptr && mean_rstd != nullptr, "gd_groupnorm_stats: null workspace/output");
+  const Geo g = make_geo(c, hw);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  gn_stats_kernel<<<dim3(g.chunks, n), g.threads, 0, st>>>(reinterpret_cast<const __half*>(x), ld, hw, c, g.c8, g.rep,
+                                                          g.px_per_chunk, partial_ws);
+  GD_CHECK_CUDA(cudaGetLastError());
+  const float inv_count = 1.0f / (static_cast<float>(hw) * static_cast<float>(c / kGroups));
+  gn_finalize_kernel<<<n, kGroups, 0, st>>>(partial_ws, g.chunks, inv_count, eps, 0, mean_rstd);
+  GD_CHECK_CUDA(cudaGetLastError());
+  count_launch(2);
+  return 0;
+}
+
+#define GD_GN_DISPATCH(KERNEL, silu, mode, ...)                                   \
+  do {                                                                            \
+    if (silu) {                                                                   \
+      if (mode == GD_GN_SAME) KERNEL<true, GD_GN_SAME> __VA_ARGS__;               \
+      else if (mode == GD_GN_AVGPOOL2) KERNEL<true, GD_GN_AVGPOOL2> __VA_ARGS__;  \
+      else KERNEL<true, GD_GN_UPSAMPLE2> __VA_ARGS__;                             \
+    } else {                                                                      \
+      if (mode == GD_GN_SAME) KERNEL<false, GD_GN_SAME> __VA_ARGS__;              \
+      else if (mode == GD_GN_AVGPOOL2) KERNEL<false, GD_GN_AVGPOOL2> __VA_ARGS__; \
+      else KERNEL<false, GD_GN_UPSAMPLE2> __VA_ARGS__;                            \
+    }                                                                             \
+  } while (0)
+
+extern "C" int gd_groupnorm_apply(const void* x, int32_t ld, const float* mean_rstd, const float* gamma,
+                                  const float* beta, const float* film, int32_t film_ld, void* out, int32_t ld_out,
+                                  int32_t n, int32_t h, int32_t w, int32_t c, int32_t silu, int32_t spatial_mode,
+                                  void* stream) {
+  if (int rc = check_gn_common("gd_groupnorm_apply", x, ld, n, h * w, c)) return rc;
+  GD_REQUIRE(mean_rstd && gamma && beta && out, "gd_groupnorm_apply: null pointer");
+  GD_REQUIRE(ld_out >= c && ld_out % 8 == 0, "gd_groupnorm_apply: bad ld_out %d", ld_out);
+  GD_REQUIRE(spatial_mode >= GD_GN_SAME && spatial_mode <= GD_GN_UPSAMPLE2, "gd_groupnorm_apply: bad spatial mode");
+  if (spatial_mode == GD_GN_AVGPOOL2) GD_REQUIRE(h % 2 == 0 && w % 2 == 0, "gd_groupnorm_apply: avgpool needs even h,w");
+  if (film) GD_REQUIRE(film_ld >= 2 * c, "gd_groupnorm_apply: film_ld %d < 2*c", film_ld);
+  const int hw_iter = spatial_mode == GD_GN_AVGPOOL2 ? (h / 2) * (w / 2) : h * w;
+  const Geo g = make_geo(c, hw_iter);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  GD_GN_DISPATCH(gn_apply_kernel, silu, spatial_mode,
+                 <<<dim3(g.chunks, n), g.threads, 0, st>>>(reinterpret_cast<const __half*>(x), ld, mean_rstd, gamma,
+                                                          beta, film, film_ld, reinterpret_cast<__half*>(out), ld_out, h,
+                                                          w, c, g.c8, g.rep, g.px_per_chunk));
+  GD_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
+
+extern "C" int gd_groupnorm_bwd(const void* x, int32_t ld, const float* mean_rstd, const float* gamma, const float* beta,
+                                const float* film, int32_t film_ld, const void* dy, int32_t ld_dy, const void* add,
+                                int32_t ld_add, void* dx, int32_t ld_dx, float* partial_ws, int32_t n, int32_t h,
+                                int32_t w, int32_t c, int32_t silu, int32_t spatial_mode, void* stream) {
+  if (int rc = check_gn_common("gd_groupnorm_bwd", x, ld, n, h * w, c)) return rc;
+  GD_REQUIRE(mean_rstd && gamma && beta && dy && dx && partial_ws, "gd_groupnorm_bwd: null pointer");
+  GD_REQUIRE(ld_dy % 8 == 0 && ld_dx % 8 == 0 && (add == nullptr || ld_add % 8 == 0), "gd_groupnorm_bwd: bad strides");
+  GD_REQUIRE(spatial_mode >= GD_GN_SAME && spatial_mode <= GD_GN_UPSAMPLE2, "gd_groupnorm_bwd: bad spatial mode");
+  if (spatial_mode == GD_GN_AVGPOOL2) GD_REQUIRE(h % 2 == 0 && w % 2 == 0, "gd_groupnorm_bwd: avgpool needs even h,w");
+  const Geo g = make_geo(c, h * w);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // partial_ws layout: [n][kMaxChunks][32][2] partials, then [n][32][2] group means
+  float* gsum = partial_ws + static_cast<size_t>(n) * kMaxChunks * kGroups * 2;
+  GD_GN_DISPATCH(gn_bwd_stats_kernel, silu, spatial_mode,
+                 <<<dim3(g.chunks, n), g.threads, 0, st>>>(reinterpret_cast<const __half*>(x), ld, mean_rstd, gamma,
+                                                          beta, film, film_ld, reinterpret_cast<const __half*>(dy),
+                                                          ld_dy, h, w, c, g.c8, g.rep, g.px_per_chunk, partial_ws));
+  GD_CHECK_CUDA(cudaGetLastError());
+  const float inv_count = 1.0f / (static_cast<float>(h * w) * static_cast<float>(c / kGroups));
+  gn_finalize_kernel<<<n, kGroups, 0, st>>>(partial_ws, g.chunks, inv_count, 0.f, 1, gsum);
+  GD_CHECK_CUDA(cudaGetLastError());
+  GD_GN_DISPATCH(gn_bwd_apply_kernel, silu, spatial_mode,
+                 <<<dim3(g.chunks, n), g.threads, 0, st>>>(
+                     reinterpret_cast<const __half*>(x), ld, mean_rstd, gamma, beta, film, film_ld,
+                     reinterpret_cast<const __half*>(dy), ld_dy, gsum, reinterpret_cast<const __half*>(add), ld_add,
+                     reinterpret_cast<__half*>(dx), ld_dx, h, w, c, g.c8, g.rep, g.px_per_chunk));
+  GD_CHECK_CUDA(cudaGetLastError());
+  count_launch(3);
+  return 0;
+}

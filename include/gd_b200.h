@@ -1,0 +1,188 @@
+/*
+ * gd_b200.h — C ABI of libgd_b200.so, the sm_100a kernel library behind the guided-diffusion sampling path.
+ *
+ * The reference (ErezYosef/guided-diffusion-clip, /root/reference) has no FFI of its own: its hot path is
+ * PyTorch calls.  Every entry point below therefore names the reference *call site* it replaces
+ * (file:line relative to /root/reference/guided_diffusion/).  Conventions:
+ *   - extern "C", plain pointers and sizes only (no torch types); device pointers unless stated.
+ *   - returns 0 on success, <0 on error; gd_last_error() gives a thread-local message.  Never throws.
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream).
+ *   - no allocation, no synchronisation inside; safe to capture into a CUDA graph.
+ *   - activations are NHWC fp16 "channel views": (pointer, C, ld) where ld is the per-pixel stride in
+ *     elements, so a view may be a channel slice of a wider concat buffer (unet.py:661 th.cat is free).
+ */
+#ifndef GD_B200_H_
+#define GD_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GD_B200_ABI_VERSION 1
+
+/* residual modes of the conv epilogue */
+enum { GD_RES_NONE = 0, GD_RES_SAME = 1, GD_RES_UPSAMPLE2 = 2, GD_RES_AVGPOOL2 = 3 };
+/* output modes of the conv epilogue */
+enum { GD_OUT_NHWC_F16 = 0, GD_OUT_NCHW_F32 = 1 };
+/* spatial modes of the fused GroupNorm apply */
+enum { GD_GN_SAME = 0, GD_GN_AVGPOOL2 = 1, GD_GN_UPSAMPLE2 = 2 };
+/* QKV channel order: unet.py:347 (legacy: [head][q,k,v][d]) vs unet.py:380-388 (new: [q,k,v][head][d]) */
+enum { GD_QKV_LEGACY = 0, GD_QKV_NEW = 1 };
+
+const char* gd_last_error(void);
+int gd_version(void);
+/* Number of kernels launched by this library on this thread since the last gd_launch_count_reset(). */
+int64_t gd_launch_count(void);
+void gd_launch_count_reset(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution on tcgen05 (3x3 pad 1 stride 1, or 1x1), fp16 operands, fp32 accumulate.
+ * Replaces nn.Conv2d / nn.Conv1d(k=1): unet.py:185,211 (ResBlock convs), :222 (1x1 skip), :286,294
+ * (qkv / proj_out), :483 is handled by gd_conv3x3_small_cin, :616 (out head).  With gd_pack-ed flipped
+ * weights the same entry point is the conv backward-data of the guidance gradient
+ * (scripts/classifier_sample.py:54-61 autograd through unet.py:872-895).
+ *   out[n,y,x,co] = out_scale * ( bias[co] + sum_{tap,c} a0[n,y+dy,x+dx,c] * W[co][tap*C0+c]
+ *                                 + sum_c a1[n,y,x,c] * W[co][taps*C0+c]  + residual )
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct gd_conv_desc {
+  const void* a0; /* fp16 NHWC view [n,h,w,c0], per-pixel stride ld0 */
+  int32_t c0, ld0, taps; /* taps: 9 (3x3) or 1 (1x1) */
+  const void* a1; /* optional second source, 1x1 (fused skip_connection); NULL if unused */
+  int32_t c1, ld1;
+  int32_t n, h, w;
+  const void* wpack; /* fp16 [n_pad][k_total], k = tap*C0 + c then C1 channels (see gd pack helpers) */
+  int32_t k_total, n_pad;
+  const float* bias; /* fp32 [cout] or NULL */
+  int32_t cout;
+  const void* res; /* fp16 NHWC view with cout channels (resolution per res_mode) or NULL */
+  int32_t ld_res, res_mode;
+  void* out;
+  int32_t ld_out, out_mode;
+  int32_t bn; /* N tile, 0 = auto */
+  float out_scale; /* 0 is treated as 1 */
+} gd_conv_desc;
+int gd_conv_igemm(const gd_conv_desc* desc, void* stream);
+
+/* Direct 3x3 conv for tiny C_in (3 or 6): the first layer input_blocks.0.0 (unet.py:483,741).
+ * x: fp32 NCHW [n,cin,h,w]; w: fp32 [cout][cin*9] (OIHW flattened); out: fp16 NHWC view. */
+int gd_conv3x3_small_cin(const float* x, const float* w, const float* bias, void* out, int32_t ld_out, int32_t n,
+                         int32_t cin, int32_t h, int32_t w_, int32_t cout, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GroupNorm32 (+SiLU) (+FiLM scale/shift) (+avgpool2 / nearest-upsample2), nn.py:17-19,93-100 with
+ * unet.py:184,200-208,248-252 and the h_upd of unet.py:191-195.  Two launches: statistics, then apply.
+ * stats: mean_rstd[n][32][2] fp32 (biased variance, eps 1e-5).
+ * apply: y = act( (x-mean)*rstd*gamma+beta ) with optional *(1+scale)+shift before act;
+ *        film points at [n][2*c] fp32, scale first (unet.py:250), film_ld = row stride in floats.
+ * ---------------------------------------------------------------------------------------------- */
+int gd_groupnorm_stats(const void* x, int32_t ld, int32_t n, int32_t hw, int32_t c, float eps, float* partial_ws,
+                       float* mean_rstd, void* stream);
+int64_t gd_groupnorm_ws_floats(int32_t n, int32_t hw, int32_t c);
+int gd_groupnorm_apply(const void* x, int32_t ld, const float* mean_rstd, const float* gamma, const float* beta,
+                       const float* film, int32_t film_ld, void* out, int32_t ld_out, int32_t n, int32_t h, int32_t w,
+                       int32_t c, int32_t silu, int32_t spatial_mode, void* stream);
+/* Backward of the fused op above w.r.t. x (no parameter gradients; the guidance gradient needs dX only).
+ * dy is at the OUTPUT resolution of the forward op; dx (fp16 view, input resolution) = result (+ add if given). */
+int gd_groupnorm_bwd(const void* x, int32_t ld, const float* mean_rstd, const float* gamma, const float* beta,
+                     const float* film, int32_t film_ld, const void* dy, int32_t ld_dy, const void* add, int32_t ld_add,
+                     void* dx, int32_t ld_dx, float* partial_ws, int32_t n, int32_t h, int32_t w, int32_t c,
+                     int32_t silu, int32_t spatial_mode, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused attention, head dim 64: out[n,t,head*64+j] = sum_s softmax_s(q_t.k_s / 8) v_s  (fp32 softmax).
+ * Replaces QKVAttentionLegacy.forward / QKVAttention.forward, unet.py:337-354,370-389.
+ * qkv: fp16 [n,t,3*heads*64] view (ld), out: fp16 [n,t,heads*64] view. lse (optional): fp32 [n,heads,t].
+ * ---------------------------------------------------------------------------------------------- */
+int gd_attention_fwd(const void* qkv, int32_t ld_qkv, void* out, int32_t ld_out, float* lse, int32_t n, int32_t t,
+                     int32_t heads, int32_t order, void* stream);
+/* dqkv from dout, using saved qkv, out and lse. delta_ws: fp32 [n,heads,t]. */
+int gd_attention_bwd(const void* qkv, int32_t ld_qkv, const void* out, int32_t ld_out, const void* dout,
+                     int32_t ld_dout, const float* lse, float* delta_ws, void* dqkv, int32_t ld_dqkv, int32_t n,
+                     int32_t t, int32_t heads, int32_t order, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Small fp32 pieces.
+ * ---------------------------------------------------------------------------------------------- */
+/* nn.py:103-121 timestep_embedding: out[b] = [cos(t*f_k) | sin(t*f_k)], f_k = exp(-ln(1e4) k/half). */
+int gd_timestep_embedding(const float* t, float* out, int32_t n, int32_t dim, void* stream);
+/* y[m][n] = act_out( sum_k act_in(x[m][k]) * W[n][k] + b[n] ) (+ add[m][n]); nn.Linear of time_embed,
+ * label_emb MLP and every ResBlock.emb_layers (unet.py:199-205,472-476; unet_other.py:29-33). */
+int gd_linear_f32(const float* x, int32_t ldx, const float* w, const float* b, const float* add, int32_t ld_add,
+                  float* y, int32_t ldy, int32_t m, int32_t k, int32_t n, int32_t silu_in, int32_t silu_out,
+                  void* stream);
+/* out[b][:] = table[idx[b]][:]  (nn.Embedding label_emb, unet.py:479,653; the add happens in gd_linear_f32). */
+int gd_embedding_gather(const float* table, const int64_t* idx, float* out, int32_t n, int32_t dim, int32_t num_rows,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Attention-pool head of the classifier (unet.py:22-51, 833-841) forward and dX backward, fp32.
+ * h: fp16 NHWC [n,s,s,c] = SiLU(GN(h)) already applied.  See csrc/attnpool.cu for workspace layout.
+ * ---------------------------------------------------------------------------------------------- */
+int64_t gd_attnpool_ws_floats(int32_t n, int32_t tokens, int32_t c);
+int gd_attnpool_fwd(const void* h, int32_t ld, const float* pos_emb, const float* w_qkv, const float* b_qkv,
+                    const float* w_c, const float* b_c, float* logits, float* ws, int32_t n, int32_t hw, int32_t c,
+                    int32_t heads, int32_t n_out, void* stream);
+/* w_qkv_t: [c][3c] and w_c_t: [c][n_out] are host-side transposes of the forward weights. */
+int gd_attnpool_bwd(const float* dlogits, const float* w_qkv_t, const float* w_c_t, float* ws, void* dh, int32_t ld_dh,
+                    int32_t n, int32_t hw, int32_t c, int32_t heads, int32_t n_out, float out_scale, void* stream);
+/* dlogits[b][j] = scale * (1[j==y_b] - softmax(logits[b])_j): gradient of sum_b log_softmax(logits)[b,y_b]
+ * (scripts/classifier_sample.py:58-61). */
+int gd_logsoftmax_select_bwd(const float* logits, const int64_t* y, float* dlogits, int32_t n, int32_t classes,
+                             float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused posterior / noise update, one launch per sampling step (gaussian_diffusion.py:232-326, 356-393,
+ * 395-439, 546-594).  All tensors fp32 NCHW [n,3,h,w] except model_out [n,6 or 3,h,w].
+ * coef: device fp32 table [T'][GD_COEF_STRIDE]; step_idx: device int32 scalar selecting the row.
+ * ---------------------------------------------------------------------------------------------- */
+enum {
+  GD_COEF_SQRT_RECIP_ACP = 0,   /* sqrt_recip_alphas_cumprod      gaussian_diffusion.py:150 */
+  GD_COEF_SQRT_RECIPM1_ACP = 1, /* sqrt_recipm1_alphas_cumprod    :151 */
+  GD_COEF_POST_MEAN1 = 2,       /* posterior_mean_coef1           :162 */
+  GD_COEF_POST_MEAN2 = 3,       /* posterior_mean_coef2           :165 */
+  GD_COEF_LOG_BETA = 4,         /* log(betas) (max_log)           :272 */
+  GD_COEF_POST_LOGVAR = 5,      /* posterior_log_variance_clipped :159 */
+  GD_COEF_FIXED_VAR = 6,        /* model_variance for FIXED_*     :278-291 */
+  GD_COEF_FIXED_LOGVAR = 7,
+  GD_COEF_ACP = 8,              /* alphas_cumprod                 :141 */
+  GD_COEF_ACP_PREV = 9,         /* alphas_cumprod_prev            :142 */
+  GD_COEF_NONZERO = 10,         /* 1.0 if t != 0 else 0.0         :431-433 */
+  GD_COEF_STRIDE = 12
+};
+enum { GD_VAR_LEARNED_RANGE = 0, GD_VAR_FIXED = 1, GD_VAR_LEARNED = 2 };
+enum { GD_MEAN_EPSILON = 0, GD_MEAN_START_X = 1 };
+typedef struct gd_posterior_desc {
+  const float* x;         /* x_t */
+  const float* model_out; /* eps (and v) */
+  const float* grad;      /* cond_fn output (already scaled) or NULL */
+  const float* noise;     /* z */
+  float* sample;          /* x_{t-1} (may alias x) */
+  float* pred_xstart;     /* may be NULL */
+  const float* coef;
+  const int32_t* step_idx;
+  int32_t n, c, hw;
+  int32_t var_type, mean_type, clip_denoised;
+  int32_t ddim;
+  float eta;
+} gd_posterior_desc;
+int gd_posterior_step(const gd_posterior_desc* desc, void* stream);
+
+/* ((x+1)*127.5).clamp(0,255).to(uint8) NCHW -> NHWC (scripts/classifier_sample.py:87-89; truncation). */
+int gd_to_uint8_nhwc(const float* x, uint8_t* out, int32_t n, int32_t c, int32_t h, int32_t w, void* stream);
+
+/* Layout helpers used at the API boundary and by tests. */
+int gd_nchw_f32_to_nhwc_f16(const float* x, void* out, int32_t ld_out, int32_t n, int32_t c, int32_t h, int32_t w,
+                            void* stream);
+int gd_nhwc_f16_to_nchw_f32(const void* x, int32_t ld, float* out, int32_t n, int32_t c, int32_t h, int32_t w,
+                            void* stream);
+/* bilinear (align_corners=False) upsample of low_res fp32 NCHW into channels of an NCHW fp32 buffer
+ * (SuperResModel.forward, unet.py:677-681). */
+int gd_bilinear_upsample_nchw(const float* x, float* out, int32_t n, int32_t c, int32_t h_in, int32_t w_in,
+                              int32_t h_out, int32_t w_out, int32_t out_c_total, int32_t out_c_offset, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GD_B200_H_ */
