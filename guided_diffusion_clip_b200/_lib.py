@@ -1,0 +1,106 @@
+"""ctypes binding of libgd_b200.so (include/gd_b200.h).  This is the ONLY compute backend of the package:
+there is no CPU or eager-PyTorch fallback, and a missing library is a hard error."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgd_b200.so")
+
+# enums (keep in sync with include/gd_b200.h)
+RES_NONE, RES_SAME, RES_UPSAMPLE2, RES_AVGPOOL2 = 0, 1, 2, 3
+OUT_NHWC_F16, OUT_NCHW_F32 = 0, 1
+GN_SAME, GN_AVGPOOL2, GN_UPSAMPLE2 = 0, 1, 2
+QKV_LEGACY, QKV_NEW = 0, 1
+VAR_LEARNED_RANGE, VAR_FIXED, VAR_LEARNED = 0, 1, 2
+MEAN_EPSILON, MEAN_START_X = 0, 1
+(COEF_SQRT_RECIP_ACP, COEF_SQRT_RECIPM1_ACP, COEF_POST_MEAN1, COEF_POST_MEAN2, COEF_LOG_BETA, COEF_POST_LOGVAR,
+ COEF_FIXED_VAR, COEF_FIXED_LOGVAR, COEF_ACP, COEF_ACP_PREV, COEF_NONZERO) = range(11)
+COEF_STRIDE = 12
+
+i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [
+        ("a0", vp), ("c0", i32), ("ld0", i32), ("taps", i32),
+        ("a1", vp), ("c1", i32), ("ld1", i32),
+        ("n", i32), ("h", i32), ("w", i32),
+        ("wpack", vp), ("k_total", i32), ("n_pad", i32),
+        ("bias", vp), ("cout", i32),
+        ("res", vp), ("ld_res", i32), ("res_mode", i32),
+        ("out", vp), ("ld_out", i32), ("out_mode", i32),
+        ("bn", i32), ("out_scale", f32),
+    ]
+
+
+class PosteriorDesc(C.Structure):
+    _fields_ = [
+        ("x", vp), ("model_out", vp), ("grad", vp), ("noise", vp), ("sample", vp), ("pred_xstart", vp),
+        ("mean_out", vp), ("var_out", vp), ("logvar_out", vp),
+        ("coef", vp), ("t", vp),
+        ("n", i32), ("c", i32), ("hw", i32),
+        ("var_type", i32), ("mean_type", i32), ("clip_denoised", i32), ("ddim", i32), ("eta", f32),
+    ]
+
+
+# name -> (restype, argtypes); every symbol declared in include/gd_b200.h
+SIGNATURES = {
+    "gd_last_error": (C.c_char_p, []),
+    "gd_version": (C.c_int, []),
+    "gd_launch_count": (i64, []),
+    "gd_launch_count_reset": (None, []),
+    "gd_conv_igemm": (C.c_int, [C.POINTER(ConvDesc), vp]),
+    "gd_conv3x3_small_cin": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "gd_groupnorm_stats": (C.c_int, [vp, i32, i32, i32, i32, f32, vp, vp, vp]),
+    "gd_groupnorm_ws_floats": (i64, [i32, i32, i32]),
+    "gd_groupnorm_apply": (C.c_int, [vp, i32, vp, vp, vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
+    "gd_groupnorm_bwd": (C.c_int, [vp, i32, vp, vp, vp, vp, i32, vp, i32, vp, i32, i32, vp, i32, vp, i32, i32, i32,
+                                   i32, i32, i32, vp]),
+    "gd_attention_fwd": (C.c_int, [vp, i32, vp, i32, vp, i32, i32, i32, i32, vp]),
+    "gd_attention_bwd": (C.c_int, [vp, i32, vp, i32, vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "gd_timestep_embedding": (C.c_int, [vp, vp, i32, i32, vp]),
+    "gd_linear_f32": (C.c_int, [vp, i32, vp, vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "gd_embedding_gather": (C.c_int, [vp, vp, vp, i32, i32, i32, vp]),
+    "gd_attnpool_ws_floats": (i64, [i32, i32, i32]),
+    "gd_attnpool_fwd": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "gd_attnpool_bwd": (C.c_int, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, vp]),
+    "gd_logsoftmax_select_bwd": (C.c_int, [vp, vp, vp, i32, i32, f32, vp]),
+    "gd_posterior_step": (C.c_int, [C.POINTER(PosteriorDesc), vp]),
+    "gd_to_uint8_nhwc": (C.c_int, [vp, vp, i32, i32, i32, i32, vp]),
+    "gd_nchw_f32_to_nhwc_f16": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, vp]),
+    "gd_nhwc_f16_to_nchw_f32": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, vp]),
+    "gd_bilinear_upsample_nchw": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
+}
+
+_lib = None
+
+
+class GdError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the kernel library (building nothing: see _build.py / __graft_entry__.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GdError(
+            f"{LIB_PATH} is missing. Build it with `python -m guided_diffusion_clip_b200._build` "
+            "(nvcc, sm_100a). There is no fallback compute path."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the ABI and the header disagree
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().gd_last_error().decode("utf-8", "replace")
+        raise GdError(f"{what or 'gd call'} failed (rc={rc}): {msg}")

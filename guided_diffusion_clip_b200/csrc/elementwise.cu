@@ -19,8 +19,11 @@ struct PostArgs {
   const float* noise;
   float* sample;
   float* pred_xstart;
+  float* mean_out;
+  float* var_out;
+  float* logvar_out;
   const float* coef;
-  const int32_t* step_idx;
+  const int64_t* t;
   int n, c, hw;
   int var_type, mean_type, clip, ddim;
   float eta;
@@ -31,18 +34,19 @@ __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b);
 __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
 
 __global__ void posterior_kernel(const PostArgs p) {
-  const float* co = p.coef + static_cast<size_t>(*p.step_idx) * GD_COEF_STRIDE;
-  const float sr = co[GD_COEF_SQRT_RECIP_ACP], srm1 = co[GD_COEF_SQRT_RECIPM1_ACP];
-  const float c1 = co[GD_COEF_POST_MEAN1], c2 = co[GD_COEF_POST_MEAN2];
-  const float max_log = co[GD_COEF_LOG_BETA], min_log = co[GD_COEF_POST_LOGVAR];
-  const float acp = co[GD_COEF_ACP], acp_prev = co[GD_COEF_ACP_PREV];
-  const float nonzero = co[GD_COEF_NONZERO];
   const size_t chw = static_cast<size_t>(p.c) * p.hw;
   const size_t total = static_cast<size_t>(p.n) * chw;
   const int out_c = (p.var_type == GD_VAR_FIXED) ? p.c : 2 * p.c;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const size_t b = i / chw, r = i - b * chw;
+    // per-sample timestep index into the coefficient table (_extract_into_tensor, gaussian_diffusion.py:904-917)
+    const float* co = p.coef + static_cast<size_t>(p.t[b]) * GD_COEF_STRIDE;
+    const float sr = co[GD_COEF_SQRT_RECIP_ACP], srm1 = co[GD_COEF_SQRT_RECIPM1_ACP];
+    const float c1 = co[GD_COEF_POST_MEAN1], c2 = co[GD_COEF_POST_MEAN2];
+    const float max_log = co[GD_COEF_LOG_BETA], min_log = co[GD_COEF_POST_LOGVAR];
+    const float acp = co[GD_COEF_ACP], acp_prev = co[GD_COEF_ACP_PREV];
+    const float nonzero = co[GD_COEF_NONZERO];
     const size_t mo = b * static_cast<size_t>(out_c) * p.hw + r;
     const float x = p.x[i];
     const float m_out = p.model_out[mo];
@@ -66,9 +70,16 @@ __global__ void posterior_kernel(const PostArgs p) {
       x0 = m_out;
     }
     if (p.clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+    float mean = add(mul(c1, x0), mul(c2, x));
+    if (p.mean_out != nullptr) p.mean_out[i] = mean;
+    if (p.var_out != nullptr) p.var_out[i] = var;
+    if (p.logvar_out != nullptr) p.logvar_out[i] = logvar;
+    if (p.noise == nullptr) {  // p_mean_variance only
+      if (p.pred_xstart != nullptr) p.pred_xstart[i] = x0;
+      continue;
+    }
     float out;
     if (!p.ddim) {
-      float mean = add(mul(c1, x0), mul(c2, x));
       if (p.grad != nullptr) mean = add(mean, mul(var, p.grad[i]));
       const float z = p.noise[i];
       out = add(mean, mul(mul(nonzero, expf(mul(0.5f, logvar))), z));
@@ -314,14 +325,16 @@ using namespace gd;
 
 extern "C" int gd_posterior_step(const gd_posterior_desc* d, void* stream) {
   GD_REQUIRE(d != nullptr, "gd_posterior_step: null descriptor");
-  GD_REQUIRE(d->x && d->model_out && d->noise && d->sample && d->coef && d->step_idx, "gd_posterior_step: null pointer");
+  GD_REQUIRE(d->x && d->model_out && d->coef && d->t, "gd_posterior_step: null pointer");
+  GD_REQUIRE(d->noise == nullptr || d->sample != nullptr, "gd_posterior_step: noise given but no sample output");
   GD_REQUIRE(d->n > 0 && d->c > 0 && d->hw > 0, "gd_posterior_step: bad shape");
   GD_REQUIRE(d->var_type >= GD_VAR_LEARNED_RANGE && d->var_type <= GD_VAR_LEARNED, "gd_posterior_step: bad var_type");
   GD_REQUIRE(d->mean_type == GD_MEAN_EPSILON || d->mean_type == GD_MEAN_START_X,
              "gd_posterior_step: model_mean_type PREVIOUS_X is not on the sampling path built here");
   PostArgs p;
   p.x = d->x; p.model_out = d->model_out; p.grad = d->grad; p.noise = d->noise;
-  p.sample = d->sample; p.pred_xstart = d->pred_xstart; p.coef = d->coef; p.step_idx = d->step_idx;
+  p.sample = d->sample; p.pred_xstart = d->pred_xstart; p.coef = d->coef; p.t = d->t;
+  p.mean_out = d->mean_out; p.var_out = d->var_out; p.logvar_out = d->logvar_out;
   p.n = d->n; p.c = d->c; p.hw = d->hw;
   p.var_type = d->var_type; p.mean_type = d->mean_type; p.clip = d->clip_denoised; p.ddim = d->ddim; p.eta = d->eta;
   const size_t total = static_cast<size_t>(d->n) * d->c * d->hw;

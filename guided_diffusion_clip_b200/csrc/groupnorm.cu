@@ -40,21 +40,30 @@ Geo make_geo(int c, int hw) {
   return g;
 }
 
-// Reduce this thread's 8 per-channel values into per-group shared accumulators.
-__device__ __forceinline__ void group_accumulate(float* s_acc, const float (&v)[8], int ch0, int cpg) {
-  int g = ch0 / cpg;
-  float run = 0.f;
+// Deterministic block reduction of two per-thread [8]-channel partials into per-group sums:
+// every thread parks its values in shared memory, then thread (which, g) adds its group's
+// cpg channels x rep pixel lanes in a fixed order (no atomics -> bitwise reproducible statistics).
+// s_part: dynamic smem [2][blockDim.x][8] floats; s_acc: [2][32] result.
+__device__ __forceinline__ void block_group_reduce(float* s_part, float* s_acc, const float (&a)[8],
+                                                   const float (&b)[8], int c8, int rep, int cpg) {
+  const int T = blockDim.x, tid = threadIdx.x;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int gj = (ch0 + j) / cpg;
-    if (gj != g) {
-      atomicAdd(&s_acc[g], run);
-      run = 0.f;
-      g = gj;
-    }
-    run += v[j];
+    s_part[tid * 8 + j] = a[j];
+    s_part[(T + tid) * 8 + j] = b[j];
   }
-  atomicAdd(&s_acc[g], run);
+  __syncthreads();
+  if (tid < 2 * kGroups) {
+    const int which = tid / kGroups, g = tid % kGroups;
+    const float* src = s_part + static_cast<size_t>(which) * T * 8;
+    float acc = 0.f;
+    for (int ch = g * cpg; ch < (g + 1) * cpg; ++ch) {
+      const int cch = ch >> 3, j = ch & 7;
+      for (int pl = 0; pl < rep; ++pl) acc += src[(pl * c8 + cch) * 8 + j];
+    }
+    s_acc[tid] = acc;
+  }
+  __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -64,7 +73,7 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, int ld, int hw, in
                                 float* __restrict__ partial) {
   __shared__ float s_acc[2 * kGroups];
   const int n = blockIdx.y, chunk = blockIdx.x;
-  if (threadIdx.x < 2 * kGroups) s_acc[threadIdx.x] = 0.f;
+  extern __shared__ float s_part[];
   __syncthreads();
   const int cch = threadIdx.x % c8, pl = threadIdx.x / c8;
   const int p0 = chunk * px_per_chunk;
@@ -101,8 +110,7 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, int ld, int hw, in
     for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] += f[j] * f[j]; }
   }
   const int cpg = c / kGroups;
-  group_accumulate(s_acc, s, cch * 8, cpg);
-  group_accumulate(s_acc + kGroups, ss, cch * 8, cpg);
+  block_group_reduce(s_part, s_acc, s, ss, c8, rep, cpg);
   __syncthreads();
   if (threadIdx.x < kGroups) {
     float* o = partial + ((static_cast<size_t>(n) * gridDim.x + chunk) * kGroups + threadIdx.x) * 2;
@@ -327,7 +335,7 @@ __global__ void gn_bwd_stats_kernel(const __half* __restrict__ x, int ld, const 
                                     float* __restrict__ partial) {
   __shared__ float s_acc[2 * kGroups];
   const int n = blockIdx.y, chunk = blockIdx.x;
-  if (threadIdx.x < 2 * kGroups) s_acc[threadIdx.x] = 0.f;
+  extern __shared__ float s_part[];
   __syncthreads();
   const int cch = threadIdx.x % c8, pl = threadIdx.x / c8;
   BwdAffine A;
@@ -352,8 +360,7 @@ __global__ void gn_bwd_stats_kernel(const __half* __restrict__ x, int ld, const 
     }
   }
   const int cpg = c / kGroups;
-  group_accumulate(s_acc, s1, cch * 8, cpg);
-  group_accumulate(s_acc + kGroups, s2, cch * 8, cpg);
+  block_group_reduce(s_part, s_acc, s1, s2, c8, rep, cpg);
   __syncthreads();
   if (threadIdx.x < kGroups) {
     float* o = partial + ((static_cast<size_t>(n) * gridDim.x + chunk) * kGroups + threadIdx.x) * 2;
@@ -367,8 +374,8 @@ __global__ void gn_bwd_apply_kernel(const __half* __restrict__ x, int ld, const 
                                     const float* __restrict__ gamma, const float* __restrict__ beta,
                                     const float* __restrict__ film, int film_ld, const __half* __restrict__ dy, int ld_dy,
                                     const float* __restrict__ gsum, const __half* __restrict__ add, int ld_add,
-                                    __half* __restrict__ dx, int ld_dx, int h, int w, int c, int c8, int rep,
-                                    int px_per_chunk) {
+                                    int add_mode, __half* __restrict__ dx, int ld_dx, int h, int w, int c, int c8,
+                                    int rep, int px_per_chunk) {
   const int n = blockIdx.y, chunk = blockIdx.x;
   const int cch = threadIdx.x % c8, pl = threadIdx.x / c8;
   BwdAffine A;
@@ -398,9 +405,17 @@ __global__ void gn_bwd_apply_kernel(const __half* __restrict__ x, int ld, const 
     const size_t off = (static_cast<size_t>(n) * hw + p);
     if (add != nullptr) {
       float t[8];
-      half8_to_float(ld_half8(add + off * ld_add + cch * 8), t);
+      if (add_mode == GD_GN_SAME) {
+        half8_to_float(ld_half8(add + off * ld_add + cch * 8), t);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) r[j] += t[j];
+        for (int j = 0; j < 8; ++j) r[j] += t[j];
+      } else {  // gradient of the avg-pooled copy of x, stored at half resolution
+        const int iy = p / w, ix = p - iy * w;
+        const size_t q = (static_cast<size_t>(n) * (h / 2) + iy / 2) * (w / 2) + ix / 2;
+        half8_to_float(ld_half8(add + q * ld_add + cch * 8), t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] += 0.25f * t[j];
+      }
     }
     st_half8(dx + off * ld_dx + cch * 8, float_to_half8(r));
   }
@@ -420,7 +435,7 @@ extern "C" int64_t gd_groupnorm_ws_floats(int32_t n, int32_t hw, int32_t c) {
 static int check_gn_common(const char* who, const void* x, int ld, int n, int hw, int c) {
   GD_REQUIRE(x != nullptr, "%s: null input", who);
   GD_REQUIRE(n > 0 && hw > 0, "%s: bad n/hw", who);
-  GD_REQUIRE(c > 0 && c % 32 == 0 && c <= 8192, "%s: channels must be a multiple of 32 (GroupNorm32), got %d", who, c);
+  GD_REQUIRE(c > 0 && c % 32 == 0 && c <= 4096, "%s: channels must be a multiple of 32 (GroupNorm32), got %d", who, c);
   GD_REQUIRE(ld >= c && ld % 8 == 0, "%s: bad ld %d for c %d", who, ld, c);
   return 0;
 }
@@ -431,7 +446,7 @@ extern "C" int gd_groupnorm_stats(const void* x, int32_t ld, int32_t n, int32_t 
   GD_REQUIRE(partial_ws != nullptr && mean_rstd != nullptr, "gd_groupnorm_stats: null workspace/output");
   const Geo g = make_geo(c, hw);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  gn_stats_kernel<<<dim3(g.chunks, n), g.threads, 0, st>>>(reinterpret_cast<const __half*>(x), ld, hw, c, g.c8, g.rep,
+  gn_stats_kernel<<<dim3(g.chunks, n), g.threads, g.threads * 16 * sizeof(float), st>>>(reinterpret_cast<const __half*>(x), ld, hw, c, g.c8, g.rep,
                                                           g.px_per_chunk, partial_ws);
   GD_CHECK_CUDA(cudaGetLastError());
   const float inv_count = 1.0f / (static_cast<float>(hw) * static_cast<float>(c / kGroups));
@@ -478,19 +493,20 @@ extern "C" int gd_groupnorm_apply(const void* x, int32_t ld, const float* mean_r
 
 extern "C" int gd_groupnorm_bwd(const void* x, int32_t ld, const float* mean_rstd, const float* gamma, const float* beta,
                                 const float* film, int32_t film_ld, const void* dy, int32_t ld_dy, const void* add,
-                                int32_t ld_add, void* dx, int32_t ld_dx, float* partial_ws, int32_t n, int32_t h,
-                                int32_t w, int32_t c, int32_t silu, int32_t spatial_mode, void* stream) {
+                                int32_t ld_add, int32_t add_mode, void* dx, int32_t ld_dx, float* partial_ws, int32_t n,
+                                int32_t h, int32_t w, int32_t c, int32_t silu, int32_t spatial_mode, void* stream) {
   if (int rc = check_gn_common("gd_groupnorm_bwd", x, ld, n, h * w, c)) return rc;
   GD_REQUIRE(mean_rstd && gamma && beta && dy && dx && partial_ws, "gd_groupnorm_bwd: null pointer");
   GD_REQUIRE(ld_dy % 8 == 0 && ld_dx % 8 == 0 && (add == nullptr || ld_add % 8 == 0), "gd_groupnorm_bwd: bad strides");
   GD_REQUIRE(spatial_mode >= GD_GN_SAME && spatial_mode <= GD_GN_UPSAMPLE2, "gd_groupnorm_bwd: bad spatial mode");
+  GD_REQUIRE(add_mode == GD_GN_SAME || add_mode == GD_GN_AVGPOOL2, "gd_groupnorm_bwd: bad add_mode");
   if (spatial_mode == GD_GN_AVGPOOL2) GD_REQUIRE(h % 2 == 0 && w % 2 == 0, "gd_groupnorm_bwd: avgpool needs even h,w");
   const Geo g = make_geo(c, h * w);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // partial_ws layout: [n][kMaxChunks][32][2] partials, then [n][32][2] group means
   float* gsum = partial_ws + static_cast<size_t>(n) * kMaxChunks * kGroups * 2;
   GD_GN_DISPATCH(gn_bwd_stats_kernel, silu, spatial_mode,
-                 <<<dim3(g.chunks, n), g.threads, 0, st>>>(reinterpret_cast<const __half*>(x), ld, mean_rstd, gamma,
+                 <<<dim3(g.chunks, n), g.threads, g.threads * 16 * sizeof(float), st>>>(reinterpret_cast<const __half*>(x), ld, mean_rstd, gamma,
                                                           beta, film, film_ld, reinterpret_cast<const __half*>(dy),
                                                           ld_dy, h, w, c, g.c8, g.rep, g.px_per_chunk, partial_ws));
   GD_CHECK_CUDA(cudaGetLastError());
@@ -501,7 +517,7 @@ extern "C" int gd_groupnorm_bwd(const void* x, int32_t ld, const float* mean_rst
                  <<<dim3(g.chunks, n), g.threads, 0, st>>>(
                      reinterpret_cast<const __half*>(x), ld, mean_rstd, gamma, beta, film, film_ld,
                      reinterpret_cast<const __half*>(dy), ld_dy, gsum, reinterpret_cast<const __half*>(add), ld_add,
-                     reinterpret_cast<__half*>(dx), ld_dx, h, w, c, g.c8, g.rep, g.px_per_chunk));
+                     add_mode, reinterpret_cast<__half*>(dx), ld_dx, h, w, c, g.c8, g.rep, g.px_per_chunk));
   GD_CHECK_CUDA(cudaGetLastError());
   count_launch(3);
   return 0;

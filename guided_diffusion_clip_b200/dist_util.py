@@ -1,0 +1,141 @@
+"""Batch sharding across the GPUs of one box: the role of guided_diffusion/dist_util.py:21-83 plus the
+sampling-driver bookkeeping of scripts/classifier_sample.py:70-107, without MPI.
+
+One process per GPU (torchrun-style env rendezvous), every rank samples its own batch with seed
+`base_seed + rank`; the ONLY collective is the final all_gather of uint8 NHWC samples and int64 labels
+(NCCL over NVLink on GPUs, gloo in the CPU tests).  The integer bookkeeping — iteration count, rank-major
+output order, truncation to num_samples — follows the reference driver exactly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import io
+import os
+from typing import Callable, List, Optional, Tuple
+
+import numpy as np
+import torch as th
+import torch.distributed as dist
+
+from . import _lib as L
+
+
+def setup_dist(backend: Optional[str] = None) -> None:
+    """Initialise torch.distributed from RANK / WORLD_SIZE / MASTER_* (dist_util.py:21-42 without mpi4py) and
+    bind this process to cuda:LOCAL_RANK (the reference leaves that to the launcher, dist_util.py:27,49-50)."""
+    if dist.is_initialized():
+        return
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29533")
+    if backend is None:
+        backend = "nccl" if th.cuda.is_available() else "gloo"
+    if th.cuda.is_available():
+        th.cuda.set_device(local % th.cuda.device_count())
+    dist.init_process_group(backend=backend, rank=rank, world_size=world)
+
+
+def dev() -> th.device:
+    """dist_util.py:45-51."""
+    if th.cuda.is_available():
+        return th.device("cuda", th.cuda.current_device())
+    return th.device("cpu")
+
+
+def world_size() -> int:
+    return dist.get_world_size() if dist.is_initialized() else 1
+
+
+def rank() -> int:
+    return dist.get_rank() if dist.is_initialized() else 0
+
+
+def load_state_dict(path, **kwargs):
+    """dist_util.py:54-74 semantics (a flat OrderedDict[str, Tensor]) without the MPI broadcast: every rank of a
+    single box reads the file itself."""
+    with open(path, "rb") as f:
+        data = f.read()
+    return th.load(io.BytesIO(data), **kwargs)
+
+
+# ---- sharding bookkeeping (bit-exact with scripts/classifier_sample.py:70,93,99-102) -------------------
+def num_iterations(num_samples: int, batch_size: int, world: int) -> int:
+    """`while len(all_images) * batch_size < num_samples` with `world` entries appended per iteration."""
+    it, n_lists = 0, 0
+    while n_lists * batch_size < num_samples:
+        n_lists += world
+        it += 1
+    return it
+
+
+def rank_seed(base_seed: int, r: int) -> int:
+    """The reference never seeds; this package defines seed = base + rank."""
+    return int(base_seed) + int(r)
+
+
+def shard_slice(global_batch: int, world: int, r: int) -> Tuple[int, int]:
+    """Contiguous [lo, hi) share of a global batch for rank r (global_batch must divide evenly)."""
+    assert global_batch % world == 0, "global batch must be divisible by the world size"
+    per = global_batch // world
+    return r * per, (r + 1) * per
+
+
+def to_uint8_nhwc(sample: th.Tensor) -> th.Tensor:
+    """((sample + 1) * 127.5).clamp(0, 255).to(uint8).permute(0, 2, 3, 1) (classifier_sample.py:87-89)."""
+    if sample.device.type != "cuda":
+        raise L.GdError("to_uint8_nhwc only runs on CUDA; there is no CPU path")
+    n, c, h, w = sample.shape
+    x = sample.float().contiguous()
+    out = th.empty((n, h, w, c), dtype=th.uint8, device=sample.device)
+    stream = C.c_void_p(th.cuda.current_stream().cuda_stream)
+    L.check(L.load().gd_to_uint8_nhwc(C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), n, c, h, w, stream),
+            "gd_to_uint8_nhwc")
+    return out
+
+
+def all_gather_batch(sample_u8: th.Tensor, labels: th.Tensor) -> Tuple[List[th.Tensor], List[th.Tensor]]:
+    """The one collective of the path (classifier_sample.py:91-96): per-rank lists in rank order."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return [sample_u8], [labels]
+    imgs = [th.zeros_like(sample_u8) for _ in range(dist.get_world_size())]
+    dist.all_gather(imgs, sample_u8)
+    labs = [th.zeros_like(labels) for _ in range(dist.get_world_size())]
+    dist.all_gather(labs, labels)
+    return imgs, labs
+
+
+def sample_sharded(sample_batch: Callable[[th.Tensor], th.Tensor], *, num_samples: int, batch_size: int,
+                   num_classes: int, device, base_seed: int = 0, to_uint8: Callable = to_uint8_nhwc,
+                   generator: Optional[th.Generator] = None):
+    """The sampling driver loop of scripts/classifier_sample.py:70-102.
+
+    `sample_batch(classes) -> [batch_size, 3, H, W] float` runs one full sampling loop on this rank.
+    Labels are drawn per iteration BEFORE the sampler's noise (classifier_sample.py:72-74) from this rank's
+    generator.  Returns (arr uint8 [num_samples,H,W,3], label_arr int64 [num_samples]) — identical on all ranks."""
+    all_images: List[np.ndarray] = []
+    all_labels: List[np.ndarray] = []
+    while len(all_images) * batch_size < num_samples:
+        classes = th.randint(low=0, high=num_classes, size=(batch_size,), device=device, generator=generator)
+        sample = sample_batch(classes)
+        u8 = to_uint8(sample).contiguous()
+        imgs, labs = all_gather_batch(u8, classes)
+        all_images.extend(t.cpu().numpy() for t in imgs)
+        all_labels.extend(t.cpu().numpy() for t in labs)
+    arr = np.concatenate(all_images, axis=0)[:num_samples]
+    label_arr = np.concatenate(all_labels, axis=0)[:num_samples]
+    return arr, label_arr
+
+
+def save_npz(out_dir: str, arr: np.ndarray, label_arr: Optional[np.ndarray] = None) -> Optional[str]:
+    """Rank 0 writes samples_{N}x{H}x{W}x3.npz with arr_0 / arr_1 (classifier_sample.py:103-107)."""
+    if rank() != 0:
+        return None
+    shape_str = "x".join(str(x) for x in arr.shape)
+    path = os.path.join(out_dir, f"samples_{shape_str}.npz")
+    if label_arr is None:
+        np.savez(path, arr)
+    else:
+        np.savez(path, arr, label_arr)
+    return path

@@ -1,0 +1,644 @@
+"""Host-side execution planner: turns a model spec (unet.py) into a static sequence of C-ABI kernel launches
+over pre-allocated device buffers.  A plan is built once per (model, batch, resolution); running it is a
+tight loop of ctypes calls on the current CUDA stream, which makes it CUDA-graph capturable as is.
+
+Data layout in HBM:
+  * activations: NHWC fp16 "channel views" (buffer, channel offset, C); the skip concatenations of
+    unet.py:661 are physical buffers whose channel slices are written directly by their producers.
+  * conv weights: packed once to fp16 [N_pad][K] (K = tap*C_in + c, then fused 1x1-skip channels).
+  * everything fp32 in the reference (time/label embedding MLPs, emb_layers, GroupNorm parameters and
+    statistics, the pool head, the diffusion update) stays fp32.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import torch as th
+
+from . import _lib as L
+from .unet import AttnSpec, ConvInSpec, ResSpec
+
+GN_EPS = 1e-5
+
+
+def norm_device(device) -> th.device:
+    """Canonical device (cuda -> cuda:<current index>) so plan-cache keys agree between callers."""
+    d = th.device(device)
+    if d.type == "cuda" and d.index is None:
+        d = th.device("cuda", th.cuda.current_device())
+    return d
+
+
+def _require_cuda(device) -> None:
+    if th.device(device).type != "cuda":
+        raise L.GdError(
+            "guided_diffusion_clip_b200 only computes on CUDA (sm_100a); there is no CPU path. "
+            f"Got device {device}.")
+
+
+# ------------------------------------------------------------------------------------------------
+# views and program
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class View:
+    """NHWC fp16 channel view into a [N,H,W,LD] buffer."""
+    buf: th.Tensor
+    off: int
+    c: int
+
+    @property
+    def n(self): return self.buf.shape[0]
+    @property
+    def h(self): return self.buf.shape[1]
+    @property
+    def w(self): return self.buf.shape[2]
+    @property
+    def ld(self): return self.buf.shape[3]
+    @property
+    def ptr(self): return self.buf.data_ptr() + 2 * self.off
+
+    def slice(self, off: int, c: int) -> "View":
+        assert off + c <= self.c
+        return View(self.buf, self.off + off, c)
+
+    def torch(self) -> th.Tensor:
+        return self.buf[..., self.off:self.off + self.c]
+
+
+def new_act(n, h, w, c, device) -> View:
+    return View(th.empty((n, h, w, c), dtype=th.float16, device=device), 0, c)
+
+
+class Program:
+    """A recorded list of (C function, args) — replayed on whatever stream is current."""
+
+    def __init__(self):
+        self.calls: List[Tuple[object, tuple, str]] = []
+        self.keep: List[object] = []
+
+    def add(self, name: str, *args) -> None:
+        fn = getattr(L.load(), name)
+        self.calls.append((fn, args, name))
+
+    def run(self) -> None:
+        stream = C.c_void_p(th.cuda.current_stream().cuda_stream)
+        for fn, args, name in self.calls:
+            rc = fn(*args, stream)
+            if rc != 0:
+                L.check(rc, name)
+
+    @property
+    def launches(self) -> int:
+        per = {"gd_groupnorm_stats": 2, "gd_groupnorm_bwd": 3, "gd_attention_bwd": 3, "gd_attnpool_fwd": 6,
+               "gd_attnpool_bwd": 4}
+        return sum(per.get(name, 1) for _, _, name in self.calls)
+
+
+def _p(t: Optional[th.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+# ------------------------------------------------------------------------------------------------
+# weight packing (host side, once per plan)
+# ------------------------------------------------------------------------------------------------
+def _pad_rows(w2d: th.Tensor) -> th.Tensor:
+    n = w2d.shape[0]
+    n_pad = (n + 15) // 16 * 16
+    if n_pad != n:
+        w2d = th.cat([w2d, w2d.new_zeros(n_pad - n, w2d.shape[1])], 0)
+    return w2d.to(th.float16).contiguous()
+
+
+def pack_conv3x3(w: th.Tensor, skip_w: Optional[th.Tensor] = None) -> th.Tensor:
+    """OIHW [Co,Ci,3,3] -> [Co_pad][9*Ci (+ Cskip)] with k = (ky*3+kx)*Ci + ci; A-side tap offset (ky-1,kx-1)."""
+    co, ci = w.shape[:2]
+    m = w.float().permute(0, 2, 3, 1).reshape(co, 9 * ci)
+    if skip_w is not None:
+        m = th.cat([m, skip_w.float().reshape(co, -1)], 1)
+    return _pad_rows(m)
+
+
+def pack_conv3x3_bwd(w: th.Tensor) -> th.Tensor:
+    """Weights of the data-gradient conv: dX[ci] = sum_{tap',co} dY[y+dy',x+dx'][co] * W[co][ci][2-ky'][2-kx']."""
+    co, ci = w.shape[:2]
+    m = w.float().flip(2, 3).permute(1, 2, 3, 0).reshape(ci, 9 * co)
+    return _pad_rows(m)
+
+
+def pack_1x1(w: th.Tensor) -> th.Tensor:
+    return _pad_rows(w.float().reshape(w.shape[0], -1))
+
+
+def pack_1x1_bwd(w: th.Tensor) -> th.Tensor:
+    return _pad_rows(w.float().reshape(w.shape[0], -1).t())
+
+
+class Emitter:
+    """Shared emission helpers for the UNet and classifier plans."""
+
+    def __init__(self, model, n: int, device):
+        _require_cuda(device)
+        L.load()
+        self.model = model
+        self.n = n
+        self.device = device
+        self.P: Dict[str, th.Tensor] = {k: v.detach() for k, v in model.named_parameters()}
+        self.prog = Program()
+        self._scratch: Dict[str, th.Tensor] = {}
+        self._f32: Dict[str, th.Tensor] = {}
+        self.keep: List[th.Tensor] = []
+        self.gn_ws = None
+        self._gn_ws_floats = 0
+
+    # ---- buffers ------------------------------------------------------------------------------
+    def scratch(self, role: str, n, h, w, c) -> View:
+        """Reusable fp16 scratch, grown to the largest request per role (allocated in finalize())."""
+        need = n * h * w * c
+        cur = self._scratch.get(role)
+        if cur is None or cur.numel() < need:
+            self._scratch[role] = th.empty(need, dtype=th.float16, device=self.device)
+            # earlier views of this role keep their (smaller) tensor alive through Program.keep
+        buf = self._scratch[role][:need].view(n, h, w, c)
+        self.keep.append(buf)
+        return View(buf, 0, c)
+
+    def f32(self, name: str) -> th.Tensor:
+        """fp32 copy of a parameter (biases / GN affine / linear weights); fp16-rounded if the model holds it in fp16."""
+        t = self._f32.get(name)
+        if t is None:
+            t = self.P[name].float().contiguous()
+            self._f32[name] = t
+        return t
+
+    def stats_buf(self) -> th.Tensor:
+        t = th.empty((self.n, 32, 2), dtype=th.float32, device=self.device)
+        self.keep.append(t)
+        return t
+
+    def _gn_workspace(self) -> th.Tensor:
+        if self.gn_ws is None:
+            floats = int(L.load().gd_groupnorm_ws_floats(self.n, 1, 32))
+            self.gn_ws = th.empty(floats, dtype=th.float32, device=self.device)
+        return self.gn_ws
+
+    # ---- op emitters --------------------------------------------------------------------------
+    def conv(self, a0: View, wpack: th.Tensor, bias: Optional[th.Tensor], cout: int, out, *, taps=9,
+             a1: Optional[View] = None, res: Optional[View] = None, res_mode=L.RES_NONE, out_mode=L.OUT_NHWC_F16,
+             out_scale=1.0, geom: Optional[Tuple[int, int, int]] = None) -> None:
+        n, h, w = geom if geom is not None else (a0.n, a0.h, a0.w)
+        d = L.ConvDesc()
+        d.a0, d.c0, d.ld0, d.taps = a0.ptr, a0.c, a0.ld, taps
+        if a1 is not None:
+            d.a1, d.c1, d.ld1 = a1.ptr, a1.c, a1.ld
+        else:
+            d.a1, d.c1, d.ld1 = None, 0, 0
+        d.n, d.h, d.w = n, h, w
+        d.wpack, d.k_total, d.n_pad = wpack.data_ptr(), wpack.shape[1], wpack.shape[0]
+        assert wpack.shape[1] == taps * a0.c + (a1.c if a1 is not None else 0), (wpack.shape, taps, a0.c)
+        d.bias = bias.data_ptr() if bias is not None else None
+        d.cout = cout
+        if res is not None:
+            d.res, d.ld_res, d.res_mode = res.ptr, res.ld, res_mode
+        else:
+            d.res, d.ld_res, d.res_mode = None, 0, L.RES_NONE
+        if out_mode == L.OUT_NHWC_F16:
+            d.out, d.ld_out = out.ptr, out.ld
+        else:
+            d.out, d.ld_out = out.data_ptr(), 0
+        d.out_mode = out_mode
+        d.bn = 0
+        d.out_scale = out_scale
+        self.keep += [wpack, bias, d]
+        self.prog.add("gd_conv_igemm", C.byref(d))
+
+    def gn_stats(self, x: View, stats: th.Tensor) -> None:
+        self.prog.add("gd_groupnorm_stats", C.c_void_p(x.ptr), x.ld, x.n, x.h * x.w, x.c, C.c_float(GN_EPS),
+                      _p(self._gn_workspace()), _p(stats))
+
+    def gn_apply(self, x: View, stats, gamma, beta, out: View, *, silu: bool, film=None, film_ld=0,
+                 mode=L.GN_SAME) -> None:
+        self.keep += [gamma, beta]
+        self.prog.add("gd_groupnorm_apply", C.c_void_p(x.ptr), x.ld, _p(stats), _p(gamma), _p(beta),
+                      C.c_void_p(film) if film else None, film_ld, C.c_void_p(out.ptr), out.ld, x.n, x.h, x.w, x.c,
+                      int(silu), mode)
+
+    def gn_bwd(self, x: View, stats, gamma, beta, dy: View, dx: View, *, silu: bool, film=None, film_ld=0,
+               mode=L.GN_SAME, add: Optional[View] = None, add_mode=L.GN_SAME) -> None:
+        self.prog.add("gd_groupnorm_bwd", C.c_void_p(x.ptr), x.ld, _p(stats), _p(gamma), _p(beta),
+                      C.c_void_p(film) if film else None, film_ld, C.c_void_p(dy.ptr), dy.ld,
+                      C.c_void_p(add.ptr) if add is not None else None, add.ld if add is not None else 0, add_mode,
+                      C.c_void_p(dx.ptr), dx.ld, _p(self._gn_workspace()), x.n, x.h, x.w, x.c, int(silu), mode)
+
+    def linear(self, x: th.Tensor, w: th.Tensor, b, y: th.Tensor, *, m, k, n, ldx=None, ldy=None, add=None,
+               silu_in=False, silu_out=False) -> None:
+        self.keep += [x, w, b, y, add]
+        self.prog.add("gd_linear_f32", _p(x), ldx or k, _p(w), _p(b), _p(add), (add.shape[-1] if add is not None else 0),
+                      _p(y), ldy or n, m, k, n, int(silu_in), int(silu_out))
+
+    # ---- embeddings ---------------------------------------------------------------------------
+    def emit_embedding(self, t_buf: th.Tensor, cond: Optional[th.Tensor], spec) -> th.Tensor:
+        """timestep_embedding -> time_embed MLP (+ label embedding) -> SiLU -> ONE batched emb_layers GEMM
+        producing every ResBlock's (scale, shift).  Returns film_all [n, film_total] fp32."""
+        n, mc, e = self.n, spec.model_channels, spec.emb_dim
+        dev = self.device
+        temb = th.empty((n, mc), dtype=th.float32, device=dev)
+        h1 = th.empty((n, e), dtype=th.float32, device=dev)
+        emb_silu = th.empty((n, e), dtype=th.float32, device=dev)
+        self.prog.add("gd_timestep_embedding", _p(t_buf), _p(temb), n, mc)
+        self.keep += [t_buf, temb]
+        self.linear(temb, self.f32("time_embed.0.weight"), self.f32("time_embed.0.bias"), h1, m=n, k=mc, n=e,
+                    silu_out=True)
+        lab = None
+        model = self.model
+        if getattr(model, "num_classes", None) is not None:
+            lab = th.empty((n, e), dtype=th.float32, device=dev)
+            if model.label_mlp:
+                nc = model.num_classes
+                l1 = th.empty((n, e), dtype=th.float32, device=dev)
+                self.linear(cond, self.f32("label_emb.0.weight"), self.f32("label_emb.0.bias"), l1, m=n, k=nc, n=e,
+                            silu_out=True)
+                self.linear(l1, self.f32("label_emb.2.weight"), self.f32("label_emb.2.bias"), lab, m=n, k=e, n=e)
+            else:
+                table = self.f32("label_emb.weight")
+                self.keep += [table, cond, lab]
+                self.prog.add("gd_embedding_gather", _p(table), _p(cond), _p(lab), n, e, table.shape[0])
+        # emb = time_embed(...) + label ; every consumer applies SiLU first (unet.py:200) -> store SiLU(emb)
+        self.linear(h1, self.f32("time_embed.2.weight"), self.f32("time_embed.2.bias"), emb_silu, m=n, k=e, n=e,
+                    add=lab, silu_out=True)
+        blocks = spec.res_blocks()
+        if not self.model.use_scale_shift_norm:
+            raise NotImplementedError("use_scale_shift_norm=False has no CUDA path (every BASELINE config sets it)")
+        w_all = th.cat([self.f32(f"{r.key}.emb_layers.1.weight") for r in blocks], 0).contiguous()
+        b_all = th.cat([self.f32(f"{r.key}.emb_layers.1.bias") for r in blocks], 0).contiguous()
+        film_all = th.empty((n, spec.film_total), dtype=th.float32, device=dev)
+        self.linear(emb_silu, w_all, b_all, film_all, m=n, k=e, n=spec.film_total)
+        return film_all
+
+    # ---- blocks -------------------------------------------------------------------------------
+    def conv_in(self, l: ConvInSpec, x_nchw: th.Tensor, out: View) -> None:
+        w = self.P[f"{l.key}.weight"]
+        w32 = w.float().reshape(l.cout, -1).contiguous()
+        b32 = self.f32(f"{l.key}.bias")
+        self.keep += [w32, x_nchw]
+        self.prog.add("gd_conv3x3_small_cin", _p(x_nchw), _p(w32), _p(b32), C.c_void_p(out.ptr), out.ld, out.n, l.cin,
+                      out.h, out.w, l.cout)
+
+    def res_block(self, r: ResSpec, x: View, out: View, film_all: th.Tensor, tape: Optional[list] = None) -> None:
+        """ResBlock._forward (unet.py:236-256) in 6 launches: GN stats, GN-apply(+SiLU, +pool/upsample), conv,
+        GN stats, GN-apply(+FiLM+SiLU), conv (+1x1 skip as extra K blocks | identity residual in the epilogue)."""
+        n = self.n
+        if r.mode == "down":
+            ho, wo, gmode, rmode = x.h // 2, x.w // 2, L.GN_AVGPOOL2, L.RES_AVGPOOL2
+        elif r.mode == "up":
+            ho, wo, gmode, rmode = x.h * 2, x.w * 2, L.GN_UPSAMPLE2, L.RES_UPSAMPLE2
+        else:
+            ho, wo, gmode, rmode = x.h, x.w, L.GN_SAME, L.RES_SAME
+        assert (out.h, out.w, out.c) == (ho, wo, r.cout), (out.buf.shape, ho, wo, r.cout)
+        k = r.key
+        st1, st2 = self.stats_buf(), self.stats_buf()
+        a = self.scratch("gn_out", n, ho, wo, r.cin)
+        self.gn_stats(x, st1)
+        self.gn_apply(x, st1, self.f32(f"{k}.in_layers.0.weight"), self.f32(f"{k}.in_layers.0.bias"), a, silu=True,
+                      mode=gmode)
+        h1 = new_act(n, ho, wo, r.cout, self.device) if tape is not None else self.scratch("h1", n, ho, wo, r.cout)
+        w1 = pack_conv3x3(self.P[f"{k}.in_layers.2.weight"])
+        self.conv(a, w1, self.f32(f"{k}.in_layers.2.bias"), r.cout, h1)
+        self.gn_stats(h1, st2)
+        b = self.scratch("gn_out2", n, ho, wo, r.cout)
+        film_ptr = film_all.data_ptr() + 4 * r.film_offset
+        self.gn_apply(h1, st2, self.f32(f"{k}.out_layers.0.weight"), self.f32(f"{k}.out_layers.0.bias"), b, silu=True,
+                      film=film_ptr, film_ld=film_all.shape[1])
+        if r.has_skip_conv:
+            assert r.mode == "none"
+            w2 = pack_conv3x3(self.P[f"{k}.out_layers.3.weight"], self.P[f"{k}.skip_connection.weight"])
+            bias2 = (self.f32(f"{k}.out_layers.3.bias") + self.f32(f"{k}.skip_connection.bias")).contiguous()
+            self.conv(b, w2, bias2, r.cout, out, a1=x)
+        else:
+            w2 = pack_conv3x3(self.P[f"{k}.out_layers.3.weight"])
+            self.conv(b, w2, self.f32(f"{k}.out_layers.3.bias"), r.cout, out, res=x, res_mode=rmode)
+        if tape is not None:
+            tape.append(("res", r, x, st1, h1, st2, film_ptr, film_all.shape[1], out))
+
+    def attn_block(self, a: AttnSpec, x: View, out: View, tape: Optional[list] = None) -> None:
+        """AttentionBlock._forward (unet.py:299-305): GN, qkv 1x1, fused attention, proj 1x1 + residual."""
+        if a.ch != a.heads * 64:
+            raise NotImplementedError(
+                f"attention head dim {a.ch // a.heads} != 64: only num_head_channels=64 has a CUDA path")
+        n, h, w = x.n, x.h, x.w
+        k = a.key
+        st = self.stats_buf()
+        g = self.scratch("gn_out", n, h, w, a.ch)
+        self.gn_stats(x, st)
+        self.gn_apply(x, st, self.f32(f"{k}.norm.weight"), self.f32(f"{k}.norm.bias"), g, silu=False)
+        keep = tape is not None
+        qkv = new_act(n, h, w, 3 * a.ch, self.device) if keep else self.scratch("qkv", n, h, w, 3 * a.ch)
+        att = new_act(n, h, w, a.ch, self.device) if keep else self.scratch("att", n, h, w, a.ch)
+        lse = th.empty((n, a.heads, h * w), dtype=th.float32, device=self.device) if keep else None
+        self.conv(g, pack_1x1(self.P[f"{k}.qkv.weight"]), self.f32(f"{k}.qkv.bias"), 3 * a.ch, qkv, taps=1)
+        order = L.QKV_NEW if a.new_order else L.QKV_LEGACY
+        self.keep.append(lse)
+        self.prog.add("gd_attention_fwd", C.c_void_p(qkv.ptr), qkv.ld, C.c_void_p(att.ptr), att.ld, _p(lse), n, h * w,
+                      a.heads, order)
+        self.conv(att, pack_1x1(self.P[f"{k}.proj_out.weight"]), self.f32(f"{k}.proj_out.bias"), a.ch, out, taps=1,
+                  res=x, res_mode=L.RES_SAME)
+        if tape is not None:
+            tape.append(("attn", a, x, st, qkv, att, lse, out))
+
+
+# ------------------------------------------------------------------------------------------------
+# UNet forward plan
+# ------------------------------------------------------------------------------------------------
+class UNetPlan:
+    """UNetModel.forward (unet.py:635-664) for a fixed (batch, H, W)."""
+
+    def __init__(self, model, n: int, h: int, w: int, device):
+        em = Emitter(model, n, device)
+        self.em = em
+        spec = model.spec
+        dev = device
+        self.x_in = th.empty((n, model.in_channels, h, w), dtype=th.float32, device=dev)
+        self.t_in = th.empty((n,), dtype=th.float32, device=dev)
+        self.cond_in = None
+        if model.num_classes is not None:
+            self.cond_in = (th.empty((n, model.num_classes), dtype=th.float32, device=dev) if model.label_mlp
+                            else th.empty((n,), dtype=th.int64, device=dev))
+        self.out = th.empty((n, model.out_channels, h, w), dtype=th.float32, device=dev)
+        film_all = em.emit_embedding(self.t_in, self.cond_in, spec)
+
+        # --- geometry of every input-block output (the hs stack, unet.py:648,658) -------------------
+        hs_shapes = []  # (c, h, w)
+        ch, hh, ww = None, h, w
+        for blk in spec.input_blocks:
+            for l in blk:
+                if isinstance(l, ConvInSpec):
+                    ch = l.cout
+                elif isinstance(l, ResSpec):
+                    ch = l.cout
+                    if l.mode == "down":
+                        hh, ww = hh // 2, ww // 2
+            hs_shapes.append((ch, hh, ww))
+        # --- concat buffers: output block j consumes cat([h, hs.pop()]) ------------------------------
+        n_out = len(spec.output_blocks)
+        cat_bufs: List[View] = []
+        hcur = (ch, hh, ww)  # middle block output geometry
+        hs_stack = list(hs_shapes)
+        for j, blk in enumerate(spec.output_blocks):
+            sc, sh, sw = hs_stack.pop()
+            assert (sh, sw) == (hcur[1], hcur[2]), "skip / h resolution mismatch"
+            cat_bufs.append(new_act(n, sh, sw, hcur[0] + sc, dev))
+            c2, h2, w2 = hcur
+            for l in blk:
+                if isinstance(l, ResSpec):
+                    c2 = l.cout
+                    if l.mode == "up":
+                        h2, w2 = h2 * 2, w2 * 2
+            hcur = (c2, h2, w2)
+        final_view = new_act(n, hcur[1], hcur[2], hcur[0], dev)
+
+        def hs_view(i: int) -> View:
+            # hs[i] is popped by output block j = n_out-1-i and sits after h's channels
+            j = n_out - 1 - i
+            cb = cat_bufs[j]
+            c_skip = hs_shapes[i][0]
+            return cb.slice(cb.c - c_skip, c_skip)
+
+        def run_block(layers, x: View, dst: View):
+            cur = x
+            for li, l in enumerate(layers):
+                last = li == len(layers) - 1
+                if isinstance(l, ResSpec):
+                    oh, ow = ((cur.h // 2, cur.w // 2) if l.mode == "down" else
+                              (cur.h * 2, cur.w * 2) if l.mode == "up" else (cur.h, cur.w))
+                    o = dst if last else em.scratch(f"blk{li % 2}", n, oh, ow, l.cout)
+                    em.res_block(l, cur, o, film_all)
+                else:
+                    o = dst if last else em.scratch(f"blk{li % 2}", n, cur.h, cur.w, l.ch)
+                    em.attn_block(l, cur, o)
+                cur = o
+            return cur
+
+        # --- input blocks ---------------------------------------------------------------------------
+        cur: Optional[View] = None
+        for i, blk in enumerate(spec.input_blocks):
+            dst = hs_view(i)
+            if isinstance(blk[0], ConvInSpec):
+                em.conv_in(blk[0], self.x_in, dst)
+                cur = dst
+            else:
+                cur = run_block(blk, cur, dst)
+        # --- middle ---------------------------------------------------------------------------------
+        mid_dst = cat_bufs[0].slice(0, cat_bufs[0].c - hs_shapes[-1][0]) if n_out else final_view
+        cur = run_block(spec.middle_block, cur, mid_dst)
+        # --- output blocks --------------------------------------------------------------------------
+        for j, blk in enumerate(spec.output_blocks):
+            if j + 1 < n_out:
+                nxt = cat_bufs[j + 1]
+                dst = nxt.slice(0, nxt.c - hs_shapes[n_out - 2 - j][0])
+            else:
+                dst = final_view
+            cur = run_block(blk, cat_bufs[j], dst)
+        # --- out head: GN -> SiLU -> conv3x3 (fp32 in the reference, unet.py:613-617,663-664) ---------
+        st = em.stats_buf()
+        g = em.scratch("gn_out", n, cur.h, cur.w, cur.c)
+        em.gn_stats(cur, st)
+        em.gn_apply(cur, st, em.f32("out.0.weight"), em.f32("out.0.bias"), g, silu=True)
+        em.conv(g, pack_conv3x3(em.P["out.2.weight"]), em.f32("out.2.bias"), model.out_channels, self.out,
+                out_mode=L.OUT_NCHW_F32)
+        self.prog = em.prog
+
+    def load_inputs(self, x, timesteps, cond) -> None:
+        self.x_in.copy_(x)
+        self.t_in.copy_(timesteps)
+        if self.cond_in is not None:
+            self.cond_in.copy_(cond)
+
+    def run(self, x, timesteps, cond) -> th.Tensor:
+        self.load_inputs(x, timesteps, cond)
+        self.prog.run()
+        return self.out
+
+
+def bilinear_concat(x: th.Tensor, low_res: th.Tensor) -> th.Tensor:
+    """cat([x, F.interpolate(low_res, (H,W), mode='bilinear')], 1) (unet.py:677-680) via the CUDA kernel."""
+    _require_cuda(x.device)
+    n, c, h, w = x.shape
+    cl = low_res.shape[1]
+    out = th.empty((n, c + cl, h, w), dtype=th.float32, device=x.device)
+    out[:, :c].copy_(x)
+    lr = low_res.float().contiguous()
+    stream = C.c_void_p(th.cuda.current_stream().cuda_stream)
+    L.check(L.load().gd_bilinear_upsample_nchw(_p(lr), _p(out), n, cl, lr.shape[2], lr.shape[3], h, w, c + cl, c, stream),
+            "gd_bilinear_upsample_nchw")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# classifier forward + dX backward plan
+# ------------------------------------------------------------------------------------------------
+class ClassifierPlan:
+    """EncoderUNetModel.forward (unet.py:872-895) with every tensor the data-gradient needs kept resident
+    (no recompute, no parameter gradients — unlike the reference's CheckpointFunction, nn.py:152-170), and
+    the matching backward program producing d(sum selected log-probs)/dx in fp32 NCHW."""
+
+    LOSS_SCALE = 256.0  # static fp16 gradient scale, undone in the last conv's epilogue
+
+    def __init__(self, model, n: int, h: int, w: int, device):
+        em = Emitter(model, n, device)
+        self.em = em
+        self.model = model
+        spec = model.spec
+        dev = device
+        self.n = n
+        self.x_in = th.empty((n, model.in_channels, h, w), dtype=th.float32, device=dev)
+        self.t_in = th.empty((n,), dtype=th.float32, device=dev)
+        self.logits = th.empty((n, model.out_channels), dtype=th.float32, device=dev)
+        self.dlogits = th.empty((n, model.out_channels), dtype=th.float32, device=dev)
+        self.dx = th.empty((n, model.in_channels, h, w), dtype=th.float32, device=dev)
+        self.grad_scale = th.ones((), dtype=th.float32)
+        film_all = em.emit_embedding(self.t_in, None, spec)
+        tape: list = []
+        cur: Optional[View] = None
+        hh, ww = h, w
+        for blk in spec.input_blocks + [spec.middle_block]:
+            for l in blk:
+                if isinstance(l, ConvInSpec):
+                    o = new_act(n, hh, ww, l.cout, dev)
+                    em.conv_in(l, self.x_in, o)
+                    tape.append(("conv_in", l, o))
+                elif isinstance(l, ResSpec):
+                    if l.mode == "down":
+                        hh, ww = hh // 2, ww // 2
+                    o = new_act(n, hh, ww, l.cout, dev)
+                    em.res_block(l, cur, o, film_all, tape)
+                else:
+                    o = new_act(n, hh, ww, l.ch, dev)
+                    em.attn_block(l, cur, o, tape)
+                cur = o
+        # head: GN -> SiLU -> AttentionPool2d (unet.py:833-841)
+        st = em.stats_buf()
+        pooled_in = new_act(n, hh, ww, cur.c, dev)
+        em.gn_stats(cur, st)
+        em.gn_apply(cur, st, em.f32("out.0.weight"), em.f32("out.0.bias"), pooled_in, silu=True)
+        hw, cch, heads = hh * ww, cur.c, model.pool_heads
+        lib = L.load()
+        ws = th.empty(int(lib.gd_attnpool_ws_floats(n, hw + 1, cch)), dtype=th.float32, device=dev)
+        pos = em.f32("out.2.positional_embedding")
+        wqkv = em.P["out.2.qkv_proj.weight"].float().reshape(3 * cch, cch).contiguous()
+        bqkv = em.f32("out.2.qkv_proj.bias")
+        wc = em.P["out.2.c_proj.weight"].float().reshape(model.out_channels, cch).contiguous()
+        bc = em.f32("out.2.c_proj.bias")
+        em.keep += [ws, pos, wqkv, bqkv, wc, bc]
+        em.prog.add("gd_attnpool_fwd", C.c_void_p(pooled_in.ptr), pooled_in.ld, _p(pos), _p(wqkv), _p(bqkv), _p(wc),
+                    _p(bc), _p(self.logits), _p(ws), n, hw, cch, heads, model.out_channels)
+        self.fwd = em.prog
+
+        # ------------------------------------------------------------------ backward program
+        em.prog = Program()
+        bw = em
+        wqkv_t = wqkv.t().contiguous()
+        wc_t = wc.t().contiguous()
+        em.keep += [wqkv_t, wc_t]
+        d_pool = bw.scratch("g_pool", n, hh, ww, cch)
+        bw.prog.add("gd_attnpool_bwd", _p(self.dlogits), _p(wqkv_t), _p(wc_t), _p(ws), C.c_void_p(d_pool.ptr), d_pool.ld,
+                    n, hw, cch, heads, model.out_channels, C.c_float(self.LOSS_SCALE))
+        g = bw.scratch("gA", n, hh, ww, cch)
+        bw.gn_bwd(cur, st, em.f32("out.0.weight"), em.f32("out.0.bias"), d_pool, g, silu=True)
+        flip = 0
+        for entry in reversed(tape):
+            kind = entry[0]
+            if kind == "res":
+                _, r, x, st1, h1, st2, film_ptr, film_ld, o = entry
+                k = r.key
+                t1 = bw.scratch("t1", n, o.h, o.w, r.cout)
+                bw.conv(g, pack_conv3x3_bwd(em.P[f"{k}.out_layers.3.weight"]), None, r.cout, t1)
+                t2 = bw.scratch("t2", n, o.h, o.w, r.cout)
+                bw.gn_bwd(h1, st2, em.f32(f"{k}.out_layers.0.weight"), em.f32(f"{k}.out_layers.0.bias"), t1, t2,
+                          silu=True, film=film_ptr, film_ld=film_ld)
+                t3 = bw.scratch("t3", n, o.h, o.w, r.cin)
+                bw.conv(t2, pack_conv3x3_bwd(em.P[f"{k}.in_layers.2.weight"]), None, r.cin, t3)
+                if r.has_skip_conv:
+                    t4 = bw.scratch("t4", n, o.h, o.w, r.cin)
+                    bw.conv(g, pack_1x1_bwd(em.P[f"{k}.skip_connection.weight"]), None, r.cin, t4, taps=1)
+                    add, add_mode = t4, L.GN_SAME
+                else:
+                    add, add_mode = g, (L.GN_AVGPOOL2 if r.mode == "down" else L.GN_SAME)
+                if r.mode == "up":
+                    raise NotImplementedError("up ResBlock backward is not needed by the encoder classifier")
+                flip ^= 1
+                g_in = bw.scratch("gB" if flip else "gA", n, x.h, x.w, r.cin)
+                bw.gn_bwd(x, st1, em.f32(f"{k}.in_layers.0.weight"), em.f32(f"{k}.in_layers.0.bias"), t3, g_in,
+                          silu=True, mode=(L.GN_AVGPOOL2 if r.mode == "down" else L.GN_SAME), add=add,
+                          add_mode=add_mode)
+                g = g_in
+            elif kind == "attn":
+                _, a, x, st_a, qkv, att, lse, o = entry
+                k = a.key
+                d_att = bw.scratch("t1", n, x.h, x.w, a.ch)
+                bw.conv(g, pack_1x1_bwd(em.P[f"{k}.proj_out.weight"]), None, a.ch, d_att, taps=1)
+                dqkv = bw.scratch("t5", n, x.h, x.w, 3 * a.ch)
+                delta = th.empty((n, a.heads, x.h * x.w), dtype=th.float32, device=dev)
+                em.keep.append(delta)
+                order = L.QKV_NEW if a.new_order else L.QKV_LEGACY
+                bw.prog.add("gd_attention_bwd", C.c_void_p(qkv.ptr), qkv.ld, C.c_void_p(att.ptr), att.ld,
+                            C.c_void_p(d_att.ptr), d_att.ld, _p(lse), _p(delta), C.c_void_p(dqkv.ptr), dqkv.ld, n,
+                            x.h * x.w, a.heads, order)
+                d_a = bw.scratch("t2", n, x.h, x.w, a.ch)
+                bw.conv(dqkv, pack_1x1_bwd(em.P[f"{k}.qkv.weight"]), None, a.ch, d_a, taps=1)
+                flip ^= 1
+                g_in = bw.scratch("gB" if flip else "gA", n, x.h, x.w, a.ch)
+                bw.gn_bwd(x, st_a, em.f32(f"{k}.norm.weight"), em.f32(f"{k}.norm.bias"), d_a, g_in, silu=False, add=g,
+                          add_mode=L.GN_SAME)
+                g = g_in
+            else:  # conv_in: dX in fp32 NCHW, loss scale undone, user scale applied at run time by self.scale
+                _, l, o = entry
+                self._dx_desc_index = len(bw.prog.calls)
+                bw.conv(g, pack_conv3x3_bwd(em.P[f"{l.key}.weight"]), None, l.cin, self.dx, out_mode=L.OUT_NCHW_F32,
+                        out_scale=1.0 / self.LOSS_SCALE, geom=(n, o.h, o.w))
+        self.bwd = em.prog
+
+    # -- execution --------------------------------------------------------------------------------
+    def forward(self, x, timesteps) -> th.Tensor:
+        self.x_in.copy_(x)
+        self.t_in.copy_(timesteps)
+        self.fwd.run()
+        return self.logits
+
+    def backward(self, dlogits: th.Tensor) -> th.Tensor:
+        """dlogits: fp32 [n, classes] gradient w.r.t. the logits. Returns d/dx in fp32 NCHW (static buffer)."""
+        self.dlogits.copy_(dlogits)
+        self.bwd.run()
+        return self.dx
+
+    def guidance(self, x, timesteps, y, scale: float) -> th.Tensor:
+        """scale * d/dx sum_b log_softmax(classifier(x,t))[b, y_b]   (scripts/classifier_sample.py:54-61)."""
+        self.forward(x, timesteps)
+        stream = C.c_void_p(th.cuda.current_stream().cuda_stream)
+        yy = y.to(th.int64).contiguous()
+        L.check(L.load().gd_logsoftmax_select_bwd(_p(self.logits), _p(yy), _p(self.dlogits), self.n,
+                                                   self.logits.shape[1], C.c_float(float(scale)), stream),
+                "gd_logsoftmax_select_bwd")
+        self.bwd.run()
+        return self.dx
+
+
+class _ClassifierFn(th.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, timesteps, model):
+        n, c, h, w = x.shape
+        plan = model.plan(n, h, w, x.device)
+        ctx.plan = plan
+        return plan.forward(x.detach(), timesteps).clone()
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        return ctx.plan.backward(dlogits.float().contiguous()).clone(), None, None
+
+
+def classifier_apply(model, x: th.Tensor, timesteps: th.Tensor) -> th.Tensor:
+    _require_cuda(x.device)
+    if x.requires_grad and th.is_grad_enabled():
+        return _ClassifierFn.apply(x, timesteps, model)
+    n, c, h, w = x.shape
+    return model.plan(n, h, w, x.device).forward(x, timesteps).clone()

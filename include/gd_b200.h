@@ -85,10 +85,12 @@ int gd_groupnorm_apply(const void* x, int32_t ld, const float* mean_rstd, const 
                        int32_t c, int32_t silu, int32_t spatial_mode, void* stream);
 /* Backward of the fused op above w.r.t. x (no parameter gradients; the guidance gradient needs dX only).
  * dy is at the OUTPUT resolution of the forward op; dx (fp16 view, input resolution) = result (+ add if given). */
+/* add_mode: GD_GN_SAME = add is at dx's resolution; GD_GN_AVGPOOL2 = add is the gradient of an avg-pooled copy of x
+ * (x_upd of a down ResBlock, unet.py:195,241) living at half resolution: dx += add[y/2,x/2] / 4. */
 int gd_groupnorm_bwd(const void* x, int32_t ld, const float* mean_rstd, const float* gamma, const float* beta,
                      const float* film, int32_t film_ld, const void* dy, int32_t ld_dy, const void* add, int32_t ld_add,
-                     void* dx, int32_t ld_dx, float* partial_ws, int32_t n, int32_t h, int32_t w, int32_t c,
-                     int32_t silu, int32_t spatial_mode, void* stream);
+                     int32_t add_mode, void* dx, int32_t ld_dx, float* partial_ws, int32_t n, int32_t h, int32_t w,
+                     int32_t c, int32_t silu, int32_t spatial_mode, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused attention, head dim 64: out[n,t,head*64+j] = sum_s softmax_s(q_t.k_s / 8) v_s  (fp32 softmax).
@@ -135,7 +137,8 @@ int gd_logsoftmax_select_bwd(const float* logits, const int64_t* y, float* dlogi
 /* ------------------------------------------------------------------------------------------------
  * Fused posterior / noise update, one launch per sampling step (gaussian_diffusion.py:232-326, 356-393,
  * 395-439, 546-594).  All tensors fp32 NCHW [n,3,h,w] except model_out [n,6 or 3,h,w].
- * coef: device fp32 table [T'][GD_COEF_STRIDE]; step_idx: device int32 scalar selecting the row.
+ * coef: device fp32 table [T'][GD_COEF_STRIDE]; t: device int64 [n], the (respaced) timestep index of each
+ * sample selecting the row.  noise == NULL computes p_mean_variance only (mean/var/logvar/pred_xstart).
  * ---------------------------------------------------------------------------------------------- */
 enum {
   GD_COEF_SQRT_RECIP_ACP = 0,   /* sqrt_recip_alphas_cumprod      gaussian_diffusion.py:150 */
@@ -157,11 +160,14 @@ typedef struct gd_posterior_desc {
   const float* x;         /* x_t */
   const float* model_out; /* eps (and v) */
   const float* grad;      /* cond_fn output (already scaled) or NULL */
-  const float* noise;     /* z */
+  const float* noise;     /* z, or NULL */
   float* sample;          /* x_{t-1} (may alias x) */
   float* pred_xstart;     /* may be NULL */
+  float* mean_out;        /* optional p_mean_variance outputs (pre-guidance), may be NULL */
+  float* var_out;
+  float* logvar_out;
   const float* coef;
-  const int32_t* step_idx;
+  const int64_t* t;
   int32_t n, c, hw;
   int32_t var_type, mean_type, clip_denoised;
   int32_t ddim;

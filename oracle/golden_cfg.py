@@ -1,0 +1,124 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  Shared definition of the golden cases: configurations, seeds and
+input generators used both by oracle/make_golden.py (which runs the reference) and by the tests."""
+from __future__ import annotations
+
+import torch as th
+
+IMAGE = 64
+UNET_SEED, CLF_SEED, INPUT_SEED, STEP_SEED, STEP_NOISE_SEED, TRAJ_SEED = 11, 12, 13, 14, 15, 16
+CLF_SCALE = 1.0
+TRAJ_BATCH = 2
+
+# tiny class-conditional ADM: 64 -> 128 -> 192 -> 256 channels, attention at 16x16 and 8x8 (new order)
+UNET_KW = dict(image_size=IMAGE, num_channels=64, num_res_blocks=1, channel_mult="", learn_sigma=True,
+               class_cond=True, use_checkpoint=False, attention_resolutions="16,8", num_heads=4, num_head_channels=64,
+               num_heads_upsample=-1, use_scale_shift_norm=True, dropout=0.0, resblock_updown=True, use_fp16=False,
+               use_new_attention_order=True)
+UNET_STRUCT = dict(num_res_blocks=1, channel_mult_len=4, head_dim=64, new_order=True)
+
+# tiny classifier: width 64, depth 1, legacy attention at 16x16 and 8x8, attention pool over 8x8 (+1) tokens
+CLASSIFIER_KW = dict(image_size=IMAGE, classifier_use_fp16=False, classifier_width=64, classifier_depth=1,
+                     classifier_attention_resolutions="16,8", classifier_use_scale_shift_norm=True,
+                     classifier_resblock_updown=True, classifier_pool="attention")
+CLF_STRUCT = dict(num_res_blocks=1, channel_mult_len=4, head_dim=64)
+
+
+def ref_unet_kwargs():
+    """Constructor kwargs of the upstream-semantics reference unet.UNetModel for UNET_KW."""
+    return dict(image_size=IMAGE, in_channels=3, model_channels=64, out_channels=6, num_res_blocks=1,
+                attention_resolutions=(4, 8), dropout=0.0, channel_mult=(1, 2, 3, 4), num_classes=1000,
+                use_checkpoint=False, use_fp16=False, num_heads=4, num_head_channels=64, num_heads_upsample=-1,
+                use_scale_shift_norm=True, resblock_updown=True, use_new_attention_order=True)
+
+
+def model_inputs():
+    g = th.Generator().manual_seed(INPUT_SEED)
+    x = th.randn(2, 3, IMAGE, IMAGE, generator=g)
+    t = th.tensor([37, 961])
+    y = th.tensor([3, 977])
+    return x, t, y
+
+
+def traj_labels():
+    return th.tensor([5, 640])
+
+
+SPACE_CASES = [(1000, "25"), (1000, "250"), (1000, "ddim25"), (1000, "ddim50"), (1000, "50"), (1000, "100"),
+               (300, "10,15,20"), (1000, "1000"), (1000, "1"), (1000, "ddim1000"), (4000, "250"), (1000, "10"),
+               (1000, "3,1,7"), (7, "7"), (1000, "ddim4"), (1000, "4"), (1000, "ddim7"), (1000, "3")]
+SPACE_ERRORS = [(1000, "ddim999"), (10, "20"), (30, "5,20,5")]
+
+_LIN250 = dict(steps=1000, learn_sigma=True, noise_schedule="linear", timestep_respacing="250")
+DIFFUSION_CASES = {
+    "linear_250_learned": _LIN250,
+    "cosine_25_learned": dict(steps=1000, learn_sigma=True, noise_schedule="cosine", timestep_respacing="25"),
+    "linear_ddim50_fixed": dict(steps=1000, learn_sigma=False, noise_schedule="linear", timestep_respacing="ddim50"),
+    "linear_full_small": dict(steps=1000, learn_sigma=False, sigma_small=True, noise_schedule="linear"),
+    "linear_10_rescaled": dict(steps=1000, learn_sigma=True, noise_schedule="linear", timestep_respacing="10",
+                               rescale_timesteps=True),
+    "cosine_4000_ddim25_xstart": dict(steps=4000, learn_sigma=True, noise_schedule="cosine",
+                                      timestep_respacing="ddim25", predict_xstart=True),
+}
+
+# per-step arithmetic cases: (diffusion kwargs, ddim?, eta, guided?, step index)
+STEP_CASES = {
+    "ddpm_guided_mid": dict(diffusion=_LIN250, ddim=False, eta=0.0, guided=True, index=125),
+    "ddpm_guided_t0": dict(diffusion=_LIN250, ddim=False, eta=0.0, guided=True, index=0),
+    "ddpm_plain_last": dict(diffusion=_LIN250, ddim=False, eta=0.0, guided=False, index=249),
+    "ddpm_fixed_large": dict(diffusion=DIFFUSION_CASES["linear_ddim50_fixed"], ddim=False, eta=0.0, guided=False,
+                             index=17),
+    "ddpm_fixed_small": dict(diffusion=DIFFUSION_CASES["linear_full_small"], ddim=False, eta=0.0, guided=True,
+                             index=500),
+    "ddim_guided_eta0": dict(diffusion=DIFFUSION_CASES["linear_ddim50_fixed"], ddim=True, eta=0.0, guided=True,
+                             index=30),
+    "ddim_plain_eta1": dict(diffusion=DIFFUSION_CASES["cosine_25_learned"], ddim=True, eta=1.0, guided=False,
+                            index=12),
+    "ddim_xstart_t0": dict(diffusion=DIFFUSION_CASES["cosine_4000_ddim25_xstart"], ddim=True, eta=0.5, guided=True,
+                           index=0),
+}
+
+
+def step_inputs(name: str):
+    kw = STEP_CASES[name]
+    g = th.Generator().manual_seed(STEP_SEED + sorted(STEP_CASES).index(name))
+    learn = kw["diffusion"].get("learn_sigma", False)
+    xs = th.randn(2, 3, 8, 8, generator=g)
+    mo = th.randn(2, 6 if learn else 3, 8, 8, generator=g)
+    grad = 0.3 * th.randn(2, 3, 8, 8, generator=g)
+    return xs, mo, grad, kw["index"]
+
+
+_TR = dict(steps=1000, learn_sigma=True, noise_schedule="linear")
+TRAJ_CASES = {
+    "ddpm_guided_4": dict(diffusion=dict(_TR, timestep_respacing="4"), ddim=False, guided=True),
+    "ddim_guided_4": dict(diffusion=dict(_TR, timestep_respacing="ddim4"), ddim=True, guided=True),
+    "ddpm_plain_3": dict(diffusion=dict(_TR, timestep_respacing="3"), ddim=False, guided=False),
+}
+
+
+# ---- full-size configurations of BASELINE.json (layout hashes only; built on the meta device) --------
+UNET256_KW = dict(image_size=256, num_channels=256, num_res_blocks=2, channel_mult="", learn_sigma=True,
+                  class_cond=True, use_checkpoint=False, attention_resolutions="32,16,8", num_heads=4,
+                  num_head_channels=64, num_heads_upsample=-1, use_scale_shift_norm=True, dropout=0.0,
+                  resblock_updown=True, use_fp16=True, use_new_attention_order=False)
+CLF256_KW = dict(image_size=256, classifier_use_fp16=False, classifier_width=128, classifier_depth=2,
+                 classifier_attention_resolutions="32,16,8", classifier_use_scale_shift_norm=True,
+                 classifier_resblock_updown=True, classifier_pool="attention")
+SR512_KW = dict(large_size=512, small_size=128, num_channels=192, num_res_blocks=2, learn_sigma=True,
+                class_cond=True, use_checkpoint=False, attention_resolutions="32,16", num_heads=4,
+                num_head_channels=64, num_heads_upsample=-1, use_scale_shift_norm=True, dropout=0.0,
+                resblock_updown=True, use_fp16=True)
+
+
+def ref_unet256_kwargs():
+    return dict(image_size=256, in_channels=3, model_channels=256, out_channels=6, num_res_blocks=2,
+                attention_resolutions=(8, 16, 32), dropout=0.0, channel_mult=(1, 1, 2, 2, 4, 4), num_classes=1000,
+                use_checkpoint=False, use_fp16=True, num_heads=4, num_head_channels=64, num_heads_upsample=-1,
+                use_scale_shift_norm=True, resblock_updown=True, use_new_attention_order=False)
+
+
+def ref_sr512_kwargs():
+    return dict(image_size=512, in_channels=3, model_channels=192, out_channels=6, num_res_blocks=2,
+                attention_resolutions=(16, 32), dropout=0.0, channel_mult=(1, 1, 2, 2, 4, 4), num_classes=1000,
+                use_checkpoint=False, use_fp16=True, num_heads=4, num_head_channels=64, num_heads_upsample=-1,
+                use_scale_shift_norm=True, resblock_updown=True)

@@ -1,0 +1,26 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="session")
+def lib():
+    """The C-ABI library; built in-tree if missing (nvcc cross-compiles without a GPU)."""
+    from guided_diffusion_clip_b200 import _build, _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        _build.build()
+    return _lib.load()

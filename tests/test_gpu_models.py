@@ -1,0 +1,195 @@
+"""GPU parity of the whole path against the reference golden vectors (tests/golden, produced by the real
+reference in oracle/make_golden.py) and against the CPU oracle on the same seeded weights and inputs.
+
+Stated tolerance (BASELINE.json north_star): max-abs error relative to the reference's max-abs <= 2e-2 for
+per-step model outputs, the guidance gradient and short trajectories (fp16 storage vs the fp32 reference);
+integer outputs (timestep maps, uint8 images up to the rounding boundary, sharding order) bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch as th
+import torch.nn.functional as F
+
+from guided_diffusion_clip_b200 import script_util as su
+from guided_diffusion_clip_b200.sampler import ClassifierGuidance, GraphedStepper, ModelFn
+from oracle import golden_cfg as cfg
+from oracle import oracle_diffusion as od
+from oracle import oracle_models as om
+from tests import gpu_helpers as H
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-2
+
+
+@pytest.fixture(scope="module")
+def G(golden_dir):
+    return np.load(os.path.join(golden_dir, "models_golden.npz"))
+
+
+def _load(model, seed):
+    sd = om.make_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed)
+    model.load_state_dict(sd, strict=True)
+    return sd
+
+
+@pytest.fixture(scope="module")
+def unet():
+    m = su.create_model(**cfg.UNET_KW)
+    sd = _load(m, cfg.UNET_SEED)
+    return m.cuda().eval(), sd
+
+
+@pytest.fixture(scope="module")
+def clf():
+    m = su.create_classifier(**cfg.CLASSIFIER_KW)
+    sd = _load(m, cfg.CLF_SEED)
+    return m.cuda().eval(), sd
+
+
+def test_unet_forward_matches_reference(lib, G, unet):
+    model, _ = unet
+    x, t, y = (v.cuda() for v in cfg.model_inputs())
+    with th.no_grad():
+        out = model(x, t, y)
+    ref = th.from_numpy(G["unet_out"]).cuda()
+    err = H.rel_err(out, ref)
+    print(f"tiny UNet fwd vs reference golden: rel err {err:.3e} (ref max {float(ref.abs().max()):.3f})")
+    assert out.shape == ref.shape and out.dtype == th.float32
+    assert err < TOL
+
+
+def test_unet_fp16_converted_matches_reference(lib, G):
+    """use_fp16=True + convert_to_fp16() (both required by the reference, unet.py:465,619) stays within tolerance."""
+    m = su.create_model(**dict(cfg.UNET_KW, use_fp16=True))
+    _load(m, cfg.UNET_SEED)
+    m.cuda()
+    m.convert_to_fp16()
+    assert m.dtype == th.float16
+    sd = m.state_dict()
+    assert sd["input_blocks.1.0.in_layers.2.weight"].dtype == th.float16   # torso conv
+    assert sd["input_blocks.1.0.emb_layers.1.weight"].dtype == th.float32  # Linear stays fp32 (fp16_util.py:15-22)
+    assert sd["out.2.weight"].dtype == th.float32                          # out head is not in the torso
+    x, t, y = (v.cuda() for v in cfg.model_inputs())
+    with th.no_grad():
+        out = m(x, t, y)
+    assert H.rel_err(out, th.from_numpy(G["unet_out"]).cuda()) < TOL
+
+
+def test_classifier_logits_and_reference_closure_gradient(lib, G, clf):
+    """The reference's own cond_fn closure (scripts/classifier_sample.py:54-61), verbatim, on our classifier."""
+    classifier, _ = clf
+    x, t, y = (v.cuda() for v in cfg.model_inputs())
+    with th.no_grad():
+        logits = classifier(x, t)
+    err = H.rel_err(logits, th.from_numpy(G["clf_logits"]).cuda())
+    print(f"classifier logits rel err {err:.3e}")
+    assert err < TOL
+
+    def cond_fn(x, t, y=None):
+        assert y is not None
+        with th.enable_grad():
+            x_in = x.detach().requires_grad_(True)
+            logits = classifier(x_in, t)
+            log_probs = F.log_softmax(logits, dim=-1)
+            selected = log_probs[range(len(logits)), y.view(-1)]
+            return th.autograd.grad(selected.sum(), x_in)[0] * cfg.CLF_SCALE
+
+    g = cond_fn(x, t, y=y)
+    ref = th.from_numpy(G["clf_grad"]).cuda()
+    err = H.rel_err(g, ref)
+    print(f"guidance gradient (autograd closure) rel err {err:.3e} (ref max {float(ref.abs().max()):.3e})")
+    assert err < TOL
+    g2 = ClassifierGuidance(classifier, cfg.CLF_SCALE)(x, t, y=y)
+    err2 = H.rel_err(g2, ref)
+    print(f"guidance gradient (fused object) rel err {err2:.3e}")
+    assert err2 < TOL
+
+
+def _cuda_noise_like_loop(shape, steps, seed):
+    """Replay the RNG draws of the sampling loop on the CUDA generator: randn(shape) then one randn_like per step."""
+    th.manual_seed(seed)
+    init = th.randn(*shape, device="cuda")
+    return init, [th.randn_like(init) for _ in range(steps)]
+
+
+@pytest.mark.parametrize("name", sorted(cfg.TRAJ_CASES))
+@pytest.mark.parametrize("graph", [False, True])
+def test_short_trajectory_matches_oracle(lib, unet, clf, name, graph, monkeypatch):
+    """p_sample_loop / ddim_sample_loop end to end (3-4 respaced steps, guided and unguided) vs the CPU oracle fed the
+    SAME noise (CUDA and CPU generators differ), through both the eager and CUDA-graph paths."""
+    monkeypatch.setenv("GD_B200_NO_GRAPH", "0" if graph else "1")
+    kw = cfg.TRAJ_CASES[name]
+    model, usd = unet
+    classifier, csd = clf
+    d = su.create_gaussian_diffusion(**kw["diffusion"])
+    shape = (cfg.TRAJ_BATCH, 3, cfg.IMAGE, cfg.IMAGE)
+    y = cfg.traj_labels()
+    init, zs = _cuda_noise_like_loop(shape, d.num_timesteps, 77)
+    # ---- oracle on CPU with that noise
+    tab = od.Tables(schedule=kw["diffusion"]["noise_schedule"], steps=kw["diffusion"]["steps"],
+                    respacing=kw["diffusion"]["timestep_respacing"], learn_sigma=True)
+    assert tab.timestep_map == d.timestep_map
+    img = init.cpu()
+    with th.no_grad():
+        for k, i in enumerate(reversed(range(tab.T))):
+            tt = th.full((shape[0],), tab.timestep_map[i])
+            mo = om.unet_forward(usd, img, tt, y, **cfg.UNET_STRUCT)
+            g = om.classifier_guidance(csd, img, tt, y, cfg.CLF_SCALE, **cfg.CLF_STRUCT) if kw["guided"] else None
+            z = zs[k].cpu()
+            r = tab.ddim_sample(mo, img, i, z, g) if kw["ddim"] else tab.p_sample(mo, img, i, z, g)
+            img = r["sample"]
+    # ---- ours
+    th.manual_seed(77)
+    fn = d.ddim_sample_loop if kw["ddim"] else d.p_sample_loop
+    cond = ClassifierGuidance(classifier, cfg.CLF_SCALE) if kw["guided"] else None
+    got = fn(ModelFn(model, True), shape, model_kwargs={"y": y.cuda()}, cond_fn=cond, device="cuda")
+    err = H.rel_err(got, img.cuda())
+    print(f"trajectory {name} graph={graph}: rel err {err:.3e}")
+    assert err < TOL
+    from guided_diffusion_clip_b200.dist_util import to_uint8_nhwc
+    u8 = to_uint8_nhwc(got).cpu()
+    ref_u8 = od.to_uint8_nhwc(img)
+    assert (u8.int() - ref_u8.int()).abs().max() <= 3  # 2e-2 * 127.5
+
+
+def test_graph_and_eager_paths_are_bitwise_identical(lib, unet, clf, monkeypatch):
+    model, _ = unet
+    classifier, _ = clf
+    d = su.create_gaussian_diffusion(steps=1000, learn_sigma=True, noise_schedule="linear", timestep_respacing="3")
+    shape = (2, 3, cfg.IMAGE, cfg.IMAGE)
+    y = cfg.traj_labels().cuda()
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("GD_B200_NO_GRAPH", flag)
+        th.manual_seed(5)
+        outs.append(d.p_sample_loop(ModelFn(model, True), shape, model_kwargs={"y": y},
+                                    cond_fn=ClassifierGuidance(classifier, 1.0), device="cuda"))
+    assert th.equal(outs[0], outs[1])
+
+
+def test_loop_passes_original_timesteps_to_model_and_cond_fn(lib):
+    """respace.py wraps BOTH callables: with respacing "10" they must see t = 999, 888, ..., 111, 0."""
+    d = su.create_gaussian_diffusion(steps=1000, learn_sigma=True, timestep_respacing="10")
+    seen_m, seen_c = [], []
+
+    def model(x, t, **kw):
+        seen_m.append(int(t[0]))
+        return th.zeros(x.shape[0], 6, *x.shape[2:], device=x.device)
+
+    def cond(x, t, **kw):
+        seen_c.append(int(t[0]))
+        return th.zeros_like(x)
+
+    out = d.p_sample_loop(model, (2, 3, 8, 8), cond_fn=cond, model_kwargs={}, device="cuda")
+    assert seen_m == seen_c == [999, 888, 777, 666, 555, 444, 333, 222, 111, 0]
+    assert out.shape == (2, 3, 8, 8) and th.isfinite(out).all()
+
+
+def test_cpu_tensors_fail_loudly(lib, unet):
+    model, _ = unet
+    from guided_diffusion_clip_b200._lib import GdError
+    x, t, y = cfg.model_inputs()
+    cpu_model = su.create_model(**cfg.UNET_KW)
+    with pytest.raises(GdError):
+        cpu_model(x, t, y)

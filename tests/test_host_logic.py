@@ -1,0 +1,202 @@
+"""CPU: the product's host-side logic against the reference golden vectors — respaced timestep sets / maps
+(bit-exact integers), float64 tables, factory defaults, state_dict layout — plus the C-ABI surface:
+libgd_b200.so loads, exports every symbol include/gd_b200.h declares, validates arguments without a GPU and
+the package refuses to compute on CPU tensors (no fallback)."""
+import ctypes
+import hashlib
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch as th
+
+from guided_diffusion_clip_b200 import gaussian_diffusion as gd
+from guided_diffusion_clip_b200 import respace
+from guided_diffusion_clip_b200 import script_util as su
+from oracle import golden_cfg as cfg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def J(golden_dir):
+    with open(os.path.join(golden_dir, "diffusion_golden.json")) as f:
+        return json.load(f)
+
+
+def test_space_timesteps_bit_exact(J):
+    for key, want in J["space_timesteps"].items():
+        T, spec = key.split("|")
+        got = respace.space_timesteps(int(T), spec)
+        assert isinstance(got, set) and sorted(got) == want, key
+    assert sorted(respace.space_timesteps(300, [10, 15, 20])) == J["space_timesteps"]["300|10,15,20"]
+    for key, msg in J["errors"].items():
+        T, spec = key.split("|")
+        with pytest.raises(ValueError) as e:
+            respace.space_timesteps(int(T), spec)
+        assert str(e.value) == msg
+
+
+def test_survey_appendix_c_vectors():
+    def h(xs):
+        return hashlib.sha256(np.array(sorted(xs), dtype="<i8").tobytes()).hexdigest()[:16]
+    assert h(respace.space_timesteps(1000, "25")) == "e22cac1bf1562a06"
+    assert h(respace.space_timesteps(1000, "250")) == "d802631b9565348c"
+    assert h(respace.space_timesteps(1000, "ddim25")) == "5ac9828e4fbaa105"
+    assert h(respace.space_timesteps(1000, "ddim50")) == "ebc60f0baaa7a6bc"
+    assert h(respace.space_timesteps(1000, "50")) == "c5bdf9b959c7973b"
+    assert h(respace.space_timesteps(1000, "100")) == "432f07a847b37dff"
+    assert h(respace.space_timesteps(300, "10,15,20")) == "9293baff71d3533b"
+
+
+def test_diffusion_tables_and_maps_bit_exact(J):
+    for name, kw in cfg.DIFFUSION_CASES.items():
+        d = su.create_gaussian_diffusion(**kw)
+        g = J["tables"][name]
+        assert d.timestep_map == J["maps"][name]
+        assert d.num_timesteps == g["num_timesteps"]
+        assert d.model_mean_type.name == g["model_mean_type"] and d.model_var_type.name == g["model_var_type"]
+        assert d.loss_type.name == g["loss_type"] and bool(d.rescale_timesteps) == g["rescale_timesteps"]
+        for key in ("betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_recip_alphas_cumprod",
+                    "sqrt_recipm1_alphas_cumprod", "posterior_variance", "posterior_log_variance_clipped",
+                    "posterior_mean_coef1", "posterior_mean_coef2"):
+            a, b = getattr(d, key), np.array(g[key], dtype=np.float64)
+            assert a.dtype == np.float64 and np.array_equal(a, b), (name, key)  # same float64 bits
+        tab = d.coef_table()
+        assert tab.dtype == np.float32 and tab.shape == (d.num_timesteps, 12)
+        assert tab[0, 10] == 0.0 and (tab[1:, 10] == 1.0).all()
+
+
+def test_factory_defaults_match_reference(J):
+    D = J["defaults"]
+    assert su.diffusion_defaults() == D["diffusion_defaults"]
+    assert su.classifier_defaults() == D["classifier_defaults"]
+    assert su.model_and_diffusion_defaults() == D["model_and_diffusion_defaults"]
+    assert su.sr_model_and_diffusion_defaults() == D["sr_model_and_diffusion_defaults"]
+    assert su.NUM_CLASSES == 512
+    assert su.str2bool("yes") and not su.str2bool("0")
+
+
+def test_wrapped_model_maps_and_rescales():
+    d = su.create_gaussian_diffusion(steps=1000, learn_sigma=True, timestep_respacing="10", rescale_timesteps=True)
+    seen = {}
+    w = d._wrap(lambda x, t, **kw: seen.setdefault("t", t))
+    w(None, th.tensor([9, 0, 3]))
+    assert seen["t"].dtype == th.float32 and seen["t"].tolist() == [999.0, 0.0, 333.0]
+    assert d._wrap(w) is w
+    d2 = su.create_gaussian_diffusion(steps=4000, learn_sigma=True, timestep_respacing="ddim25")
+    got = {}
+    d2._wrap(lambda x, t, **kw: got.setdefault("t", t))(None, th.tensor([24, 1]))
+    assert got["t"].dtype == th.int64 and got["t"].tolist() == [3840, 160]
+
+
+def _layout_hash(sd):
+    h = hashlib.sha256()
+    for k, v in sd.items():
+        h.update(f"{k}:{tuple(v.shape)};".encode())
+    return h.hexdigest()[:16], len(sd)
+
+
+def test_state_dict_layout_matches_reference(J):
+    """Key names, order and shapes of SURVEY App. E; hashes recorded from the reference modules by make_golden.py."""
+    L = J["layouts"]
+    m = su.create_model(**cfg.UNET_KW)
+    assert list(_layout_hash(m.state_dict())) == L["unet_tiny"]
+    c = su.create_classifier(**cfg.CLASSIFIER_KW)
+    assert list(_layout_hash(c.state_dict())) == L["clf_tiny"]
+    with th.device("meta"):
+        m256 = su.create_model(**cfg.UNET256_KW)
+        c256 = su.create_classifier(**cfg.CLF256_KW)
+        sr = su.sr_create_model(**cfg.SR512_KW)
+    assert list(_layout_hash(m256.state_dict())) == L["unet_256"] and len(m256.state_dict()) == 567
+    assert list(_layout_hash(c256.state_dict())) == L["clf_256"] and len(c256.state_dict()) == 249
+    assert list(_layout_hash(sr.state_dict())) == L["sr_512"]
+    assert sum(p.numel() for p in m256.parameters()) == L["unet_256_params"]
+
+
+def test_zero_modules_and_fp16_conversion():
+    m = su.create_model(**cfg.UNET_KW)
+    sd = m.state_dict()
+    assert float(sd["out.2.weight"].abs().max()) == 0.0                       # unet.py:616
+    assert float(sd["input_blocks.1.0.out_layers.3.weight"].abs().max()) == 0  # unet.py:210
+    assert float(sd["middle_block.1.proj_out.weight"].abs().max()) == 0        # unet.py:294
+    m.convert_to_fp16()
+    sd = m.state_dict()
+    assert sd["middle_block.1.qkv.weight"].dtype == th.float16
+    assert sd["middle_block.0.in_layers.0.weight"].dtype == th.float32   # GroupNorm stays fp32
+    assert sd["time_embed.0.weight"].dtype == th.float32
+    m.convert_to_fp32()
+    assert m.state_dict()["middle_block.1.qkv.weight"].dtype == th.float32
+
+
+def test_unsupported_configurations_raise():
+    with pytest.raises(NotImplementedError):
+        su.create_model(64, 64, 1, resblock_updown=False, num_head_channels=64)
+    with pytest.raises(ValueError):
+        su.create_model(96, 64, 1)
+    with pytest.raises(NotImplementedError):
+        from guided_diffusion_clip_b200.unet import EncoderUNetModel
+        EncoderUNetModel(64, 3, 64, 10, 1, (4,), num_head_channels=64, resblock_updown=True, pool="adaptive")
+
+
+# ------------------------------------------------------------------------------------------------ C ABI
+def _declared_symbols():
+    with open(os.path.join(ROOT, "include", "gd_b200.h")) as f:
+        src = f.read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gd_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from guided_diffusion_clip_b200 import _lib
+    names = _declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/gd_b200.h but not exported"
+    assert sorted(_lib.SIGNATURES) == names  # the ctypes binding covers exactly the header
+    assert lib.gd_version() == 1
+
+
+def test_abi_validates_arguments_without_gpu(lib):
+    from guided_diffusion_clip_b200 import _lib
+    d = _lib.ConvDesc()
+    assert lib.gd_conv_igemm(d, None) == -1
+    assert b"null tensor pointer" in lib.gd_last_error()
+    d.a0 = d.wpack = d.out = 16
+    d.taps, d.c0, d.ld0 = 9, 48, 48
+    assert lib.gd_conv_igemm(d, None) == -1 and b"multiple of 64" in lib.gd_last_error()
+    assert lib.gd_attention_fwd(ctypes.c_void_p(16), 192, ctypes.c_void_p(16), 64, None, 1, 65, 1, 0, None) == -1
+    assert b"multiple of 64" in lib.gd_last_error()
+    assert lib.gd_groupnorm_stats(ctypes.c_void_p(16), 48, 1, 4, 48, ctypes.c_float(1e-5), ctypes.c_void_p(16),
+                                  ctypes.c_void_p(16), None) == -1
+    assert b"multiple of 32" in lib.gd_last_error()
+    p = _lib.PosteriorDesc()
+    assert lib.gd_posterior_step(p, None) == -1
+    assert lib.gd_groupnorm_ws_floats(8, 1, 32) == 8 * 129 * 64
+
+
+def test_no_cpu_fallback():
+    from guided_diffusion_clip_b200._lib import GdError
+    m = su.create_model(**cfg.UNET_KW)
+    x, t, y = cfg.model_inputs()
+    with pytest.raises(GdError):
+        m(x, t, y)
+    d = su.create_gaussian_diffusion(steps=1000, learn_sigma=True, timestep_respacing="4")
+    with pytest.raises(GdError):
+        d.p_sample(lambda x, t, **k: th.zeros(2, 6, 8, 8), th.zeros(2, 3, 8, 8), th.tensor([1, 1]), model_kwargs={})
+    c = su.create_classifier(**cfg.CLASSIFIER_KW)
+    with pytest.raises(GdError):
+        c(x, t)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "guided_diffusion_clip_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                with open(os.path.join(dirpath, fn)) as f:
+                    src = f.read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
+                assert "/root/reference" not in src, fn
