@@ -248,6 +248,12 @@ class GaussianDiffusion:
             raise NotImplementedError("denoised_fn is a Python hook inside the fused update; not supported")
         x = x.float().contiguous()
         t = t.to(th.int64).contiguous()
+        # fast path: our own UNet (+ our own guidance object) -> the whole step is one CUDA-graph replay
+        from .sampler import GraphedStepper
+        stepper = GraphedStepper.cached(self, model, cond_fn, tuple(x.shape), x.device, model_kwargs, clip_denoised,
+                                        ddim, eta)
+        if stepper is not None:
+            return stepper.step(x, t, noise=noise, labels=(model_kwargs or {}).get("y"))
         model_out = self._call_model(model, x, t, model_kwargs)
         if noise is None:
             noise = th.randn_like(x)
@@ -286,19 +292,11 @@ class GaussianDiffusion:
         if progress:
             from tqdm.auto import tqdm
             indices = tqdm(indices)
-        # fast path: our own UNet + our own guidance object -> whole step is one CUDA-graph replay
-        from .sampler import GraphedStepper
-        stepper = GraphedStepper.maybe_create(self, model, cond_fn, shape, device, model_kwargs, clip_denoised, ddim,
-                                              eta)
         t = th.empty((shape[0],), dtype=th.int64, device=device)
         for i in indices:
             t.fill_(i)
             with th.no_grad():
-                if stepper is not None:
-                    out = stepper.step(img, t)
-                else:
-                    out = self._sample_step(model, img, t, clip_denoised, denoised_fn, cond_fn, model_kwargs, ddim,
-                                            eta)
+                out = self._sample_step(model, img, t, clip_denoised, denoised_fn, cond_fn, model_kwargs, ddim, eta)
                 yield out
                 img = out["sample"]
 

@@ -51,6 +51,26 @@ class GraphedStepper:
     """One sampling step as a single CUDA-graph replay (only for our own model / guidance objects)."""
 
     @staticmethod
+    def cached(diffusion, model, cond_fn, shape, device, model_kwargs, clip_denoised, ddim, eta):
+        """Stepper for this (diffusion, model, guidance, shape) or None when the fast path does not apply.
+        Cached on the diffusion object; invalidated when either model's parameters change."""
+        if os.environ.get("GD_B200_NO_GRAPH", "0") == "1" or th.device(device).type != "cuda":
+            return None
+        m = model.model if isinstance(model, ModelFn) else model
+        if type(m) is not UNetModel:
+            return None
+        if cond_fn is not None and not isinstance(cond_fn, ClassifierGuidance):
+            return None
+        key = (id(m), m._param_version, getattr(model, "class_cond", True),
+               (id(cond_fn.classifier), cond_fn.classifier._param_version, cond_fn.classifier_scale) if cond_fn else None,
+               tuple(shape), str(device), bool(clip_denoised), bool(ddim), float(eta))
+        cache = diffusion.__dict__.setdefault("_steppers", {})
+        if key not in cache:
+            cache[key] = GraphedStepper.maybe_create(diffusion, model, cond_fn, shape, device, model_kwargs,
+                                                     clip_denoised, ddim, eta)
+        return cache[key]
+
+    @staticmethod
     def maybe_create(diffusion, model, cond_fn, shape, device, model_kwargs, clip_denoised, ddim, eta):
         if os.environ.get("GD_B200_NO_GRAPH", "0") == "1":
             return None
@@ -92,6 +112,7 @@ class GraphedStepper:
         self.sample = th.empty(shape, dtype=th.float32, device=dev)
         self.x0 = th.empty(shape, dtype=th.float32, device=dev)
         self.y = y.to(device=dev, dtype=th.int64).contiguous().clone() if isinstance(y, th.Tensor) else None
+        self.uses_y = uses_y
         if uses_y:
             self.unet.cond_in.copy_(self.y)
         self.map = diffusion.map_tensor(dev) if hasattr(diffusion, "map_tensor") else None
@@ -137,7 +158,12 @@ class GraphedStepper:
             n += self.clf.fwd.launches + self.clf.bwd.launches + 1
         return n
 
-    def step(self, img: th.Tensor, t: th.Tensor, noise: Optional[th.Tensor] = None):
+    def step(self, img: th.Tensor, t: th.Tensor, noise: Optional[th.Tensor] = None,
+             labels: Optional[th.Tensor] = None):
+        if labels is not None and self.y is not None:
+            self.y.copy_(labels)
+            if self.uses_y:
+                self.unet.cond_in.copy_(self.y)
         self.unet.x_in.copy_(img)
         self.t_idx.copy_(t)
         if noise is None:

@@ -122,3 +122,20 @@ def ref_sr512_kwargs():
                 attention_resolutions=(16, 32), dropout=0.0, channel_mult=(1, 1, 2, 2, 4, 4), num_classes=1000,
                 use_checkpoint=False, use_fp16=True, num_heads=4, num_head_channels=64, num_heads_upsample=-1,
                 use_scale_shift_norm=True, resblock_updown=True)
+
+
+# well-conditioned 10-step prefixes of the real chains (north_star: "short 10-step trajectories"): the first 10
+# reverse steps of the 250-step ancestral chain and of the 50-step DDIM chain, classifier-guided
+TRAJ10_STEPS = 10
+TRAJ10_CASES = {
+    "ddpm250_guided": dict(diffusion=dict(_TR, timestep_respacing="250"), ddim=False, guided=True),
+    "ddim50_guided": dict(diffusion=dict(_TR, timestep_respacing="ddim50"), ddim=True, guided=True),
+    "ddpm250_plain": dict(diffusion=dict(_TR, timestep_respacing="250"), ddim=False, guided=False),
+}
+
+
+def traj10_noise():
+    """The reference's CPU-generator draws: randn(shape) then one randn_like per step (gaussian_diffusion.py:516,430)."""
+    th.manual_seed(TRAJ_SEED)
+    init = th.randn(TRAJ_BATCH, 3, IMAGE, IMAGE)
+    return init, [th.randn(TRAJ_BATCH, 3, IMAGE, IMAGE) for _ in range(TRAJ10_STEPS)]

@@ -159,6 +159,21 @@ def models_golden():
         out[f"traj_{name}"] = s.numpy()
         out[f"traj_{name}_ts"] = np.array(ts_seen, dtype=np.int64)
         out[f"traj_{name}_u8"] = ((s + 1) * 127.5).clamp(0, 255).to(th.uint8).permute(0, 2, 3, 1).contiguous().numpy()
+    # first 10 steps of the full-length chains through the reference's progressive generators
+    for name, kw in cfg.TRAJ10_CASES.items():
+        d = rsu.create_gaussian_diffusion(**kw["diffusion"])
+        th.manual_seed(cfg.TRAJ_SEED)
+        yy = cfg.traj_labels()
+        gen = (d.ddim_sample_loop_progressive if kw["ddim"] else d.p_sample_loop_progressive)(
+            lambda x_, t_, y=None: unet(x_, t_, y), (cfg.TRAJ_BATCH, 3, cfg.IMAGE, cfg.IMAGE), model_kwargs={"y": yy},
+            cond_fn=cond_fn if kw["guided"] else None, device="cpu", **({} if kw["ddim"] else {"denoise_start_point": -1}))
+        last = None
+        for k, o in enumerate(gen):
+            last = o
+            if k + 1 == cfg.TRAJ10_STEPS:
+                break
+        out[f"traj10_{name}_sample"] = last["sample"].numpy()
+        out[f"traj10_{name}_x0"] = last["pred_xstart"].numpy()
     np.savez_compressed(os.path.join(OUT, "models_golden.npz"), **out)
     for k, v in out.items():
         print(k, v.shape, float(np.abs(v).max()) if v.dtype != np.uint8 else "")

@@ -19,6 +19,12 @@ from tests import gpu_helpers as H
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _fp32_reference():
+    th.backends.cudnn.allow_tf32 = False
+    th.backends.cuda.matmul.allow_tf32 = False
+
+
 def _rand(shape, seed, scale=1.0):
     g = th.Generator().manual_seed(seed)
     return (th.randn(shape, generator=g) * scale).cuda()
@@ -188,7 +194,8 @@ def test_timestep_embedding_and_linear(lib):
     t = th.tensor([0, 1, 37, 999], device="cuda")
     ref = om.timestep_embedding(t.cpu(), 256)
     got = timestep_embedding(t, 256)
-    assert float((got.cpu() - ref).abs().max()) < 2e-5  # sin/cos of arguments up to 999
+    # arguments reach 999 where one fp32 ulp is 6e-5, so a 1-ulp difference in freq shows up at that size
+    assert float((got.cpu() - ref).abs().max()) < 2e-4
     m, k, n = 5, 300, 77
     x, w, b, add = _rand((m, k), 16), _rand((n, k), 17, k ** -0.5), _rand((n,), 18), _rand((m, n), 19)
     y = th.empty((m, n), device="cuda")
