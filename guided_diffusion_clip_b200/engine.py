@@ -12,6 +12,7 @@ Data layout in HBM:
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
@@ -84,6 +85,16 @@ class Program:
 
     def run(self) -> None:
         stream = C.c_void_p(th.cuda.current_stream().cuda_stream)
+        if os.environ.get("GD_B200_DEBUG_SYNC", "0") == "1":  # locate a faulting launch: sync after every call
+            for i, (fn, args, name) in enumerate(self.calls):
+                rc = fn(*args, stream)
+                if rc != 0:
+                    L.check(rc, name)
+                try:
+                    th.cuda.synchronize()
+                except Exception as e:  # noqa: BLE001
+                    raise L.GdError(f"launch #{i} {name} faulted: {e}") from e
+            return
         for fn, args, name in self.calls:
             rc = fn(*args, stream)
             if rc != 0:
@@ -163,6 +174,13 @@ class Emitter:
         buf = self._scratch[role][:need].view(n, h, w, c)
         self.keep.append(buf)
         return View(buf, 0, c)
+
+    def act(self, n, h, w, c) -> View:
+        """A dedicated activation buffer OWNED by this emitter (kernels only see raw pointers, so every buffer a
+        recorded launch touches must stay referenced for the lifetime of the plan)."""
+        v = new_act(n, h, w, c, self.device)
+        self.keep.append(v.buf)
+        return v
 
     def f32(self, name: str) -> th.Tensor:
         """fp32 copy of a parameter (biases / GN affine / linear weights); fp16-rounded if the model holds it in fp16."""
@@ -302,7 +320,7 @@ class Emitter:
         self.gn_stats(x, st1)
         self.gn_apply(x, st1, self.f32(f"{k}.in_layers.0.weight"), self.f32(f"{k}.in_layers.0.bias"), a, silu=True,
                       mode=gmode)
-        h1 = new_act(n, ho, wo, r.cout, self.device) if tape is not None else self.scratch("h1", n, ho, wo, r.cout)
+        h1 = self.act(n, ho, wo, r.cout) if tape is not None else self.scratch("h1", n, ho, wo, r.cout)
         w1 = pack_conv3x3(self.P[f"{k}.in_layers.2.weight"])
         self.conv(a, w1, self.f32(f"{k}.in_layers.2.bias"), r.cout, h1)
         self.gn_stats(h1, st2)
@@ -333,8 +351,8 @@ class Emitter:
         self.gn_stats(x, st)
         self.gn_apply(x, st, self.f32(f"{k}.norm.weight"), self.f32(f"{k}.norm.bias"), g, silu=False)
         keep = tape is not None
-        qkv = new_act(n, h, w, 3 * a.ch, self.device) if keep else self.scratch("qkv", n, h, w, 3 * a.ch)
-        att = new_act(n, h, w, a.ch, self.device) if keep else self.scratch("att", n, h, w, a.ch)
+        qkv = self.act(n, h, w, 3 * a.ch) if keep else self.scratch("qkv", n, h, w, 3 * a.ch)
+        att = self.act(n, h, w, a.ch) if keep else self.scratch("att", n, h, w, a.ch)
         lse = th.empty((n, a.heads, h * w), dtype=th.float32, device=self.device) if keep else None
         self.conv(g, pack_1x1(self.P[f"{k}.qkv.weight"]), self.f32(f"{k}.qkv.bias"), 3 * a.ch, qkv, taps=1)
         order = L.QKV_NEW if a.new_order else L.QKV_LEGACY
@@ -387,7 +405,7 @@ class UNetPlan:
         for j, blk in enumerate(spec.output_blocks):
             sc, sh, sw = hs_stack.pop()
             assert (sh, sw) == (hcur[1], hcur[2]), "skip / h resolution mismatch"
-            cat_bufs.append(new_act(n, sh, sw, hcur[0] + sc, dev))
+            cat_bufs.append(em.act(n, sh, sw, hcur[0] + sc))
             c2, h2, w2 = hcur
             for l in blk:
                 if isinstance(l, ResSpec):
@@ -395,7 +413,7 @@ class UNetPlan:
                     if l.mode == "up":
                         h2, w2 = h2 * 2, w2 * 2
             hcur = (c2, h2, w2)
-        final_view = new_act(n, hcur[1], hcur[2], hcur[0], dev)
+        final_view = em.act(n, hcur[1], hcur[2], hcur[0])
 
         def hs_view(i: int) -> View:
             # hs[i] is popped by output block j = n_out-1-i and sits after h's channels
@@ -504,21 +522,21 @@ class ClassifierPlan:
         for blk in spec.input_blocks + [spec.middle_block]:
             for l in blk:
                 if isinstance(l, ConvInSpec):
-                    o = new_act(n, hh, ww, l.cout, dev)
+                    o = em.act(n, hh, ww, l.cout)
                     em.conv_in(l, self.x_in, o)
                     tape.append(("conv_in", l, o))
                 elif isinstance(l, ResSpec):
                     if l.mode == "down":
                         hh, ww = hh // 2, ww // 2
-                    o = new_act(n, hh, ww, l.cout, dev)
+                    o = em.act(n, hh, ww, l.cout)
                     em.res_block(l, cur, o, film_all, tape)
                 else:
-                    o = new_act(n, hh, ww, l.ch, dev)
+                    o = em.act(n, hh, ww, l.ch)
                     em.attn_block(l, cur, o, tape)
                 cur = o
         # head: GN -> SiLU -> AttentionPool2d (unet.py:833-841)
         st = em.stats_buf()
-        pooled_in = new_act(n, hh, ww, cur.c, dev)
+        pooled_in = em.act(n, hh, ww, cur.c)
         em.gn_stats(cur, st)
         em.gn_apply(cur, st, em.f32("out.0.weight"), em.f32("out.0.bias"), pooled_in, silu=True)
         hw, cch, heads = hh * ww, cur.c, model.pool_heads

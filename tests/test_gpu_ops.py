@@ -248,7 +248,8 @@ def test_attention_pool_head(lib):
     print(f"attnpool fwd rel err {err:.3e}")
     assert err < 1e-4
     dh = th.zeros((n, s, s, c), dtype=th.float16, device="cuda")
-    L.check(lib.gd_attnpool_bwd(H.vp(dl), H.vp(wq.t().contiguous()), H.vp(wc.t().contiguous()), H.vp(ws), H.vp(dh), c,
+    wq_t, wc_t = wq.t().contiguous(), wc.t().contiguous()  # must outlive the launch: the ABI only sees pointers
+    L.check(lib.gd_attnpool_bwd(H.vp(dl), H.vp(wq_t), H.vp(wc_t), H.vp(ws), H.vp(dh), c,
                                 n, hw, c, heads, n_out, C.c_float(1.0), H.stream()))
     th.cuda.synchronize()
     err = H.rel_err(dh.permute(0, 3, 1, 2), hmap.grad)
