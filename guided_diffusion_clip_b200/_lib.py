@@ -51,6 +51,7 @@ SIGNATURES = {
     "gd_version": (C.c_int, []),
     "gd_launch_count": (i64, []),
     "gd_launch_count_reset": (None, []),
+    "gd_debug_set": (None, [C.c_int, C.c_int]),
     "gd_conv_igemm": (C.c_int, [C.POINTER(ConvDesc), vp]),
     "gd_conv3x3_small_cin": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "gd_groupnorm_stats": (C.c_int, [vp, i32, i32, i32, i32, f32, vp, vp, vp]),

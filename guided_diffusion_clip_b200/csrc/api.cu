@@ -16,7 +16,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches += n; }
+void conv_debug_set(int key, int value);
 }  // namespace gd
+
+extern "C" void gd_debug_set(int key, int value) { gd::conv_debug_set(key, value); }
 
 extern "C" const char* gd_last_error(void) { return gd::g_err; }
 extern "C" int gd_version(void) { return GD_B200_ABI_VERSION; }

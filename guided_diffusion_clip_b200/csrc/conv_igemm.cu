@@ -58,6 +58,7 @@ struct ConvArgs {
   int ld_out;
   int out_mode;
   float out_scale;
+  int debug;  // 0 = normal; 1 = epilogue skipped (barriers only); 2 = TMEM loads only (timing experiments)
 };
 
 __device__ __forceinline__ void tile_coords(const ConvArgs& p, int m_tile, int& n0, int& y0, int& x0) {
@@ -68,6 +69,120 @@ __device__ __forceinline__ void tile_coords(const ConvArgs& p, int m_tile, int& 
   n0 = ig * p.bi;
   y0 = py * p.bh;
   x0 = px * p.bw;
+}
+
+struct EpiCtx {
+  int img, y, x;
+  bool valid;
+  size_t pix;
+};
+
+// Epilogue for kCols accumulator columns of this thread's row: all TMEM loads of the chunk are issued back to
+// back, the residual (a contiguous 2*kCols-byte run of this pixel) is prefetched while they are in flight, then ONE
+// tcgen05.wait::ld; bias comes in as float4 broadcast loads; the row leaves as kCols/8 16-byte stores.
+template <int kCols>
+__device__ __forceinline__ void epi_chunk(const ConvArgs& p, uint32_t taddr, int col, const EpiCtx& e) {
+  uint32_t v[kCols];
+  if constexpr (kCols == 64) {
+    tmem_ld_x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+    tmem_ld_x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+  } else if constexpr (kCols == 32) {
+    tmem_ld_x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+  } else {
+    tmem_ld_x16(taddr, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+  }
+  const bool full = col + kCols <= p.cout;
+  const bool use_res = p.res_mode != GD_RES_NONE && e.valid && full && p.debug == 0;
+  Half8 rv[kCols / 8];
+  float racc[kCols];
+  if (use_res) {
+    if (p.res_mode == GD_RES_SAME || p.res_mode == GD_RES_UPSAMPLE2) {
+      // UPSAMPLE2: the residual lives at half resolution, nearest-neighbour x2 (unet.py:107,241)
+      const size_t rpix = p.res_mode == GD_RES_SAME
+                              ? e.pix
+                              : (static_cast<size_t>(e.img) * (p.h >> 1) + (e.y >> 1)) * (p.w >> 1) + (e.x >> 1);
+      const __half* rp = p.res + rpix * p.ld_res + col;
+#pragma unroll
+      for (int q = 0; q < kCols / 8; ++q) rv[q] = ld_half8(rp + 8 * q);
+    } else {  // GD_RES_AVGPOOL2: the residual lives at double resolution (unet.py:136,241)
+#pragma unroll
+      for (int j = 0; j < kCols; ++j) racc[j] = 0.f;
+#pragma unroll
+      for (int s4 = 0; s4 < 4; ++s4) {
+        const size_t rpix = (static_cast<size_t>(e.img) * (p.h * 2) + (2 * e.y + (s4 >> 1))) * (p.w * 2) +
+                            (2 * e.x + (s4 & 1));
+        const __half* rp = p.res + rpix * p.ld_res + col;
+#pragma unroll
+        for (int q = 0; q < kCols / 8; ++q) rv[q] = ld_half8(rp + 8 * q);
+#pragma unroll
+        for (int q = 0; q < kCols / 8; ++q) {
+          float t[8];
+          half8_to_float(rv[q], t);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) racc[8 * q + j] += t[j];
+        }
+      }
+    }
+  }
+  tmem_ld_wait();
+  if (!e.valid || p.debug != 0) return;
+  float f[kCols];
+#pragma unroll
+  for (int j = 0; j < kCols; ++j) f[j] = __uint_as_float(v[j]);
+  if (p.bias != nullptr) {
+    if (full) {
+      const float4* bp = reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+      for (int q = 0; q < kCols / 4; ++q) {
+        const float4 b4 = __ldg(bp + q);
+        f[4 * q] += b4.x;
+        f[4 * q + 1] += b4.y;
+        f[4 * q + 2] += b4.z;
+        f[4 * q + 3] += b4.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < kCols; ++j)
+        if (col + j < p.cout) f[j] += __ldg(p.bias + col + j);
+    }
+  }
+  if (use_res) {
+    if (p.res_mode == GD_RES_AVGPOOL2) {
+#pragma unroll
+      for (int j = 0; j < kCols; ++j) f[j] += 0.25f * racc[j];
+    } else {
+#pragma unroll
+      for (int q = 0; q < kCols / 8; ++q) {
+        float t[8];
+        half8_to_float(rv[q], t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[8 * q + j] += t[j];
+      }
+    }
+  }
+  if (p.out_scale != 1.0f) {
+#pragma unroll
+    for (int j = 0; j < kCols; ++j) f[j] *= p.out_scale;
+  }
+  if (p.out_mode == GD_OUT_NHWC_F16) {
+    __half* op = reinterpret_cast<__half*>(p.out) + e.pix * p.ld_out + col;
+    if (full) {
+#pragma unroll
+      for (int q = 0; q < kCols / 8; ++q)
+        st_half8(op + 8 * q, float_to_half8(*reinterpret_cast<float(*)[8]>(&f[8 * q])));
+    } else {
+#pragma unroll
+      for (int j = 0; j < kCols; ++j)
+        if (col + j < p.cout) op[j] = __float2half_rn(f[j]);
+    }
+  } else {  // GD_OUT_NCHW_F32: adjacent threads are adjacent x -> coalesced per channel plane
+    float* op = reinterpret_cast<float*>(p.out);
+    const size_t plane = static_cast<size_t>(p.h) * p.w;
+#pragma unroll
+    for (int j = 0; j < kCols; ++j)
+      if (col + j < p.cout)
+        op[(static_cast<size_t>(e.img) * p.cout + col + j) * plane + static_cast<size_t>(e.y) * p.w + e.x] = f[j];
+  }
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -210,75 +325,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       const int col_base = n_tile * p.bn;
       const size_t pix = (static_cast<size_t>(img) * p.h + y) * p.w + x;
 
-      for (int c0 = 0; c0 < p.bn; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld_x16(t_row + static_cast<uint32_t>(c0), v);
-        tmem_ld_wait();
-        if (valid) {
-          const int col = col_base + c0;
-          float f[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            f[j] = __uint_as_float(v[j]);
-            if (p.bias != nullptr && col + j < p.cout) f[j] += __ldg(p.bias + col + j);
-          }
-          if (p.res_mode != GD_RES_NONE && col + 16 <= p.cout) {
-            float r[16];
-            if (p.res_mode == GD_RES_SAME) {
-              const __half* rp = p.res + pix * p.ld_res + col;
-              half8_to_float(ld_half8(rp), *reinterpret_cast<float(*)[8]>(&r[0]));
-              half8_to_float(ld_half8(rp + 8), *reinterpret_cast<float(*)[8]>(&r[8]));
-            } else if (p.res_mode == GD_RES_UPSAMPLE2) {
-              // residual lives at half resolution: nearest-neighbour x2 (unet.py:107,241)
-              const size_t rpix = (static_cast<size_t>(img) * (p.h >> 1) + (y >> 1)) * (p.w >> 1) + (x >> 1);
-              const __half* rp = p.res + rpix * p.ld_res + col;
-              half8_to_float(ld_half8(rp), *reinterpret_cast<float(*)[8]>(&r[0]));
-              half8_to_float(ld_half8(rp + 8), *reinterpret_cast<float(*)[8]>(&r[8]));
-            } else {  // GD_RES_AVGPOOL2: residual lives at double resolution (unet.py:136,241)
-#pragma unroll
-              for (int j = 0; j < 16; ++j) r[j] = 0.f;
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const size_t rpix =
-                    (static_cast<size_t>(img) * (p.h * 2) + (2 * y + (q >> 1))) * (p.w * 2) + (2 * x + (q & 1));
-                const __half* rp = p.res + rpix * p.ld_res + col;
-                float t[8];
-                half8_to_float(ld_half8(rp), t);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) r[j] += t[j];
-                half8_to_float(ld_half8(rp + 8), t);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) r[8 + j] += t[j];
-              }
-#pragma unroll
-              for (int j = 0; j < 16; ++j) r[j] *= 0.25f;
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] += r[j];
-          }
-          if (p.out_scale != 1.0f) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] *= p.out_scale;
-          }
-          if (p.out_mode == GD_OUT_NHWC_F16) {
-            __half* op = reinterpret_cast<__half*>(p.out) + pix * p.ld_out + col;
-            if (col + 16 <= p.cout) {
-              st_half8(op, float_to_half8(*reinterpret_cast<float(*)[8]>(&f[0])));
-              st_half8(op + 8, float_to_half8(*reinterpret_cast<float(*)[8]>(&f[8])));
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (col + j < p.cout) op[j] = __float2half_rn(f[j]);
-            }
-          } else {  // GD_OUT_NCHW_F32: adjacent threads are adjacent x -> coalesced per channel plane
-            float* op = reinterpret_cast<float*>(p.out);
-            const size_t plane = static_cast<size_t>(p.h) * p.w;
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (col + j < p.cout)
-                op[(static_cast<size_t>(img) * p.cout + col + j) * plane + static_cast<size_t>(y) * p.w + x] = f[j];
-          }
+      EpiCtx e;
+      e.img = img; e.y = y; e.x = x; e.valid = valid; e.pix = pix;
+      if (p.debug != 1) {
+        int c0 = 0;
+        for (; c0 + 64 <= p.bn; c0 += 64) epi_chunk<64>(p, t_row + static_cast<uint32_t>(c0), col_base + c0, e);
+        if (c0 + 32 <= p.bn) {
+          epi_chunk<32>(p, t_row + static_cast<uint32_t>(c0), col_base + c0, e);
+          c0 += 32;
         }
+        if (c0 + 16 <= p.bn) epi_chunk<16>(p, t_row + static_cast<uint32_t>(c0), col_base + c0, e);
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
@@ -346,14 +402,28 @@ int encode_weight_map(CUtensorMap* m, const void* base, int k_total, int n_pad, 
 }
 
 int g_num_sms = 0;
+int g_debug_epilogue = 0;
+int g_force_bn = 0;
 
 }  // namespace
 
-int conv_pick_bn(int n_pad) {
-  if (n_pad <= 256) return n_pad;
-  for (int bn = 256; bn >= 16; bn -= 16)
-    if (n_pad % bn == 0) return bn;
-  return 16;
+void conv_debug_set(int key, int value) {
+  if (key == 0) g_debug_epilogue = value;
+  if (key == 1) g_force_bn = value;
+}
+
+// N tile: the largest divisor of n_pad (multiple of 16, <= 256) that still yields enough tiles to fill the SMs;
+// small-spatial layers (8x8 / 16x16 with C = 1024) otherwise run on 4-16 CTAs.  Below 32 columns the MMA is
+// shared-memory bound, so 32 is the floor unless n_pad itself is smaller.
+int conv_pick_bn(int n_pad, int m_tiles, int num_sms) {
+  int best = 0;
+  for (int bn = 256; bn >= 16; bn -= 16) {
+    if (n_pad % bn != 0) continue;
+    if (best == 0) best = bn;  // largest divisor
+    if (static_cast<long long>(m_tiles) * (n_pad / bn) * 100 >= 85LL * num_sms) return bn;
+    if (bn >= 32) best = bn;
+  }
+  return best ? best : 16;
 }
 
 }  // namespace gd
@@ -373,9 +443,9 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
   GD_REQUIRE(d->k_total == k_total, "gd_conv_igemm: k_total %d != taps*C0+C1 = %d", d->k_total, k_total);
   GD_REQUIRE(d->n_pad % 16 == 0 && d->n_pad >= d->cout && d->cout > 0, "gd_conv_igemm: n_pad %d / cout %d invalid",
              d->n_pad, d->cout);
-  int bn = d->bn > 0 ? d->bn : conv_pick_bn(d->n_pad);
-  GD_REQUIRE(bn % 16 == 0 && bn >= 16 && bn <= 256 && d->n_pad % bn == 0, "gd_conv_igemm: bad N tile %d for n_pad %d", bn,
-             d->n_pad);
+  if (d->bn > 0)
+    GD_REQUIRE(d->bn % 16 == 0 && d->bn <= 256 && d->n_pad % d->bn == 0, "gd_conv_igemm: bad N tile %d for n_pad %d",
+               d->bn, d->n_pad);
   GD_REQUIRE(d->out_mode == GD_OUT_NHWC_F16 || d->out_mode == GD_OUT_NCHW_F32, "gd_conv_igemm: bad out_mode");
   if (d->out_mode == GD_OUT_NHWC_F16)
     GD_REQUIRE(d->ld_out >= d->cout && (d->ld_out % 8 == 0 || d->cout % 16 != 0), "gd_conv_igemm: bad ld_out %d", d->ld_out);
@@ -402,7 +472,19 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
   GD_REQUIRE(bi >= 1 && bi <= 256 && bw * bh * bi == 128, "gd_conv_igemm: cannot tile %dx%d into 128-pixel patches", d->h,
              d->w);
 
+  if (g_num_sms == 0) {
+    int dev = 0;
+    GD_CHECK_CUDA(cudaGetDevice(&dev));
+    GD_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int m_tiles = ((d->w + bw - 1) / bw) * ((d->h + bh - 1) / bh) * ((d->n + bi - 1) / bi);
+  int bn = d->bn > 0 ? d->bn : (g_force_bn > 0 && d->n_pad % g_force_bn == 0 ? g_force_bn
+                                                                              : conv_pick_bn(d->n_pad, m_tiles, g_num_sms));
+  GD_REQUIRE(bn % 16 == 0 && bn >= 16 && bn <= 256 && d->n_pad % bn == 0, "gd_conv_igemm: bad N tile %d for n_pad %d", bn,
+             d->n_pad);
+
   ConvArgs p;
+  p.debug = g_debug_epilogue;
   p.n_img = d->n;
   p.h = d->h;
   p.w = d->w;
@@ -445,11 +527,6 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
   rc = encode_weight_map(&mb, d->wpack, k_total, d->n_pad, bn);
   if (rc) return rc;
 
-  if (g_num_sms == 0) {
-    int dev = 0;
-    GD_CHECK_CUDA(cudaGetDevice(&dev));
-    GD_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
   // Always request (almost) the full shared memory so exactly one CTA owns an SM and its 512 TMEM columns.
   const int smem_bytes = kSmemBudget;
   static bool attr_set = false;

@@ -36,6 +36,9 @@ int gd_version(void);
 /* Number of kernels launched by this library on this thread since the last gd_launch_count_reset(). */
 int64_t gd_launch_count(void);
 void gd_launch_count_reset(void);
+/* Measurement hooks (profiles/ only): key 0 = conv epilogue mode (0 normal, 1 barriers only, 2 TMEM loads only),
+ * key 1 = force the conv N tile (0 = heuristic). */
+void gd_debug_set(int key, int value);
 
 /* ------------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution on tcgen05 (3x3 pad 1 stride 1, or 1x1), fp16 operands, fp32 accumulate.
