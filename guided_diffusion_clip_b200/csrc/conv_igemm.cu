@@ -18,7 +18,10 @@
 // Warp roles (192 threads, 1 CTA/SM, persistent over tiles):
 //   warp 0   : TMA producer (one lane)           smem ring: full[s]/empty[s] mbarriers
 //   warp 1   : TMEM alloc + tcgen05.mma issuer   accumulators: 2 x 256 TMEM columns (double buffered)
-//   warps 2-5: epilogue (tcgen05.ld -> bias/residual -> fp16 NHWC or fp32 NCHW stores)
+//   warps 2-5: epilogue.  Fast path (fp16 NHWC output, Cout % 64 == 0): per 64-column sub-tile
+//              tcgen05.ld -> + bias (smem) + residual (TMA-loaded tile) -> fp16 -> 128B-swizzled smem tile ->
+//              ONE 4-D TMA store {64ch, BW, BH, BI}: full-line writes, clipping of overhanging patches for free.
+//              Slow path (fp32 NCHW output / Cout not a multiple of 64): direct per-thread stores.
 #include "common.cuh"
 #include "../../include/gd_b200.h"
 
@@ -34,6 +37,9 @@ constexpr int kMaxStages = 8;
 constexpr int kThreads = 192;
 constexpr int kSmemBudget = 227 * 1024;
 constexpr int kBarrierBytes = 1024;
+constexpr int kBiasBytes = 1024;            // 256 floats
+constexpr int kEpiTileBytes = kBM * 64 * 2; // 16 KiB: 128 rows x 64 fp16, SWIZZLE_128B
+constexpr int kEpiBytes = 2 * kEpiTileBytes;  // output staging + residual staging
 
 struct ConvArgs {
   // geometry
@@ -58,7 +64,8 @@ struct ConvArgs {
   int ld_out;
   int out_mode;
   float out_scale;
-  int debug;  // 0 = normal; 1 = epilogue skipped (barriers only); 2 = TMEM loads only (timing experiments)
+  int tma_epi;  // 1 = staged TMA-store epilogue
+  int debug;    // 0 = normal; 1 = epilogue skipped (barriers only); 2 = TMEM loads only (timing experiments)
 };
 
 __device__ __forceinline__ void tile_coords(const ConvArgs& p, int m_tile, int& n0, int& y0, int& x0) {
@@ -71,98 +78,71 @@ __device__ __forceinline__ void tile_coords(const ConvArgs& p, int m_tile, int& 
   x0 = px * p.bw;
 }
 
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(m), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// 16-byte chunk `chunk` of row `row` inside a [rows][128 B] tile laid out with the 128-byte swizzle
+__device__ __forceinline__ uint8_t* sw128(uint8_t* tile, int row, int chunk) {
+  return tile + row * 128 + ((chunk ^ (row & 7)) << 4);
+}
+
 struct EpiCtx {
   int img, y, x;
   bool valid;
   size_t pix;
 };
 
-// Epilogue for kCols accumulator columns of this thread's row: all TMEM loads of the chunk are issued back to
-// back, the residual (a contiguous 2*kCols-byte run of this pixel) is prefetched while they are in flight, then ONE
-// tcgen05.wait::ld; bias comes in as float4 broadcast loads; the row leaves as kCols/8 16-byte stores.
+// ---- slow-path epilogue: direct per-thread stores (fp32 NCHW outputs and Cout not a multiple of 64) ----------
 template <int kCols>
-__device__ __forceinline__ void epi_chunk(const ConvArgs& p, uint32_t taddr, int col, const EpiCtx& e) {
+__device__ __forceinline__ void epi_chunk_direct(const ConvArgs& p, uint32_t taddr, int col, const EpiCtx& e) {
   uint32_t v[kCols];
-  if constexpr (kCols == 64) {
-    tmem_ld_x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-    tmem_ld_x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-  } else if constexpr (kCols == 32) {
+  if constexpr (kCols == 32) {
     tmem_ld_x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
   } else {
     tmem_ld_x16(taddr, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
   }
   const bool full = col + kCols <= p.cout;
   const bool use_res = p.res_mode != GD_RES_NONE && e.valid && full && p.debug == 0;
-  Half8 rv[kCols / 8];
   float racc[kCols];
   if (use_res) {
-    if (p.res_mode == GD_RES_SAME || p.res_mode == GD_RES_UPSAMPLE2) {
-      // UPSAMPLE2: the residual lives at half resolution, nearest-neighbour x2 (unet.py:107,241)
-      const size_t rpix = p.res_mode == GD_RES_SAME
-                              ? e.pix
-                              : (static_cast<size_t>(e.img) * (p.h >> 1) + (e.y >> 1)) * (p.w >> 1) + (e.x >> 1);
+#pragma unroll
+    for (int j = 0; j < kCols; ++j) racc[j] = 0.f;
+    const int nsrc = p.res_mode == GD_RES_AVGPOOL2 ? 4 : 1;
+    for (int s4 = 0; s4 < nsrc; ++s4) {
+      size_t rpix;
+      if (p.res_mode == GD_RES_SAME) rpix = e.pix;
+      else if (p.res_mode == GD_RES_UPSAMPLE2)
+        rpix = (static_cast<size_t>(e.img) * (p.h >> 1) + (e.y >> 1)) * (p.w >> 1) + (e.x >> 1);
+      else
+        rpix = (static_cast<size_t>(e.img) * (p.h * 2) + (2 * e.y + (s4 >> 1))) * (p.w * 2) + (2 * e.x + (s4 & 1));
       const __half* rp = p.res + rpix * p.ld_res + col;
 #pragma unroll
-      for (int q = 0; q < kCols / 8; ++q) rv[q] = ld_half8(rp + 8 * q);
-    } else {  // GD_RES_AVGPOOL2: the residual lives at double resolution (unet.py:136,241)
+      for (int q = 0; q < kCols / 8; ++q) {
+        float t[8];
+        half8_to_float(ld_half8(rp + 8 * q), t);
 #pragma unroll
-      for (int j = 0; j < kCols; ++j) racc[j] = 0.f;
-#pragma unroll
-      for (int s4 = 0; s4 < 4; ++s4) {
-        const size_t rpix = (static_cast<size_t>(e.img) * (p.h * 2) + (2 * e.y + (s4 >> 1))) * (p.w * 2) +
-                            (2 * e.x + (s4 & 1));
-        const __half* rp = p.res + rpix * p.ld_res + col;
-#pragma unroll
-        for (int q = 0; q < kCols / 8; ++q) rv[q] = ld_half8(rp + 8 * q);
-#pragma unroll
-        for (int q = 0; q < kCols / 8; ++q) {
-          float t[8];
-          half8_to_float(rv[q], t);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) racc[8 * q + j] += t[j];
-        }
+        for (int j = 0; j < 8; ++j) racc[8 * q + j] += t[j];
       }
     }
   }
   tmem_ld_wait();
   if (!e.valid || p.debug != 0) return;
+  const float rs = p.res_mode == GD_RES_AVGPOOL2 ? 0.25f : 1.0f;
   float f[kCols];
 #pragma unroll
-  for (int j = 0; j < kCols; ++j) f[j] = __uint_as_float(v[j]);
-  if (p.bias != nullptr) {
-    if (full) {
-      const float4* bp = reinterpret_cast<const float4*>(p.bias + col);
-#pragma unroll
-      for (int q = 0; q < kCols / 4; ++q) {
-        const float4 b4 = __ldg(bp + q);
-        f[4 * q] += b4.x;
-        f[4 * q + 1] += b4.y;
-        f[4 * q + 2] += b4.z;
-        f[4 * q + 3] += b4.w;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < kCols; ++j)
-        if (col + j < p.cout) f[j] += __ldg(p.bias + col + j);
-    }
-  }
-  if (use_res) {
-    if (p.res_mode == GD_RES_AVGPOOL2) {
-#pragma unroll
-      for (int j = 0; j < kCols; ++j) f[j] += 0.25f * racc[j];
-    } else {
-#pragma unroll
-      for (int q = 0; q < kCols / 8; ++q) {
-        float t[8];
-        half8_to_float(rv[q], t);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[8 * q + j] += t[j];
-      }
-    }
-  }
-  if (p.out_scale != 1.0f) {
-#pragma unroll
-    for (int j = 0; j < kCols; ++j) f[j] *= p.out_scale;
+  for (int j = 0; j < kCols; ++j) {
+    f[j] = __uint_as_float(v[j]);
+    if (p.bias != nullptr && col + j < p.cout) f[j] += __ldg(p.bias + col + j);
+    if (use_res) f[j] += rs * racc[j];
+    f[j] *= p.out_scale;
   }
   if (p.out_mode == GD_OUT_NHWC_F16) {
     __half* op = reinterpret_cast<__half*>(p.out) + e.pix * p.ld_out + col;
@@ -187,18 +167,23 @@ __device__ __forceinline__ void epi_chunk(const ConvArgs& p, uint32_t taddr, int
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
-                  const __grid_constant__ CUtensorMap map_b, const ConvArgs p) {
+                  const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out,
+                  const __grid_constant__ CUtensorMap map_res, const ConvArgs p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [barriers 1 KiB][stage 0: A | B][stage 1] ...   (stage bases are 1024-aligned)
+  // carve: [barriers 1 KiB][bias 1 KiB][stage 0: A | B] ... [out staging 16 KiB][residual staging 16 KiB]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tmem_full = empty_bar + kMaxStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  uint8_t* stage_base = smem + kBarrierBytes;
+  uint64_t* res_bar = tmem_empty + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
+  float* s_bias = reinterpret_cast<float*>(smem + kBarrierBytes);
+  uint8_t* stage_base = smem + kBarrierBytes + kBiasBytes;
   const int b_tile_bytes = p.bn * kBK * 2;
   const int stage_bytes = kATileBytes + b_tile_bytes;  // multiple of 1024 since bn % 16 == 0 -> bn*128 % 2048 == 0
+  uint8_t* s_out = stage_base + p.stages * stage_bytes;
+  uint8_t* s_res = s_out + kEpiTileBytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -208,6 +193,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     tma_prefetch_desc(&map_a0);
     tma_prefetch_desc(&map_a1);
     tma_prefetch_desc(&map_b);
+    if (p.tma_epi) {
+      tma_prefetch_desc(&map_out);
+      tma_prefetch_desc(&map_res);
+    }
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -216,6 +205,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], 128);
     }
+    mbar_init(res_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -305,11 +295,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     // ------------------------------------------------------------------ epilogue (warps 2..5)
     const int quarter = warp & 3;          // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;   // row of the 128-row tile == pixel within the patch
+    const int epi_tid = threadIdx.x - 64;  // 0..127
+    const bool leader = epi_tid == 0;
     const int patch_px = p.bh * p.bw;
     const int i_local = row / patch_px;
     const int rem = row - i_local * patch_px;
     const int y_local = rem / p.bw;
     const int x_local = rem - y_local * p.bw;
+    // row of this pixel's source inside the residual staging tile
+    const bool res_tma = p.tma_epi && (p.res_mode == GD_RES_SAME || p.res_mode == GD_RES_UPSAMPLE2) && p.debug == 0;
+    const int res_row = p.res_mode == GD_RES_UPSAMPLE2
+                            ? (i_local * (p.bh >> 1) + (y_local >> 1)) * (p.bw >> 1) + (x_local >> 1)
+                            : row;
+    const uint32_t res_bytes = p.res_mode == GD_RES_UPSAMPLE2 ? kEpiTileBytes / 4 : kEpiTileBytes;
+    uint32_t res_phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -317,32 +316,132 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       const int m_tile = tile / p.n_tiles;
       int n0, y0, x0;
       tile_coords(p, m_tile, n0, y0, x0);
-      const int img = n0 + i_local, y = y0 + y_local, x = x0 + x_local;
-      const bool valid = (img < p.n_img) && (y < p.h) && (x < p.w);
+      EpiCtx e;
+      e.img = n0 + i_local;
+      e.y = y0 + y_local;
+      e.x = x0 + x_local;
+      e.valid = (e.img < p.n_img) && (e.y < p.h) && (e.x < p.w);
+      e.pix = (static_cast<size_t>(e.img) * p.h + e.y) * p.w + e.x;
+      const int col_base = n_tile * p.bn;
+      const int rx0 = p.res_mode == GD_RES_UPSAMPLE2 ? (x0 >> 1) : x0;
+      const int ry0 = p.res_mode == GD_RES_UPSAMPLE2 ? (y0 >> 1) : y0;
+      if (p.tma_epi) {
+        // stage this tile's bias; prefetch the first residual sub-tile while the mainloop is still running
+        for (int j = epi_tid; j < p.bn; j += 128) s_bias[j] = p.bias != nullptr ? __ldg(p.bias + col_base + j) : 0.f;
+        if (leader && res_tma) {
+          mbar_arrive_expect_tx(res_bar, res_bytes);
+          tma_load_4d(s_res, &map_res, res_bar, col_base, rx0, ry0, n0);
+        }
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * 256);
-      const int col_base = n_tile * p.bn;
-      const size_t pix = (static_cast<size_t>(img) * p.h + y) * p.w + x;
 
-      EpiCtx e;
-      e.img = img; e.y = y; e.x = x; e.valid = valid; e.pix = pix;
-      if (p.debug != 1) {
+      if (p.debug == 1) {
+        // timing experiment: no epilogue work at all
+      } else if (!p.tma_epi) {
         int c0 = 0;
-        for (; c0 + 64 <= p.bn; c0 += 64) epi_chunk<64>(p, t_row + static_cast<uint32_t>(c0), col_base + c0, e);
-        if (c0 + 32 <= p.bn) {
-          epi_chunk<32>(p, t_row + static_cast<uint32_t>(c0), col_base + c0, e);
-          c0 += 32;
+        for (; c0 + 32 <= p.bn; c0 += 32) epi_chunk_direct<32>(p, t_row + static_cast<uint32_t>(c0), col_base + c0, e);
+        if (c0 + 16 <= p.bn) epi_chunk_direct<16>(p, t_row + static_cast<uint32_t>(c0), col_base + c0, e);
+      } else {
+        epi_barrier();  // s_bias visible to all epilogue threads
+        const int nsub = p.bn >> 6;
+        for (int sub = 0; sub < nsub; ++sub) {
+          const int c0 = sub * 64;
+          uint32_t v[64];
+          tmem_ld_x32(t_row + static_cast<uint32_t>(c0), *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+          tmem_ld_x32(t_row + static_cast<uint32_t>(c0 + 32), *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+          Half8 rv[8];
+          if (res_tma) {
+            mbar_wait(res_bar, res_phase);
+            res_phase ^= 1;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) rv[q] = *reinterpret_cast<const Half8*>(sw128(s_res, res_row, q));
+          } else if (p.res_mode == GD_RES_AVGPOOL2 && e.valid && p.debug == 0) {
+            // residual lives at double resolution (unet.py:136,241): direct global reads, fp32 average -> fp16
+            float racc[64];
+#pragma unroll
+            for (int j = 0; j < 64; ++j) racc[j] = 0.f;
+#pragma unroll
+            for (int s4 = 0; s4 < 4; ++s4) {
+              const size_t rpix = (static_cast<size_t>(e.img) * (p.h * 2) + (2 * e.y + (s4 >> 1))) * (p.w * 2) +
+                                  (2 * e.x + (s4 & 1));
+              const __half* rp = p.res + rpix * p.ld_res + col_base + c0;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                float t[8];
+                half8_to_float(ld_half8(rp + 8 * q), t);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) racc[8 * q + j] += t[j];
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float t[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) t[j] = 0.25f * racc[8 * q + j];
+              rv[q] = float_to_half8(t);
+            }
+          }
+          tmem_ld_wait();
+          if (sub == nsub - 1) {
+            // accumulator fully read: hand the TMEM buffer back to the MMA warp before the store phase
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[acc]);
+          }
+          // s_out is free once the previous TMA store has finished READING it
+          if (leader) bulk_wait_read0();
+          epi_barrier();  // (A) s_out reusable; every thread has consumed s_res
+          if (leader && res_tma && sub + 1 < nsub) {
+            mbar_arrive_expect_tx(res_bar, res_bytes);
+            tma_load_4d(s_res, &map_res, res_bar, col_base + c0 + 64, rx0, ry0, n0);
+          }
+          if (p.debug == 0) {
+            const bool has_res = p.res_mode != GD_RES_NONE;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float f[8];
+              const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c0 + 8 * q);
+              const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c0 + 8 * q + 4);
+              f[0] = __uint_as_float(v[8 * q + 0]) + b0.x;
+              f[1] = __uint_as_float(v[8 * q + 1]) + b0.y;
+              f[2] = __uint_as_float(v[8 * q + 2]) + b0.z;
+              f[3] = __uint_as_float(v[8 * q + 3]) + b0.w;
+              f[4] = __uint_as_float(v[8 * q + 4]) + b1.x;
+              f[5] = __uint_as_float(v[8 * q + 5]) + b1.y;
+              f[6] = __uint_as_float(v[8 * q + 6]) + b1.z;
+              f[7] = __uint_as_float(v[8 * q + 7]) + b1.w;
+              if (has_res) {
+                float t[8];
+                half8_to_float(rv[q], t);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] += t[j];
+              }
+              if (p.out_scale != 1.0f) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] *= p.out_scale;
+              }
+              *reinterpret_cast<Half8*>(sw128(s_out, row, q)) = float_to_half8(f);
+            }
+            fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+          }
+          epi_barrier();  // (B) staging tile complete
+          if (leader && p.debug == 0) {
+            tma_store_4d(&map_out, s_out, col_base + c0, x0, y0, n0);
+            bulk_commit();
+          }
         }
-        if (c0 + 16 <= p.bn) epi_chunk<16>(p, t_row + static_cast<uint32_t>(c0), col_base + c0, e);
       }
-      tc_fence_before();
-      mbar_arrive(&tmem_empty[acc]);
+      if (!p.tma_epi || p.debug == 1) {
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[acc]);
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
       }
     }
+    if (leader && p.tma_epi) bulk_wait0();  // all stores complete before the CTA (and its smem) goes away
   }
 
   tc_fence_before();
@@ -404,12 +503,14 @@ int encode_weight_map(CUtensorMap* m, const void* base, int k_total, int n_pad, 
 int g_num_sms = 0;
 int g_debug_epilogue = 0;
 int g_force_bn = 0;
+int g_disable_tma_epi = 0;
 
 }  // namespace
 
 void conv_debug_set(int key, int value) {
   if (key == 0) g_debug_epilogue = value;
   if (key == 1) g_force_bn = value;
+  if (key == 2) g_disable_tma_epi = value;
 }
 
 // N tile: the largest divisor of n_pad (multiple of 16, <= 256) that still yields enough tiles to fill the SMs;
@@ -493,11 +594,11 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
   p.bw = bw;
   p.patches_x = (d->w + bw - 1) / bw;
   p.patches_y = (d->h + bh - 1) / bh;
-  p.m_tiles = p.patches_x * p.patches_y * ((d->n + bi - 1) / bi);
+  p.m_tiles = m_tiles;
   p.n_tiles = d->n_pad / bn;
   p.bn = bn;
   const int stage_bytes = kATileBytes + bn * kBK * 2;
-  int stages = (kSmemBudget - kBarrierBytes - 1024) / stage_bytes;
+  int stages = (kSmemBudget - kBarrierBytes - kBiasBytes - kEpiBytes - 1024) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   GD_REQUIRE(stages >= 2, "gd_conv_igemm: not enough shared memory for 2 stages");
   p.stages = stages;
@@ -514,8 +615,15 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
   p.ld_out = d->ld_out;
   p.out_mode = d->out_mode;
   p.out_scale = d->out_scale == 0.0f ? 1.0f : d->out_scale;
+  // staged TMA-store epilogue: fp16 NHWC, whole 64-channel sub-tiles, 16-byte aligned rows; an upsampled residual
+  // additionally needs an even patch
+  p.tma_epi = (!g_disable_tma_epi && d->out_mode == GD_OUT_NHWC_F16 && d->cout % 64 == 0 && bn % 64 == 0 &&
+               d->ld_out % 8 == 0 && (reinterpret_cast<uintptr_t>(d->out) % 16 == 0) &&
+               !(d->res_mode == GD_RES_UPSAMPLE2 && (bw % 2 || bh % 2)))
+                  ? 1
+                  : 0;
 
-  CUtensorMap ma0, ma1, mb;
+  CUtensorMap ma0, ma1, mb, mout, mres;
   int rc = encode_act_map(&ma0, d->a0, d->c0, d->ld0, d->n, d->h, d->w, bi, bh, bw);
   if (rc) return rc;
   if (d->a1) {
@@ -526,6 +634,19 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
   }
   rc = encode_weight_map(&mb, d->wpack, k_total, d->n_pad, bn);
   if (rc) return rc;
+  mout = ma0;
+  mres = ma0;
+  if (p.tma_epi) {
+    rc = encode_act_map(&mout, d->out, d->cout, d->ld_out, d->n, d->h, d->w, bi, bh, bw);
+    if (rc) return rc;
+    if (d->res_mode == GD_RES_SAME) {
+      rc = encode_act_map(&mres, d->res, d->cout, d->ld_res, d->n, d->h, d->w, bi, bh, bw);
+      if (rc) return rc;
+    } else if (d->res_mode == GD_RES_UPSAMPLE2) {
+      rc = encode_act_map(&mres, d->res, d->cout, d->ld_res, d->n, d->h / 2, d->w / 2, bi, bh / 2, bw / 2);
+      if (rc) return rc;
+    }
+  }
 
   // Always request (almost) the full shared memory so exactly one CTA owns an SM and its 512 TMEM columns.
   const int smem_bytes = kSmemBudget;
@@ -536,7 +657,7 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
   }
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int grid = total_tiles < g_num_sms ? total_tiles : g_num_sms;
-  conv_igemm_kernel<<<grid, kThreads, smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(ma0, ma1, mb, p);
+  conv_igemm_kernel<<<grid, kThreads, smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(ma0, ma1, mb, mout, mres, p);
   GD_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
   return 0;
