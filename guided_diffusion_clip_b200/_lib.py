@@ -53,10 +53,10 @@ SIGNATURES = {
     "gd_launch_count_reset": (None, []),
     "gd_debug_set": (None, [C.c_int, C.c_int]),
     "gd_conv_igemm": (C.c_int, [C.POINTER(ConvDesc), vp]),
-    "gd_conv3x3_small_cin": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "gd_im2col3x3_small_cin": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, vp]),
     "gd_groupnorm_stats": (C.c_int, [vp, i32, i32, i32, i32, f32, vp, vp, vp]),
     "gd_groupnorm_ws_floats": (i64, [i32, i32, i32]),
-    "gd_groupnorm_apply": (C.c_int, [vp, i32, vp, vp, vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
+    "gd_groupnorm_apply": (C.c_int, [vp, i32, vp, vp, vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp]),
     "gd_groupnorm_bwd": (C.c_int, [vp, i32, vp, vp, vp, vp, i32, vp, i32, vp, i32, i32, vp, i32, vp, i32, i32, i32,
                                    i32, i32, i32, vp]),
     "gd_attention_fwd": (C.c_int, [vp, i32, vp, i32, vp, i32, i32, i32, i32, vp]),

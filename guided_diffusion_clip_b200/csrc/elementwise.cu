@@ -157,6 +157,67 @@ __global__ void linear_f32_kernel(const float* __restrict__ x, int ldx, const fl
   }
 }
 
+// Tiled fp32 GEMM for many rows (the classifier pool head: M = batch * 65 tokens): 64x64 output tile per CTA,
+// K stepped by 16 through shared memory, 4x4 register tile per thread.  Same contract as linear_f32_kernel.
+__global__ void __launch_bounds__(256)
+sgemm_nt_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w, const float* __restrict__ b,
+                const float* __restrict__ addp, int ld_add, float* __restrict__ y, int ldy, int m, int k, int n,
+                int silu_in, int silu_out) {
+  __shared__ float sx[16][64 + 4];
+  __shared__ float sw[16][64 + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int lr = tid >> 2, lk = (tid & 3) * 4;  // each thread loads 4 consecutive k of one row of each operand
+  for (int k0 = 0; k0 < k; k0 += 16) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int kk = k0 + lk + q;
+      float xv = 0.f, wv = 0.f;
+      if (kk < k) {
+        if (m0 + lr < m) {
+          xv = x[static_cast<size_t>(m0 + lr) * ldx + kk];
+          if (silu_in) xv = xv / (1.0f + expf(-xv));
+        }
+        if (n0 + lr < n) wv = __ldg(w + static_cast<size_t>(n0 + lr) * k + kk);
+      }
+      sx[lk + q][lr] = xv;
+      sw[lk + q][lr] = wv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&sx[kk][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&sw[kk][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = m0 + ty * 4 + i;
+    if (r >= m) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = n0 + tx * 4 + j;
+      if (c >= n) continue;
+      float v = acc[i][j] + (b ? b[c] : 0.f);
+      if (addp) v += addp[static_cast<size_t>(r) * ld_add + c];
+      if (silu_out) v = v / (1.0f + expf(-v));
+      y[static_cast<size_t>(r) * ldy + c] = v;
+    }
+  }
+}
+
 __global__ void embedding_gather_kernel(const float* __restrict__ table, const int64_t* __restrict__ idx,
                                         float* __restrict__ out, int n, int dim, int num_rows) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -169,59 +230,37 @@ __global__ void embedding_gather_kernel(const float* __restrict__ table, const i
 }
 
 // ---------------------------------------------------------------------------------------------
-// First conv: fp32 NCHW input with 3 or 6 channels -> fp16 NHWC.  CUDA-core direct conv (K = 27/54
-// is too thin for a tensor-core tile and is <0.1 % of the FLOPs).
+// First conv (input_blocks.0.0, unet.py:483,741): C_in is 3 (or 6 for super-resolution), far too thin for a K block.
+// The fp32 NCHW input is expanded to an fp16 NHWC im2col tensor with 64 channels, k = (ky*3+kx)*cin + ci (zero padded),
+// and the conv then runs as a 1x1 problem with K = 64 on the tcgen05 kernel (engine.pack_conv_in packs the weights the
+// same way).  One thread per pixel writes one 128-byte row.
 // ---------------------------------------------------------------------------------------------
-__global__ void conv3x3_small_cin_kernel(const float* __restrict__ x, const float* __restrict__ wgt,
-                                         const float* __restrict__ bias, __half* __restrict__ out, int ld_out, int n,
-                                         int cin, int h, int w, int cout, int c8, int rep) {
-  extern __shared__ float s_w[];  // [cin*9][cout]
-  const int kdim = cin * 9;
-  for (int i = threadIdx.x; i < kdim * cout; i += blockDim.x) {
-    const int co = i % cout, kk = i / cout;
-    s_w[i] = wgt[static_cast<size_t>(co) * kdim + kk];
-  }
-  __syncthreads();
-  const int cch = threadIdx.x % c8, pl = threadIdx.x / c8;
-  float bsum[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) bsum[j] = bias ? bias[cch * 8 + j] : 0.f;
+__global__ void im2col3x3_small_cin_kernel(const float* __restrict__ x, __half* __restrict__ out, int ld_out, int n,
+                                           int cin, int h, int w) {
   const size_t hw = static_cast<size_t>(h) * w;
   const size_t total = static_cast<size_t>(n) * hw;
-  for (size_t p = static_cast<size_t>(blockIdx.x) * rep + pl; p < total; p += static_cast<size_t>(gridDim.x) * rep) {
+  for (size_t p = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; p < total;
+       p += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int img = static_cast<int>(p / hw);
     const int rem = static_cast<int>(p - static_cast<size_t>(img) * hw);
     const int y = rem / w, xx = rem - y * w;
-    float acc[8];
+    __half vals[64];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = bsum[j];
-    for (int ci = 0; ci < cin; ++ci) {
-      const float* xp = x + (static_cast<size_t>(img) * cin + ci) * hw;
-#pragma unroll
-      for (int ky = 0; ky < 3; ++ky) {
-        const int yy = y + ky - 1;
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const int xc = xx + kx - 1;
-          float v = 0.f;
-          if (yy >= 0 && yy < h && xc >= 0 && xc < w) v = __ldg(xp + static_cast<size_t>(yy) * w + xc);
-          // the reference casts the input to fp16 before the conv (unet.py:655)
-          v = __half2float(__float2half_rn(v));
-          const float* wr = s_w + (ci * 9 + ky * 3 + kx) * cout + cch * 8;
-          const float4 w0 = *reinterpret_cast<const float4*>(wr);
-          const float4 w1 = *reinterpret_cast<const float4*>(wr + 4);
-          acc[0] = fmaf(v, w0.x, acc[0]);
-          acc[1] = fmaf(v, w0.y, acc[1]);
-          acc[2] = fmaf(v, w0.z, acc[2]);
-          acc[3] = fmaf(v, w0.w, acc[3]);
-          acc[4] = fmaf(v, w1.x, acc[4]);
-          acc[5] = fmaf(v, w1.y, acc[5]);
-          acc[6] = fmaf(v, w1.z, acc[6]);
-          acc[7] = fmaf(v, w1.w, acc[7]);
-        }
+    for (int j = 0; j < 64; ++j) vals[j] = __float2half_rn(0.f);
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = y + ky - 1;
+      if (yy < 0 || yy >= h) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xc = xx + kx - 1;
+        if (xc < 0 || xc >= w) continue;
+        for (int ci = 0; ci < cin; ++ci)
+          vals[(ky * 3 + kx) * cin + ci] =
+              __float2half_rn(__ldg(x + (static_cast<size_t>(img) * cin + ci) * hw + static_cast<size_t>(yy) * w + xc));
       }
     }
-    st_half8(out + p * ld_out + cch * 8, float_to_half8(acc));
+    Half8* o = reinterpret_cast<Half8*>(out + p * ld_out);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) o[q] = *reinterpret_cast<const Half8*>(&vals[8 * q]);
   }
 }
 
@@ -359,6 +398,13 @@ extern "C" int gd_linear_f32(const float* x, int32_t ldx, const float* w, const 
   GD_REQUIRE(x && w && y && m > 0 && k > 0 && n > 0, "gd_linear_f32: bad arguments");
   GD_REQUIRE(ldx >= k && ldy >= n, "gd_linear_f32: bad leading dimensions");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (m > 16) {  // many rows: tiled GEMM (weights are re-used across rows through shared memory)
+    dim3 grid2((n + 63) / 64, (m + 63) / 64);
+    sgemm_nt_kernel<<<grid2, 256, 0, st>>>(x, ldx, w, b, add, ld_add, y, ldy, m, k, n, silu_in, silu_out);
+    GD_CHECK_CUDA(cudaGetLastError());
+    count_launch(1);
+    return 0;
+  }
   const int warps = 8;
   const int grid = (n + warps - 1) / warps;
   if (silu_in)
@@ -381,28 +427,14 @@ extern "C" int gd_embedding_gather(const float* table, const int64_t* idx, float
   return 0;
 }
 
-extern "C" int gd_conv3x3_small_cin(const float* x, const float* w, const float* bias, void* out, int32_t ld_out,
-                                    int32_t n, int32_t cin, int32_t h, int32_t w_, int32_t cout, void* stream) {
-  GD_REQUIRE(x && w && out, "gd_conv3x3_small_cin: null pointer");
-  GD_REQUIRE(cin >= 1 && cin <= 8, "gd_conv3x3_small_cin: cin must be <= 8, got %d", cin);
-  GD_REQUIRE(cout % 8 == 0 && cout <= 1024 && ld_out % 8 == 0 && ld_out >= cout, "gd_conv3x3_small_cin: bad cout/ld_out");
-  const int c8 = cout / 8;
-  int rep = 256 / c8;
-  if (rep < 1) rep = 1;
-  const int threads = c8 * rep;
-  const size_t smem = static_cast<size_t>(cin) * 9 * cout * sizeof(float);
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    GD_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_small_cin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem)));
-    smem_set = smem;
-  }
-  const size_t total_px = static_cast<size_t>(n) * h * w_;
-  size_t grid = (total_px + rep * 8 - 1) / (rep * 8);
-  if (grid > 148 * 8) grid = 148 * 8;
-  if (grid < 1) grid = 1;
-  conv3x3_small_cin_kernel<<<static_cast<int>(grid), threads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      x, w, bias, reinterpret_cast<__half*>(out), ld_out, n, cin, h, w_, cout, c8, rep);
+extern "C" int gd_im2col3x3_small_cin(const float* x, void* out, int32_t ld_out, int32_t n, int32_t cin, int32_t h,
+                                      int32_t w, void* stream) {
+  GD_REQUIRE(x && out, "gd_im2col3x3_small_cin: null pointer");
+  GD_REQUIRE(cin >= 1 && cin * 9 <= 64, "gd_im2col3x3_small_cin: cin*9 must fit one 64-wide K block, got cin=%d", cin);
+  GD_REQUIRE(ld_out >= 64 && ld_out % 8 == 0, "gd_im2col3x3_small_cin: bad ld_out %d", ld_out);
+  const size_t total = static_cast<size_t>(n) * h * w;
+  im2col3x3_small_cin_kernel<<<grid_for(total, 128, 148 * 32), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, reinterpret_cast<__half*>(out), ld_out, n, cin, h, w);
   GD_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
   return 0;

@@ -185,8 +185,9 @@ __device__ __forceinline__ void norm_act(const Half8& v, const float (&a)[8], co
 template <bool kSilu, int kMode>
 __global__ void gn_apply_kernel(const __half* __restrict__ x, int ld, const float* __restrict__ mean_rstd,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
-                                const float* __restrict__ film, int film_ld, __half* __restrict__ out, int ld_out, int h,
-                                int w, int c, int c8, int rep, int px_per_chunk) {
+                                const float* __restrict__ film, int film_ld, __half* __restrict__ out, int ld_out,
+                                __half* __restrict__ aux, int ld_aux, int h, int w, int c, int c8, int rep,
+                                int px_per_chunk) {
   const int n = blockIdx.y, chunk = blockIdx.x;
   const int cch = threadIdx.x % c8, pl = threadIdx.x / c8;
   float a[8], b[8];
@@ -240,6 +241,18 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, int ld, const floa
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] = (acc[j] + r[j]) * 0.25f;
       st_half8(o + static_cast<size_t>(p) * ld_out, float_to_half8(acc));
+      if (aux != nullptr) {
+        // side output: avg-pool of the RAW input = x_upd(x) of a down ResBlock (unet.py:195,241), the identity
+        // residual the block's second conv adds; costs one extra quarter-size write instead of a 4-way gather there
+        float x0[8], x1[8], x2[8], x3[8];
+        half8_to_float(v0, x0);
+        half8_to_float(v1, x1);
+        half8_to_float(v2, x2);
+        half8_to_float(v3, x3);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x0[j] = 0.25f * (x0[j] + x1[j] + x2[j] + x3[j]);
+        st_half8(aux + (static_cast<size_t>(n) * hw_out + p) * ld_aux + cch * 8, float_to_half8(x0));
+      }
     }
   } else {  // GD_GN_UPSAMPLE2
     const int wo = w * 2;
@@ -472,20 +485,24 @@ extern "C" int gd_groupnorm_stats(const void* x, int32_t ld, int32_t n, int32_t 
 extern "C" int gd_groupnorm_apply(const void* x, int32_t ld, const float* mean_rstd, const float* gamma,
                                   const float* beta, const float* film, int32_t film_ld, void* out, int32_t ld_out,
                                   int32_t n, int32_t h, int32_t w, int32_t c, int32_t silu, int32_t spatial_mode,
-                                  void* stream) {
+                                  void* aux_out, int32_t ld_aux, void* stream) {
   if (int rc = check_gn_common("gd_groupnorm_apply", x, ld, n, h * w, c)) return rc;
   GD_REQUIRE(mean_rstd && gamma && beta && out, "gd_groupnorm_apply: null pointer");
   GD_REQUIRE(ld_out >= c && ld_out % 8 == 0, "gd_groupnorm_apply: bad ld_out %d", ld_out);
   GD_REQUIRE(spatial_mode >= GD_GN_SAME && spatial_mode <= GD_GN_UPSAMPLE2, "gd_groupnorm_apply: bad spatial mode");
   if (spatial_mode == GD_GN_AVGPOOL2) GD_REQUIRE(h % 2 == 0 && w % 2 == 0, "gd_groupnorm_apply: avgpool needs even h,w");
   if (film) GD_REQUIRE(film_ld >= 2 * c, "gd_groupnorm_apply: film_ld %d < 2*c", film_ld);
+  if (aux_out)
+    GD_REQUIRE(spatial_mode == GD_GN_AVGPOOL2 && ld_aux >= c && ld_aux % 8 == 0,
+               "gd_groupnorm_apply: aux output only exists for the avg-pool mode (ld_aux %d)", ld_aux);
   const int hw_iter = spatial_mode == GD_GN_AVGPOOL2 ? (h / 2) * (w / 2) : h * w;
   const Geo g = make_geo(c, hw_iter);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   GD_GN_DISPATCH(gn_apply_kernel, silu, spatial_mode,
                  <<<dim3(g.chunks, n), g.threads, 0, st>>>(reinterpret_cast<const __half*>(x), ld, mean_rstd, gamma,
-                                                          beta, film, film_ld, reinterpret_cast<__half*>(out), ld_out, h,
-                                                          w, c, g.c8, g.rep, g.px_per_chunk));
+                                                          beta, film, film_ld, reinterpret_cast<__half*>(out), ld_out,
+                                                          reinterpret_cast<__half*>(aux_out), ld_aux, h, w, c, g.c8,
+                                                          g.rep, g.px_per_chunk));
   GD_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
   return 0;

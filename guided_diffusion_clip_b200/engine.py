@@ -138,6 +138,14 @@ def pack_conv3x3_bwd(w: th.Tensor) -> th.Tensor:
     return _pad_rows(m)
 
 
+def pack_conv_in(w: th.Tensor) -> th.Tensor:
+    """First-layer weights [Co,Ci,3,3] (Ci*9 <= 64) -> [Co_pad][64] matching gd_im2col3x3_small_cin: k = (ky*3+kx)*Ci + ci."""
+    co, ci = w.shape[:2]
+    m = w.float().permute(0, 2, 3, 1).reshape(co, 9 * ci)
+    m = th.cat([m, m.new_zeros(co, 64 - 9 * ci)], 1)
+    return _pad_rows(m)
+
+
 def pack_1x1(w: th.Tensor) -> th.Tensor:
     return _pad_rows(w.float().reshape(w.shape[0], -1))
 
@@ -236,11 +244,12 @@ class Emitter:
                       _p(self._gn_workspace()), _p(stats))
 
     def gn_apply(self, x: View, stats, gamma, beta, out: View, *, silu: bool, film=None, film_ld=0,
-                 mode=L.GN_SAME) -> None:
+                 mode=L.GN_SAME, aux: Optional[View] = None) -> None:
         self.keep += [gamma, beta]
         self.prog.add("gd_groupnorm_apply", C.c_void_p(x.ptr), x.ld, _p(stats), _p(gamma), _p(beta),
                       C.c_void_p(film) if film else None, film_ld, C.c_void_p(out.ptr), out.ld, x.n, x.h, x.w, x.c,
-                      int(silu), mode)
+                      int(silu), mode, C.c_void_p(aux.ptr) if aux is not None else None,
+                      aux.ld if aux is not None else 0)
 
     def gn_bwd(self, x: View, stats, gamma, beta, dy: View, dx: View, *, silu: bool, film=None, film_ld=0,
                mode=L.GN_SAME, add: Optional[View] = None, add_mode=L.GN_SAME) -> None:
@@ -296,12 +305,11 @@ class Emitter:
 
     # ---- blocks -------------------------------------------------------------------------------
     def conv_in(self, l: ConvInSpec, x_nchw: th.Tensor, out: View) -> None:
-        w = self.P[f"{l.key}.weight"]
-        w32 = w.float().reshape(l.cout, -1).contiguous()
-        b32 = self.f32(f"{l.key}.bias")
-        self.keep += [w32, x_nchw]
-        self.prog.add("gd_conv3x3_small_cin", _p(x_nchw), _p(w32), _p(b32), C.c_void_p(out.ptr), out.ld, out.n, l.cin,
-                      out.h, out.w, l.cout)
+        """First layer (unet.py:483): im2col to one 64-wide K block (cin*9 <= 64), then a K=64 GEMM on the tcgen05 kernel."""
+        cols = self.scratch("im2col", out.n, out.h, out.w, 64)
+        self.keep.append(x_nchw)
+        self.prog.add("gd_im2col3x3_small_cin", _p(x_nchw), C.c_void_p(cols.ptr), cols.ld, out.n, l.cin, out.h, out.w)
+        self.conv(cols, pack_conv_in(self.P[f"{l.key}.weight"]), self.f32(f"{l.key}.bias"), l.cout, out, taps=1)
 
     def res_block(self, r: ResSpec, x: View, out: View, film_all: th.Tensor, tape: Optional[list] = None) -> None:
         """ResBlock._forward (unet.py:236-256) in 6 launches: GN stats, GN-apply(+SiLU, +pool/upsample), conv,
@@ -318,8 +326,10 @@ class Emitter:
         st1, st2 = self.stats_buf(), self.stats_buf()
         a = self.scratch("gn_out", n, ho, wo, r.cin)
         self.gn_stats(x, st1)
+        # down blocks: the same pass that pools SiLU(GN(x)) also emits avgpool(x), the block's identity residual
+        x_pool = self.scratch("x_pool", n, ho, wo, r.cin) if r.mode == "down" else None
         self.gn_apply(x, st1, self.f32(f"{k}.in_layers.0.weight"), self.f32(f"{k}.in_layers.0.bias"), a, silu=True,
-                      mode=gmode)
+                      mode=gmode, aux=x_pool)
         h1 = self.act(n, ho, wo, r.cout) if tape is not None else self.scratch("h1", n, ho, wo, r.cout)
         w1 = pack_conv3x3(self.P[f"{k}.in_layers.2.weight"])
         self.conv(a, w1, self.f32(f"{k}.in_layers.2.bias"), r.cout, h1)
@@ -335,7 +345,10 @@ class Emitter:
             self.conv(b, w2, bias2, r.cout, out, a1=x)
         else:
             w2 = pack_conv3x3(self.P[f"{k}.out_layers.3.weight"])
-            self.conv(b, w2, self.f32(f"{k}.out_layers.3.bias"), r.cout, out, res=x, res_mode=rmode)
+            if x_pool is not None:
+                self.conv(b, w2, self.f32(f"{k}.out_layers.3.bias"), r.cout, out, res=x_pool, res_mode=L.RES_SAME)
+            else:
+                self.conv(b, w2, self.f32(f"{k}.out_layers.3.bias"), r.cout, out, res=x, res_mode=rmode)
         if tape is not None:
             tape.append(("res", r, x, st1, h1, st2, film_ptr, film_all.shape[1], out))
 

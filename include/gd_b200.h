@@ -68,10 +68,10 @@ typedef struct gd_conv_desc {
 } gd_conv_desc;
 int gd_conv_igemm(const gd_conv_desc* desc, void* stream);
 
-/* Direct 3x3 conv for tiny C_in (3 or 6): the first layer input_blocks.0.0 (unet.py:483,741).
- * x: fp32 NCHW [n,cin,h,w]; w: fp32 [cout][cin*9] (OIHW flattened); out: fp16 NHWC view. */
-int gd_conv3x3_small_cin(const float* x, const float* w, const float* bias, void* out, int32_t ld_out, int32_t n,
-                         int32_t cin, int32_t h, int32_t w_, int32_t cout, void* stream);
+/* im2col for the first layer input_blocks.0.0 (unet.py:483,741), C_in = 3 or 6: fp32 NCHW [n,cin,h,w] -> fp16 NHWC
+ * [n,h,w,64] with channel k = (ky*3+kx)*cin + ci, zero padded; the conv itself then runs on gd_conv_igemm with taps=1. */
+int gd_im2col3x3_small_cin(const float* x, void* out, int32_t ld_out, int32_t n, int32_t cin, int32_t h, int32_t w,
+                           void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * GroupNorm32 (+SiLU) (+FiLM scale/shift) (+avgpool2 / nearest-upsample2), nn.py:17-19,93-100 with
@@ -83,9 +83,11 @@ int gd_conv3x3_small_cin(const float* x, const float* w, const float* bias, void
 int gd_groupnorm_stats(const void* x, int32_t ld, int32_t n, int32_t hw, int32_t c, float eps, float* partial_ws,
                        float* mean_rstd, void* stream);
 int64_t gd_groupnorm_ws_floats(int32_t n, int32_t hw, int32_t c);
+/* aux_out (GD_GN_AVGPOOL2 only, may be NULL): fp16 [n,h/2,w/2,c] view receiving avgpool2(x) of the RAW input, i.e. the
+ * x_upd(x) residual of a down ResBlock (unet.py:195,241). */
 int gd_groupnorm_apply(const void* x, int32_t ld, const float* mean_rstd, const float* gamma, const float* beta,
                        const float* film, int32_t film_ld, void* out, int32_t ld_out, int32_t n, int32_t h, int32_t w,
-                       int32_t c, int32_t silu, int32_t spatial_mode, void* stream);
+                       int32_t c, int32_t silu, int32_t spatial_mode, void* aux_out, int32_t ld_aux, void* stream);
 /* Backward of the fused op above w.r.t. x (no parameter gradients; the guidance gradient needs dX only).
  * dy is at the OUTPUT resolution of the forward op; dx (fp16 view, input resolution) = result (+ add if given). */
 /* add_mode: GD_GN_SAME = add is at dx's resolution; GD_GN_AVGPOOL2 = add is the gradient of an avg-pooled copy of x

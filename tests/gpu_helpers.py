@@ -60,7 +60,8 @@ def gn_stats(x_buf, c, off=0):
     return st
 
 
-def gn_apply(x_buf, c, st, gamma, beta, *, film=None, silu=True, mode=L.GN_SAME, off=0, ld_out=None, out_off=0):
+def gn_apply(x_buf, c, st, gamma, beta, *, film=None, silu=True, mode=L.GN_SAME, off=0, ld_out=None, out_off=0,
+             aux=None):
     lib = L.load()
     n, h, w, ld = x_buf.shape
     ho, wo = (h // 2, w // 2) if mode == L.GN_AVGPOOL2 else (h * 2, w * 2) if mode == L.GN_UPSAMPLE2 else (h, w)
@@ -69,7 +70,7 @@ def gn_apply(x_buf, c, st, gamma, beta, *, film=None, silu=True, mode=L.GN_SAME,
     L.check(lib.gd_groupnorm_apply(C.c_void_p(x_buf.data_ptr() + 2 * off), ld, vp(st), vp(gamma), vp(beta), vp(film),
                                    film.shape[1] if film is not None else 0,
                                    C.c_void_p(out.data_ptr() + 2 * out_off), ld_out, n, h, w, c, int(silu), mode,
-                                   stream()), "gd_groupnorm_apply")
+                                   vp(aux), aux.shape[-1] if aux is not None else 0, stream()), "gd_groupnorm_apply")
     return out
 
 

@@ -165,18 +165,21 @@ def test_conv_linearity_full_size(lib):
     assert worst < 2e-2
 
 
-def test_conv_first_layer_direct(lib):
-    n, cin, h, w, cout = 2, 3, 32, 32, 128
+@pytest.mark.parametrize("cin", [3, 6])
+def test_conv_first_layer_im2col(lib, cin):
+    """input_blocks.0.0 (unet.py:483): fp32 NCHW -> 64-wide im2col -> K=64 GEMM; cin=6 is the super-resolution input."""
+    from guided_diffusion_clip_b200.engine import pack_conv_in
+    n, h, w, cout = 2, 32, 32, 128
     x = _rand((n, cin, h, w), 24)
-    wt = _h(_rand((cout, cin, 3, 3), 25, 27 ** -0.5))
+    wt = _h(_rand((cout, cin, 3, 3), 25, (cin * 9) ** -0.5))
     b = _rand((cout,), 26, 0.1)
     ref = F.conv2d(_h(x), wt, b, padding=1)
-    out = th.zeros((n, h, w, cout), dtype=th.float16, device="cuda")
-    w32 = wt.reshape(cout, -1).contiguous()
-    L.check(lib.gd_conv3x3_small_cin(H.vp(x), H.vp(w32), H.vp(b), H.vp(out), cout, n, cin, h, w, cout, H.stream()))
+    cols = th.zeros((n, h, w, 64), dtype=th.float16, device="cuda")
+    L.check(lib.gd_im2col3x3_small_cin(H.vp(x), H.vp(cols), 64, n, cin, h, w, H.stream()))
+    out = H.conv_igemm(cols, 64, 0, pack_conv_in(wt), b, cout, n, h, w, taps=1)
     th.cuda.synchronize()
     err = H.rel_err(out.permute(0, 3, 1, 2), ref)
-    print(f"first conv: rel err {err:.3e}")
+    print(f"first conv cin={cin}: rel err {err:.3e}")
     assert err < TOL
 
 

@@ -50,8 +50,11 @@ def test_groupnorm_forward(lib, c, h, w, mode):
         y = F.interpolate(y, scale_factor=2, mode="nearest")
     xb = H.nhwc_half(x, ld=c + 32, off=32)
     st = H.gn_stats(xb, c, off=32)
-    out = H.gn_apply(xb, c, st, gamma, beta, film=film, silu=True, mode=mode, off=32)
+    aux = th.zeros((n, h // 2, w // 2, c), dtype=th.float16, device="cuda") if mode == L.GN_AVGPOOL2 else None
+    out = H.gn_apply(xb, c, st, gamma, beta, film=film, silu=True, mode=mode, off=32, aux=aux)
     th.cuda.synchronize()
+    if aux is not None:  # side output: avgpool of the raw input (x_upd of a down ResBlock)
+        assert H.rel_err(aux.permute(0, 3, 1, 2), F.avg_pool2d(x, 2)) < 2e-3
     ref_mean = x.reshape(n, 32, -1).mean(-1)
     assert float((st[..., 0] - ref_mean).abs().max()) < 1e-4
     err = H.rel_err(out.permute(0, 3, 1, 2), y)
