@@ -32,6 +32,7 @@ class ConvDesc(C.Structure):
         ("res", vp), ("ld_res", i32), ("res_mode", i32),
         ("out", vp), ("ld_out", i32), ("out_mode", i32),
         ("bn", i32), ("out_scale", f32),
+        ("stats_out", vp),
     ]
 
 
@@ -53,6 +54,8 @@ SIGNATURES = {
     "gd_launch_count_reset": (None, []),
     "gd_debug_set": (None, [C.c_int, C.c_int]),
     "gd_conv_igemm": (C.c_int, [C.POINTER(ConvDesc), vp]),
+    "gd_conv_stats_rows": (i64, [i32, i32, i32, C.POINTER(i32)]),
+    "gd_groupnorm_finalize_partials": (C.c_int, [vp, i32, i32, vp, i32, i32, i32, i32, i32, f32, vp, vp]),
     "gd_im2col3x3_small_cin": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, vp]),
     "gd_groupnorm_stats": (C.c_int, [vp, i32, i32, i32, i32, f32, vp, vp, vp]),
     "gd_groupnorm_ws_floats": (i64, [i32, i32, i32]),

@@ -65,6 +65,8 @@ struct ConvArgs {
   int out_mode;
   float out_scale;
   int tma_epi;  // 1 = staged TMA-store epilogue
+  float* stats;  // optional GroupNorm partials [m_tiles*4][stats_ld][2] (sum, sum of squares per 4-channel chunk)
+  int stats_ld;  // n_pad / 4
   int debug;    // 0 = normal; 1 = epilogue skipped (barriers only); 2 = TMEM loads only (timing experiments)
 };
 
@@ -398,6 +400,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           }
           if (p.debug == 0) {
             const bool has_res = p.res_mode != GD_RES_NONE;
+            float cs[32];  // [0,16): per-4-channel-chunk sums of this row, [16,32): sums of squares
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               float f[8];
@@ -421,7 +424,34 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
 #pragma unroll
                 for (int j = 0; j < 8; ++j) f[j] *= p.out_scale;
               }
-              *reinterpret_cast<Half8*>(sw128(s_out, row, q)) = float_to_half8(f);
+              const Half8 hv = float_to_half8(f);
+              *reinterpret_cast<Half8*>(sw128(s_out, row, q)) = hv;
+              if (p.stats != nullptr) {
+                // GroupNorm statistics of the STORED (fp16-rounded) values; rows outside the image contribute 0
+                float r[8];
+                half8_to_float(hv, r);
+                const float m = e.valid ? 1.0f : 0.0f;
+                cs[2 * q] = m * ((r[0] + r[1]) + (r[2] + r[3]));
+                cs[2 * q + 1] = m * ((r[4] + r[5]) + (r[6] + r[7]));
+                cs[16 + 2 * q] = m * ((r[0] * r[0] + r[1] * r[1]) + (r[2] * r[2] + r[3] * r[3]));
+                cs[16 + 2 * q + 1] = m * ((r[4] * r[4] + r[5] * r[5]) + (r[6] * r[6] + r[7] * r[7]));
+              }
+            }
+            if (p.stats != nullptr) {
+              // reduce the 32 values over the warp's 32 rows with a halving butterfly (31 shuffles): lane L ends up
+              // holding the warp total of value L, then one coalesced 128-byte store per warp
+#pragma unroll
+              for (int off = 16; off >= 1; off >>= 1) {
+                const bool hi = (lane & off) != 0;
+#pragma unroll
+                for (int i = 0; i < off; ++i) {
+                  const float send = hi ? cs[i] : cs[i + off];
+                  const float keep = hi ? cs[i + off] : cs[i];
+                  cs[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+              }
+              float* sp = p.stats + (static_cast<size_t>(m_tile) * 4 + quarter) * p.stats_ld * 2;
+              sp[(((col_base + c0) >> 2) + (lane & 15)) * 2 + (lane >> 4)] = cs[0];
             }
             fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
           }
@@ -516,15 +546,31 @@ void conv_debug_set(int key, int value) {
 // N tile: the largest divisor of n_pad (multiple of 16, <= 256) that still yields enough tiles to fill the SMs;
 // small-spatial layers (8x8 / 16x16 with C = 1024) otherwise run on 4-16 CTAs.  Below 32 columns the MMA is
 // shared-memory bound, so 32 is the floor unless n_pad itself is smaller.
-int conv_pick_bn(int n_pad, int m_tiles, int num_sms) {
+int conv_pick_bn(int n_pad, int m_tiles, int num_sms, int step) {
   int best = 0;
-  for (int bn = 256; bn >= 16; bn -= 16) {
+  for (int bn = 256; bn >= step; bn -= step) {
     if (n_pad % bn != 0) continue;
     if (best == 0) best = bn;  // largest divisor
     if (static_cast<long long>(m_tiles) * (n_pad / bn) * 100 >= 85LL * num_sms) return bn;
     if (bn >= 32) best = bn;
   }
   return best ? best : 16;
+}
+
+// Output patch of one 128-row tile: BW x BH pixels of BI images, BW*BH*BI == 128 (powers of two).
+bool patch_shape(int h, int w, int& bw, int& bh, int& bi) {
+  bw = w < 16 ? w : 16;
+  int p2 = 1;
+  while (p2 * 2 <= bw) p2 *= 2;
+  bw = p2;
+  bh = 128 / bw;
+  if (bh > h) {
+    int q = 1;
+    while (q * 2 <= h) q *= 2;
+    bh = q;
+  }
+  bi = 128 / (bw * bh);
+  return bi >= 1 && bi <= 256 && bw * bh * bi == 128;
 }
 
 }  // namespace gd
@@ -557,21 +603,13 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
     if (d->res_mode == GD_RES_UPSAMPLE2) GD_REQUIRE(d->h % 2 == 0 && d->w % 2 == 0, "gd_conv_igemm: odd upsample target");
   }
 
-  // patch shape: BW x BH x BI == 128 pixels
-  int bw = d->w < 16 ? d->w : 16;
-  // round bw down to a power of two so 128 % bw == 0
-  int p2 = 1;
-  while (p2 * 2 <= bw) p2 *= 2;
-  bw = p2;
-  int bh = 128 / bw;
-  if (bh > d->h) {
-    int q = 1;
-    while (q * 2 <= d->h) q *= 2;
-    bh = q;
-  }
-  int bi = 128 / (bw * bh);
-  GD_REQUIRE(bi >= 1 && bi <= 256 && bw * bh * bi == 128, "gd_conv_igemm: cannot tile %dx%d into 128-pixel patches", d->h,
-             d->w);
+  int bw, bh, bi;
+  GD_REQUIRE(patch_shape(d->h, d->w, bw, bh, bi), "gd_conv_igemm: cannot tile %dx%d into 128-pixel patches", d->h, d->w);
+  const bool want_stats = d->stats_out != nullptr;
+  if (want_stats)
+    GD_REQUIRE(d->out_mode == GD_OUT_NHWC_F16 && d->cout % 64 == 0 && d->n_pad == d->cout && bw * bh >= 32 &&
+                   (d->bn == 0 || d->bn % 64 == 0),
+               "gd_conv_igemm: fused GroupNorm statistics need fp16 NHWC output, cout %% 64 == 0 and >= 32 pixels/image");
 
   if (g_num_sms == 0) {
     int dev = 0;
@@ -579,8 +617,10 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
     GD_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int m_tiles = ((d->w + bw - 1) / bw) * ((d->h + bh - 1) / bh) * ((d->n + bi - 1) / bi);
-  int bn = d->bn > 0 ? d->bn : (g_force_bn > 0 && d->n_pad % g_force_bn == 0 ? g_force_bn
-                                                                              : conv_pick_bn(d->n_pad, m_tiles, g_num_sms));
+  int bn = d->bn > 0 ? d->bn
+                     : (g_force_bn > 0 && d->n_pad % g_force_bn == 0 && !want_stats
+                            ? g_force_bn
+                            : conv_pick_bn(d->n_pad, m_tiles, g_num_sms, want_stats ? 64 : 16));
   GD_REQUIRE(bn % 16 == 0 && bn >= 16 && bn <= 256 && d->n_pad % bn == 0, "gd_conv_igemm: bad N tile %d for n_pad %d", bn,
              d->n_pad);
 
@@ -622,6 +662,9 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
                !(d->res_mode == GD_RES_UPSAMPLE2 && (bw % 2 || bh % 2)))
                   ? 1
                   : 0;
+  GD_REQUIRE(!want_stats || p.tma_epi, "gd_conv_igemm: fused statistics need the staged epilogue (aligned fp16 output)");
+  p.stats = d->stats_out;
+  p.stats_ld = d->n_pad / 4;
 
   CUtensorMap ma0, ma1, mb, mout, mres;
   int rc = encode_act_map(&ma0, d->a0, d->c0, d->ld0, d->n, d->h, d->w, bi, bh, bw);
@@ -661,4 +704,16 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
   GD_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
   return 0;
+}
+
+extern "C" int64_t gd_conv_stats_rows(int32_t n, int32_t h, int32_t w, int32_t* rows_per_image) {
+  int bw, bh, bi;
+  if (n <= 0 || h <= 0 || w <= 0 || !gd::patch_shape(h, w, bw, bh, bi) || bw * bh < 32) {
+    if (rows_per_image) *rows_per_image = 0;
+    return 0;
+  }
+  const int tiles_per_group = ((w + bw - 1) / bw) * ((h + bh - 1) / bh);
+  const int groups = (n + bi - 1) / bi;
+  if (rows_per_image) *rows_per_image = tiles_per_group * 4 / bi;
+  return static_cast<int64_t>(groups) * tiles_per_group * 4;
 }

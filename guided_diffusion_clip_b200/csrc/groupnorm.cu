@@ -434,10 +434,70 @@ __global__ void gn_bwd_apply_kernel(const __half* __restrict__ x, int ld, const 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// mean / rstd from the partials a producing conv's epilogue emitted (gd_conv_desc.stats_out): per 32-pixel row
+// block and 4-channel chunk (sum, sum of squares).  The normalised tensor may be the concatenation of two conv
+// outputs (c0 channels from p0, then c1 from p1); a group may straddle the boundary.
+// One CTA per (group, image); fixed-order tree reduction in fp64 -> bitwise reproducible.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+gn_finalize_partials_kernel(const float* __restrict__ p0, int c0, int ld0, const float* __restrict__ p1, int c1,
+                            int ld1, int rows_per_image, double inv_count, float eps, float* __restrict__ out) {
+  __shared__ double sh[2][128];
+  const int g = blockIdx.x, n = blockIdx.y, tid = threadIdx.x;
+  const int cpg = (c0 + c1) / kGroups;
+  const int ch_lo = g * cpg, ch_hi = ch_lo + cpg;
+  double s = 0.0, ss = 0.0;
+  for (int r = tid; r < rows_per_image; r += 128) {
+    const size_t row = static_cast<size_t>(n) * rows_per_image + r;
+    for (int ch = ch_lo; ch < ch_hi; ch += 4) {
+      const float* src = ch < c0 ? p0 + (row * ld0 + (ch >> 2)) * 2 : p1 + (row * ld1 + ((ch - c0) >> 2)) * 2;
+      const float2 v = *reinterpret_cast<const float2*>(src);
+      s += v.x;
+      ss += v.y;
+    }
+  }
+  sh[0][tid] = s;
+  sh[1][tid] = ss;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if (tid < o) {
+      sh[0][tid] += sh[0][tid + o];
+      sh[1][tid] += sh[1][tid + o];
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const double mean = sh[0][0] * inv_count;
+    double var = sh[1][0] * inv_count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    float* o = out + (static_cast<size_t>(n) * kGroups + g) * 2;
+    o[0] = static_cast<float>(mean);
+    o[1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+}
+
 }  // namespace
 }  // namespace gd
 
 using namespace gd;
+
+extern "C" int gd_groupnorm_finalize_partials(const float* p0, int32_t c0, int32_t ld0, const float* p1, int32_t c1,
+                                              int32_t ld1, int32_t rows_per_image, int32_t n, int32_t hw, float eps,
+                                              float* mean_rstd, void* stream) {
+  GD_REQUIRE(p0 && mean_rstd && n > 0 && hw > 0 && rows_per_image > 0, "gd_groupnorm_finalize_partials: bad arguments");
+  if (p1 == nullptr) c1 = 0;
+  const int c = c0 + c1;
+  GD_REQUIRE(c0 > 0 && c0 % 4 == 0 && c1 % 4 == 0 && c % 32 == 0 && (c / 32) % 4 == 0,
+             "gd_groupnorm_finalize_partials: needs channels-per-group %% 4 == 0 (c0=%d c1=%d)", c0, c1);
+  GD_REQUIRE(ld0 >= c0 / 4 && (p1 == nullptr || ld1 >= c1 / 4), "gd_groupnorm_finalize_partials: bad leading dimension");
+  const double inv_count = 1.0 / (static_cast<double>(hw) * static_cast<double>(c / kGroups));
+  gn_finalize_partials_kernel<<<dim3(kGroups, n), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      p0, c0, ld0, p1, c1, ld1, rows_per_image, inv_count, eps, mean_rstd);
+  GD_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
 
 extern "C" int64_t gd_groupnorm_ws_floats(int32_t n, int32_t hw, int32_t c) {
   (void)hw;

@@ -170,6 +170,8 @@ class Emitter:
         self.keep: List[th.Tensor] = []
         self.gn_ws = None
         self._gn_ws_floats = 0
+        self._producers: Dict[tuple, tuple] = {}   # (buffer ptr, channel offset, C) -> (ConvDesc, n, h, w)
+        self._stats_bufs: Dict[int, th.Tensor] = {}  # id(ConvDesc) -> fused GroupNorm partials of that conv
 
     # ---- buffers ------------------------------------------------------------------------------
     def scratch(self, role: str, n, h, w, c) -> View:
@@ -236,10 +238,48 @@ class Emitter:
         d.out_mode = out_mode
         d.bn = 0
         d.out_scale = out_scale
+        d.stats_out = None
         self.keep += [wpack, bias, d]
         self.prog.add("gd_conv_igemm", C.byref(d))
+        if out_mode == L.OUT_NHWC_F16 and cout == out.c and cout % 64 == 0 and wpack.shape[0] == cout:
+            # latest writer of this channel view: a later GroupNorm over it can ask this conv for fused statistics
+            self._producers[(out.buf.data_ptr(), out.off, out.c)] = (d, n, h, w)
+
+    def _producers_of(self, x: View):
+        """The conv launch(es) that wrote view x: one conv, or two convs writing adjacent channel slices (skip concat)."""
+        base = x.buf.data_ptr()
+        hit = self._producers.get((base, x.off, x.c))
+        if hit is not None:
+            return [(hit, x.c)]
+        for (b, off, c), prod in self._producers.items():
+            if b == base and off == x.off and c < x.c:
+                rest = self._producers.get((base, x.off + c, x.c - c))
+                if rest is not None:
+                    return [(prod, c), (rest, x.c - c)]
+        return None
 
     def gn_stats(self, x: View, stats: th.Tensor) -> None:
+        """GroupNorm32 statistics of x.  Preferred: the producing conv(s) emit per-row-block partial sums from their
+        epilogue (no extra pass over the tensor) and a tiny finalize kernel turns them into mean/rstd; otherwise the
+        two-launch statistics kernels read the tensor once."""
+        lib = L.load()
+        parts = self._producers_of(x) if os.environ.get("GD_B200_NO_FUSED_STATS", "0") != "1" else None
+        rpi = C.c_int32(0)
+        rows = int(lib.gd_conv_stats_rows(x.n, x.h, x.w, C.byref(rpi))) if parts else 0
+        if parts and rows > 0 and (x.c // 32) % 4 == 0 and all((n_, h_, w_) == (x.n, x.h, x.w)
+                                                                for (_, n_, h_, w_), _c in parts):
+            bufs = []
+            for (desc, _n, _h, _w), c in parts:
+                buf = self._stats_bufs.get(id(desc))
+                if buf is None:
+                    buf = th.zeros((rows, c // 4, 2), dtype=th.float32, device=self.device)
+                    self._stats_bufs[id(desc)] = buf
+                    desc.stats_out = buf.data_ptr()
+                bufs.append((buf, c))
+            (p0, c0), (p1, c1) = bufs[0], (bufs[1] if len(bufs) > 1 else (None, 0))
+            self.prog.add("gd_groupnorm_finalize_partials", _p(p0), c0, c0 // 4, _p(p1), c1, c1 // 4, rpi.value, x.n,
+                          x.h * x.w, C.c_float(GN_EPS), _p(stats))
+            return
         self.prog.add("gd_groupnorm_stats", C.c_void_p(x.ptr), x.ld, x.n, x.h * x.w, x.c, C.c_float(GN_EPS),
                       _p(self._gn_workspace()), _p(stats))
 

@@ -65,8 +65,20 @@ typedef struct gd_conv_desc {
   int32_t ld_out, out_mode;
   int32_t bn; /* N tile, 0 = auto */
   float out_scale; /* 0 is treated as 1 */
+  /* Optional fused GroupNorm statistics of the stored output (consumed by gd_groupnorm_finalize_partials):
+   * fp32 [gd_conv_stats_rows(n,h,w)][n_pad/4][2] = per (32-pixel row block, 4-channel chunk) sum and sum of squares.
+   * Requires fp16 NHWC output, cout % 64 == 0 and h*w >= 32 per image; NULL = not produced. */
+  float* stats_out;
 } gd_conv_desc;
 int gd_conv_igemm(const gd_conv_desc* desc, void* stream);
+/* Geometry of the fused statistics: number of 32-pixel row blocks the conv writes (rows of stats_out), and how many
+ * consecutive rows belong to one image (rows_per_image * n == rows).  Returns 0 rows if the geometry is ineligible. */
+int64_t gd_conv_stats_rows(int32_t n, int32_t h, int32_t w, int32_t* rows_per_image);
+/* mean / rstd of GroupNorm32 over a tensor whose channels come from one or two conv outputs (a skip concatenation,
+ * unet.py:661) from their fused partials: c0 (+ c1) channels, 32 groups, biased variance.  p1 may be NULL. */
+int gd_groupnorm_finalize_partials(const float* p0, int32_t c0, int32_t ld0, const float* p1, int32_t c1, int32_t ld1,
+                                   int32_t rows_per_image, int32_t n, int32_t hw, float eps, float* mean_rstd,
+                                   void* stream);
 
 /* im2col for the first layer input_blocks.0.0 (unet.py:483,741), C_in = 3 or 6: fp32 NCHW [n,cin,h,w] -> fp16 NHWC
  * [n,h,w,64] with channel k = (ky*3+kx)*cin + ci, zero padded; the conv itself then runs on gd_conv_igemm with taps=1. */

@@ -26,7 +26,8 @@ def nhwc_half(x_nchw: th.Tensor, ld: int = None, off: int = 0) -> th.Tensor:
 
 
 def conv_igemm(a0_buf, c0, off0, wpack, bias, cout, n, h, w, *, taps=9, a1_buf=None, c1=0, off1=0, res_buf=None,
-               res_off=0, res_mode=L.RES_NONE, out_mode=L.OUT_NHWC_F16, ld_out=None, out_off=0, out_scale=1.0, bn=0):
+               res_off=0, res_mode=L.RES_NONE, out_mode=L.OUT_NHWC_F16, ld_out=None, out_off=0, out_scale=1.0, bn=0,
+               stats_out=None, out_buf=None):
     lib = L.load()
     d = L.ConvDesc()
     d.a0, d.c0, d.ld0, d.taps = a0_buf.data_ptr() + 2 * off0, c0, a0_buf.shape[-1], taps
@@ -40,12 +41,13 @@ def conv_igemm(a0_buf, c0, off0, wpack, bias, cout, n, h, w, *, taps=9, a1_buf=N
         d.res, d.ld_res, d.res_mode = res_buf.data_ptr() + 2 * res_off, res_buf.shape[-1], res_mode
     if out_mode == L.OUT_NHWC_F16:
         ld_out = ld_out or cout
-        out = th.zeros((n, h, w, ld_out), dtype=th.float16, device=a0_buf.device)
+        out = out_buf if out_buf is not None else th.zeros((n, h, w, ld_out), dtype=th.float16, device=a0_buf.device)
         d.out, d.ld_out = out.data_ptr() + 2 * out_off, ld_out
     else:
         out = th.zeros((n, cout, h, w), dtype=th.float32, device=a0_buf.device)
         d.out, d.ld_out = out.data_ptr(), 0
     d.out_mode, d.bn, d.out_scale = out_mode, bn, out_scale
+    d.stats_out = stats_out.data_ptr() if stats_out is not None else None
     L.check(lib.gd_conv_igemm(C.byref(d), stream()), "gd_conv_igemm")
     return out
 

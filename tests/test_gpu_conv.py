@@ -183,6 +183,42 @@ def test_conv_first_layer_im2col(lib, cin):
     assert err < TOL
 
 
+@pytest.mark.parametrize("n,h,w,c_a,c_b", [(2, 32, 32, 128, 128), (3, 8, 8, 256, 128), (2, 16, 16, 128, 384)])
+def test_conv_fused_groupnorm_statistics(lib, n, h, w, c_a, c_b):
+    """The conv epilogue's per-row-block partial sums + gd_groupnorm_finalize_partials == GroupNorm32 statistics of the
+    stored tensor, for one producer and for a skip concatenation of two producers whose groups straddle the boundary."""
+    import ctypes as C
+    cin = 64
+    x = _h(_rand((n, cin, h, w), 30))
+    rpi = C.c_int32(0)
+    rows = int(lib.gd_conv_stats_rows(n, h, w, C.byref(rpi)))
+    assert rpi.value > 0 and rows >= rpi.value * n
+    cat = th.zeros((n, h, w, c_a + c_b), dtype=th.float16, device="cuda")
+    parts = []
+    for off, c, seed in ((0, c_a, 31), (c_a, c_b, 32)):
+        wt = _h(_rand((c, cin, 3, 3), seed, (cin * 9) ** -0.5))
+        b = _rand((c,), seed + 10, 0.5)
+        st = th.zeros((rows, c // 4, 2), dtype=th.float32, device="cuda")
+        H.conv_igemm(H.nhwc_half(x), cin, 0, pack_conv3x3(wt), b, c, n, h, w, ld_out=c_a + c_b, out_off=off, out_buf=cat,
+                     stats_out=st)
+        parts.append(st)
+    th.cuda.synchronize()
+    stored = cat.float().permute(0, 3, 1, 2)  # what a later GroupNorm will actually read
+
+    def ref_stats(t):
+        g = t.reshape(n, 32, -1)
+        return g.mean(-1), (g.var(-1, unbiased=False) + 1e-5).rsqrt()
+
+    for (p0, c0, p1, c1, t) in ((parts[0], c_a, None, 0, stored[:, :c_a]), (parts[0], c_a, parts[1], c_b, stored)):
+        out = th.zeros((n, 32, 2), dtype=th.float32, device="cuda")
+        L.check(lib.gd_groupnorm_finalize_partials(H.vp(p0), c0, c0 // 4, H.vp(p1), c1, c1 // 4, rpi.value, n, h * w,
+                                                   C.c_float(1e-5), H.vp(out), H.stream()))
+        th.cuda.synchronize()
+        mean, rstd = ref_stats(t)
+        assert float((out[..., 0] - mean).abs().max()) < 2e-4
+        assert H.rel_err(out[..., 1], rstd) < 2e-4
+
+
 def test_conv_rejects_bad_arguments(lib):
     d = L.ConvDesc()
     rc = lib.gd_conv_igemm(d, None)
