@@ -26,14 +26,20 @@ struct Geo {
   int px_per_chunk;
 };
 
-Geo make_geo(int c, int hw) {
+// CTAs per image: ~16 pixels per thread lane on big tensors, but never fewer CTAs than ~4 per SM in total (small
+// 8x8 / 16x16 layers are latency-bound otherwise) as long as every lane still gets >= 2 pixels.
+Geo make_geo(int c, int hw, int n, int max_chunks) {
   Geo g;
   g.c8 = c / 8;
   g.rep = 256 / g.c8;
   if (g.rep < 1) g.rep = 1;
   g.threads = g.c8 * g.rep;
   int chunks = (hw + g.rep * 16 - 1) / (g.rep * 16);
-  if (chunks > kMaxChunks) chunks = kMaxChunks;
+  const int want = (4 * 148 + n - 1) / n;
+  if (chunks < want) chunks = want;
+  const int max_by_work = hw / (g.rep * 2);
+  if (chunks > max_by_work) chunks = max_by_work;
+  if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
   g.px_per_chunk = (hw + chunks - 1) / chunks;
   g.chunks = (hw + g.px_per_chunk - 1) / g.px_per_chunk;
@@ -309,7 +315,7 @@ __device__ __forceinline__ void load_dy(const __half* dy, int ld_dy, int n, int 
 template <bool kSilu>
 __device__ __forceinline__ float act_grad(float z) {
   if (!kSilu) return 1.0f;
-  const float s = 1.0f / (1.0f + __expf(-z));
+  const float s = sigmoid_f(z);
   return s * (1.0f + z * (1.0f - s));
 }
 
@@ -359,10 +365,7 @@ __global__ void gn_bwd_stats_kernel(const __half* __restrict__ x, int ld, const 
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
   const int p0 = chunk * px_per_chunk, p1 = min(hw, p0 + px_per_chunk);
-  for (int p = p0 + pl; p < p1; p += rep) {
-    float xf[8], d[8];
-    half8_to_float(ld_half8(xin + static_cast<size_t>(p) * ld), xf);
-    load_dy<kMode>(dy, ld_dy, n, h, w, p, cch * 8, d);
+  auto accumulate = [&](const float (&xf)[8], const float (&d)[8]) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float xh = fmaf(xf[j], A.xa[j], A.xb[j]);
@@ -371,6 +374,32 @@ __global__ void gn_bwd_stats_kernel(const __half* __restrict__ x, int ld, const 
       s1[j] += dxh;
       s2[j] += dxh * xh;
     }
+  };
+  int p = p0 + pl;
+  if (kMode == GD_GN_SAME) {
+    // 4 pixels per iteration: all eight 16-byte loads are issued before any arithmetic
+    const __half* dyn = dy + static_cast<size_t>(n) * hw * ld_dy + cch * 8;
+    for (; p + 3 * rep < p1; p += 4 * rep) {
+      Half8 xv[4], dv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        xv[u] = ld_half8(xin + static_cast<size_t>(p + u * rep) * ld);
+        dv[u] = ld_half8(dyn + static_cast<size_t>(p + u * rep) * ld_dy);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float xf[8], d[8];
+        half8_to_float(xv[u], xf);
+        half8_to_float(dv[u], d);
+        accumulate(xf, d);
+      }
+    }
+  }
+  for (; p < p1; p += rep) {
+    float xf[8], d[8];
+    half8_to_float(ld_half8(xin + static_cast<size_t>(p) * ld), xf);
+    load_dy<kMode>(dy, ld_dy, n, h, w, p, cch * 8, d);
+    accumulate(xf, d);
   }
   const int cpg = c / kGroups;
   block_group_reduce(s_part, s_acc, s1, s2, c8, rep, cpg);
@@ -404,10 +433,7 @@ __global__ void gn_bwd_apply_kernel(const __half* __restrict__ x, int ld, const 
   const int hw = h * w;
   const __half* xin = x + static_cast<size_t>(n) * hw * ld + cch * 8;
   const int p0 = chunk * px_per_chunk, p1 = min(hw, p0 + px_per_chunk);
-  for (int p = p0 + pl; p < p1; p += rep) {
-    float xf[8], d[8], r[8];
-    half8_to_float(ld_half8(xin + static_cast<size_t>(p) * ld), xf);
-    load_dy<kMode>(dy, ld_dy, n, h, w, p, cch * 8, d);
+  auto grad_x = [&](const float (&xf)[8], const float (&d)[8], float (&r)[8]) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float xh = fmaf(xf[j], A.xa[j], A.xb[j]);
@@ -415,6 +441,42 @@ __global__ void gn_bwd_apply_kernel(const __half* __restrict__ x, int ld, const 
       const float dxh = d[j] * act_grad<kSilu>(z) * A.ga[j];
       r[j] = A.xa[j] * (dxh - m1[j] - xh * m2[j]);
     }
+  };
+  int p = p0 + pl;
+  if (kMode == GD_GN_SAME && (add == nullptr || add_mode == GD_GN_SAME)) {
+    // 4 pixels per iteration with every load (x, dy, add) issued up front
+    const __half* dyn = dy + static_cast<size_t>(n) * hw * ld_dy + cch * 8;
+    const __half* addn = add != nullptr ? add + static_cast<size_t>(n) * hw * ld_add + cch * 8 : nullptr;
+    __half* dxn = dx + static_cast<size_t>(n) * hw * ld_dx + cch * 8;
+    for (; p + 3 * rep < p1; p += 4 * rep) {
+      Half8 xv[4], dv[4], av[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        xv[u] = ld_half8(xin + static_cast<size_t>(p + u * rep) * ld);
+        dv[u] = ld_half8(dyn + static_cast<size_t>(p + u * rep) * ld_dy);
+        if (addn != nullptr) av[u] = ld_half8(addn + static_cast<size_t>(p + u * rep) * ld_add);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float xf[8], d[8], r[8];
+        half8_to_float(xv[u], xf);
+        half8_to_float(dv[u], d);
+        grad_x(xf, d, r);
+        if (addn != nullptr) {
+          float t[8];
+          half8_to_float(av[u], t);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r[j] += t[j];
+        }
+        st_half8(dxn + static_cast<size_t>(p + u * rep) * ld_dx, float_to_half8(r));
+      }
+    }
+  }
+  for (; p < p1; p += rep) {
+    float xf[8], d[8], r[8];
+    half8_to_float(ld_half8(xin + static_cast<size_t>(p) * ld), xf);
+    load_dy<kMode>(dy, ld_dy, n, h, w, p, cch * 8, d);
+    grad_x(xf, d, r);
     const size_t off = (static_cast<size_t>(n) * hw + p);
     if (add != nullptr) {
       float t[8];
@@ -517,7 +579,7 @@ extern "C" int gd_groupnorm_stats(const void* x, int32_t ld, int32_t n, int32_t 
                                   float* partial_ws, float* mean_rstd, void* stream) {
   if (int rc = check_gn_common("gd_groupnorm_stats", x, ld, n, hw, c)) return rc;
   GD_REQUIRE(partial_ws != nullptr && mean_rstd != nullptr, "gd_groupnorm_stats: null workspace/output");
-  const Geo g = make_geo(c, hw);
+  const Geo g = make_geo(c, hw, n, kMaxChunks);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   gn_stats_kernel<<<dim3(g.chunks, n), g.threads, g.threads * 16 * sizeof(float), st>>>(reinterpret_cast<const __half*>(x), ld, hw, c, g.c8, g.rep,
                                                           g.px_per_chunk, partial_ws);
@@ -556,7 +618,7 @@ extern "C" int gd_groupnorm_apply(const void* x, int32_t ld, const float* mean_r
     GD_REQUIRE(spatial_mode == GD_GN_AVGPOOL2 && ld_aux >= c && ld_aux % 8 == 0,
                "gd_groupnorm_apply: aux output only exists for the avg-pool mode (ld_aux %d)", ld_aux);
   const int hw_iter = spatial_mode == GD_GN_AVGPOOL2 ? (h / 2) * (w / 2) : h * w;
-  const Geo g = make_geo(c, hw_iter);
+  const Geo g = make_geo(c, hw_iter, n, 4096);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   GD_GN_DISPATCH(gn_apply_kernel, silu, spatial_mode,
                  <<<dim3(g.chunks, n), g.threads, 0, st>>>(reinterpret_cast<const __half*>(x), ld, mean_rstd, gamma,
@@ -578,7 +640,8 @@ extern "C" int gd_groupnorm_bwd(const void* x, int32_t ld, const float* mean_rst
   GD_REQUIRE(spatial_mode >= GD_GN_SAME && spatial_mode <= GD_GN_UPSAMPLE2, "gd_groupnorm_bwd: bad spatial mode");
   GD_REQUIRE(add_mode == GD_GN_SAME || add_mode == GD_GN_AVGPOOL2, "gd_groupnorm_bwd: bad add_mode");
   if (spatial_mode == GD_GN_AVGPOOL2) GD_REQUIRE(h % 2 == 0 && w % 2 == 0, "gd_groupnorm_bwd: avgpool needs even h,w");
-  const Geo g = make_geo(c, h * w);
+  const Geo g = make_geo(c, h * w, n, kMaxChunks);   // statistics pass (partials buffer bounds the CTA count)
+  const Geo ga = make_geo(c, h * w, n, 4096);        // apply pass
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // partial_ws layout: [n][kMaxChunks][32][2] partials, then [n][32][2] group means
   float* gsum = partial_ws + static_cast<size_t>(n) * kMaxChunks * kGroups * 2;
@@ -591,10 +654,10 @@ extern "C" int gd_groupnorm_bwd(const void* x, int32_t ld, const float* mean_rst
   gn_finalize_kernel<<<n, kGroups, 0, st>>>(partial_ws, g.chunks, inv_count, 0.f, 1, gsum);
   GD_CHECK_CUDA(cudaGetLastError());
   GD_GN_DISPATCH(gn_bwd_apply_kernel, silu, spatial_mode,
-                 <<<dim3(g.chunks, n), g.threads, 0, st>>>(
+                 <<<dim3(ga.chunks, n), ga.threads, 0, st>>>(
                      reinterpret_cast<const __half*>(x), ld, mean_rstd, gamma, beta, film, film_ld,
                      reinterpret_cast<const __half*>(dy), ld_dy, gsum, reinterpret_cast<const __half*>(add), ld_add,
-                     add_mode, reinterpret_cast<__half*>(dx), ld_dx, h, w, c, g.c8, g.rep, g.px_per_chunk));
+                     add_mode, reinterpret_cast<__half*>(dx), ld_dx, h, w, c, ga.c8, ga.rep, ga.px_per_chunk));
   GD_CHECK_CUDA(cudaGetLastError());
   count_launch(3);
   return 0;

@@ -1,0 +1,75 @@
+"""Microbenchmark of the fused GroupNorm kernels (bandwidth-bound) on BASELINE configs[1] shapes, batch 8.
+Algorithmic bytes: apply = read x + write y (2*N*2 B; pooled/upsampled variants scale the write), bwd = 2 passes over
+(x, dy) + write dx.  Reports achieved GB/s against MEASURED_PEAKS.json hbm_gbs."""
+import ctypes as C
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch as th  # noqa: E402
+
+from guided_diffusion_clip_b200 import _lib as L  # noqa: E402
+
+SHAPES = [(8, 256, 256), (8, 256, 512), (8, 128, 256), (8, 128, 512), (8, 64, 512), (8, 64, 1024), (8, 32, 512),
+          (8, 32, 1024), (8, 16, 1024), (8, 16, 2048), (8, 8, 1024), (8, 8, 2048), (8, 256, 128)]
+
+
+def timeit(fn, reps=10):
+    evs = []
+    for _ in range(reps + 2):
+        e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        evs.append((e0, e1))
+    th.cuda.synchronize()
+    ms = sorted(a.elapsed_time(b) for a, b in evs[2:])
+    return ms[len(ms) // 2]
+
+
+def main():
+    lib = L.load()
+    peak = 6447.0
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        peak = json.load(open(p)).get("hbm_gbs", peak)
+    st = C.c_void_p(th.cuda.current_stream().cuda_stream)
+    for n, s, c in SHAPES:
+        xs = [th.randn((n, s, s, c), device="cuda", dtype=th.float16) for _ in range(2)]
+        dy = th.randn((n, s, s, c), device="cuda", dtype=th.float16)
+        y = th.empty_like(xs[0])
+        gamma, beta = th.ones(c, device="cuda"), th.zeros(c, device="cuda")
+        film = th.zeros((n, 2 * c), device="cuda")
+        ws = th.empty(int(lib.gd_groupnorm_ws_floats(n, s * s, c)), device="cuda")
+        stats = th.empty((n, 32, 2), device="cuda")
+        vp = lambda t: C.c_void_p(t.data_ptr())
+        k = [0]
+
+        def f_stats():
+            k[0] ^= 1
+            L.check(lib.gd_groupnorm_stats(vp(xs[k[0]]), c, n, s * s, c, C.c_float(1e-5), vp(ws), vp(stats), st))
+
+        def f_apply():
+            k[0] ^= 1
+            L.check(lib.gd_groupnorm_apply(vp(xs[k[0]]), c, vp(stats), vp(gamma), vp(beta), vp(film), 2 * c, vp(y), c, n,
+                                           s, s, c, 1, L.GN_SAME, None, 0, st))
+
+        def f_bwd():
+            k[0] ^= 1
+            L.check(lib.gd_groupnorm_bwd(vp(xs[k[0]]), c, vp(stats), vp(gamma), vp(beta), vp(film), 2 * c, vp(dy), c, None,
+                                         0, 0, vp(y), c, vp(ws), n, s, s, c, 1, L.GN_SAME, st))
+
+        f_stats()
+        nbytes = n * s * s * c * 2
+        row = {"shape": f"{n}x{s}x{s}x{c}", "MB": round(nbytes / 1e6, 1)}
+        for name, fn, mult in (("stats", f_stats, 1), ("apply", f_apply, 2), ("bwd", f_bwd, 5)):
+            ms = timeit(fn)
+            gbs = mult * nbytes / (ms * 1e-3) / 1e9
+            row[name] = {"us": round(ms * 1e3, 1), "GBs": round(gbs), "frac": round(gbs / peak, 3)}
+        print(json.dumps(row), flush=True)
+
+
+if __name__ == "__main__":
+    main()
