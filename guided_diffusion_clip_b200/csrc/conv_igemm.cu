@@ -547,14 +547,14 @@ void conv_debug_set(int key, int value) {
 // small-spatial layers (8x8 / 16x16 with C = 1024) otherwise run on 4-16 CTAs.  Below 32 columns the MMA is
 // shared-memory bound, so 32 is the floor unless n_pad itself is smaller.
 int conv_pick_bn(int n_pad, int m_tiles, int num_sms, int step) {
-  int best = 0;
-  for (int bn = 256; bn >= step; bn -= step) {
-    if (n_pad % bn != 0) continue;
-    if (best == 0) best = bn;  // largest divisor
-    if (static_cast<long long>(m_tiles) * (n_pad / bn) * 100 >= 85LL * num_sms) return bn;
-    if (bn >= 32) best = bn;
-  }
-  return best ? best : 16;
+  // Measured (profiles/conv_sweep.py, r01): narrower N tiles never pay off, even when they would fill more SMs —
+  // every extra N tile re-streams the whole A operand from L2 and drops the MMA below its shared-memory-bound rate
+  // (32x32x512ch: 37 us at BN=256 vs 99 us at BN=64).  So: the widest tile that divides n_pad.
+  (void)m_tiles;
+  (void)num_sms;
+  for (int bn = 256; bn >= step; bn -= step)
+    if (n_pad % bn == 0) return bn;
+  return 16;
 }
 
 // Output patch of one 128-row tile: BW x BH pixels of BI images, BW*BH*BI == 128 (powers of two).

@@ -71,7 +71,10 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--modes", default="0,1,2")
     ap.add_argument("--bn", default="0")
+    ap.add_argument("--only", default="", help="substring filter on the shape name")
     args = ap.parse_args()
+    if args.only:
+        SHAPES[:] = [s for s in SHAPES if args.only in s[0]]
     lib = L.load()
     results = []
     for bn in [int(v) for v in args.bn.split(",")]:
