@@ -7,9 +7,9 @@
 A "step" is one guided sampling step on one per-GPU batch: UNet-256 forward + classifier-256 forward + classifier
 data-gradient backward + fused posterior/noise update (gaussian_diffusion.py:395-439 of the reference).  A sample
 needs 250 such steps (timestep_respacing="250"), so  value [samples/s] = n_gpus * batch / (250 * s_per_step).
-Weak scaling: the per-GPU batch is fixed (8 -> global batch 64 on 8 GPUs, the BASELINE configuration); ranks are
-independent (no data-path collective); the one collective of the path, the all_gather of finished uint8 samples,
-is exercised after the timed region and reported as gather_ms.
+Weak scaling: the per-GPU batch is fixed at 64 (N=1 is exactly the BASELINE configs[1] batch; --batch 8 gives the
+"global 64 on 8 GPUs" split); ranks are independent (no data-path collective); the one collective of the path, the
+all_gather of finished uint8 samples, is exercised after the timed region and reported as gather_ms.
 Synthetic data: N(0,1) noise of the named shape, random-init weights (zero_module tensors re-drawn N(0,0.02)).
 """
 from __future__ import annotations
@@ -360,7 +360,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=8, help="per-GPU batch")
+    ap.add_argument("--batch", type=int, default=64,
+                    help="per-GPU batch (64 = the BASELINE configs[1] batch on one GPU; weak scaling keeps it per GPU)")
     ap.add_argument("--image-size", type=int, default=256)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-steps", type=int, default=2)
