@@ -48,6 +48,15 @@ def clf_kwargs(image_size=256):
     return d
 
 
+def workload_config(image_size, batch, world):
+    """The `config` object shared by both arms (the reference arm times a bounded sample of the same workload)."""
+    return {"workload": f"{image_size}x{image_size} class-cond ADM (256ch, 2 res blocks, attn 32/16/8) + EncoderUNet "
+                        f"classifier guidance (scale 1.0), 250 respaced steps, batch {batch}/GPU (global {batch * world}), "
+                        "fp16 storage fp32 accumulate",
+            "per_gpu_batch": batch, "global_batch": batch * world, "steps_per_sample": STEPS_PER_SAMPLE,
+            "l2_policy": "activations per step (>1 GB at batch 8) exceed the 126 MB L2; no flush needed"}
+
+
 def randomize_(model, seed):
     """Random init; every all-zero (zero_module) tensor re-drawn N(0, 0.02) so no branch is vacuous."""
     g = th.Generator(device="cpu").manual_seed(seed)
@@ -161,12 +170,12 @@ def run_reference_arm(args):
     cores = os.cpu_count() or 1
     sample = (f"{len(timed)} guided steps at batch 1, {args.image_size}x{args.image_size}, fp32 oneDNN, "
               f"{cores} threads; samples/s extrapolated x{STEPS_PER_SAMPLE} steps")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     line = {
         "impl": "reference", "metric": "guided_samples_per_sec_256", "value": value, "unit": "samples/s",
-        "n_gpus": 0, "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.image_size}x{args.image_size} class-cond ADM + EncoderUNet classifier guidance "
-                               "(scale 1.0), 250 respaced steps; CPU sample at batch 1"},
+        "config": workload_config(args.image_size, args.batch, world),
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -332,12 +341,7 @@ def run_gpu_arm(args):
         "metric": "guided_samples_per_sec_256", "value": value, "unit": "samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-        "config": {"workload": f"{S}x{S} class-cond ADM (256ch, 2 res blocks, attn 32/16/8) + EncoderUNet classifier "
-                               f"guidance (scale 1.0), 250 respaced steps, batch {B}/GPU (global {B * world}), fp16 storage "
-                               "fp32 accumulate",
-                   "per_gpu_batch": B, "global_batch": B * world, "steps_per_sample": STEPS_PER_SAMPLE,
-                   "l2_policy": "activations per step (>1 GB at batch 8) exceed the 126 MB L2; no flush needed",
-                   "finite": finite},
+        "config": workload_config(S, B, world), "finite": finite,
         "roofline": roof, "clocks": clocks.summary(), "gpu_launches": launches_per_step * args.steps,
         "launches_per_step": launches_per_step, "gather_ms": gather_ms,
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": bytes_io + B * 8,
