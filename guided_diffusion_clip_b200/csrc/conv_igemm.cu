@@ -167,6 +167,11 @@ __device__ __forceinline__ void epi_chunk_direct(const ConvArgs& p, uint32_t tad
   }
 }
 
+// kTwo = CTA-pair mode (cluster of 2, tcgen05 cta_group::2): the pair computes a 256-pixel x BN tile — rank r owns
+// pixel tile 2*pair + r and loads its own A tile plus HALF of the weight tile; the leader's single thread issues
+// M=256 MMAs that read both CTAs' shared memory and write both CTAs' TMEM.  Halving the B traffic per SM is what
+// lifts the mainloop off the shared-memory / L2->SM bandwidth limit.
+template <bool kTwo>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                   const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out,
@@ -182,14 +187,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
   float* s_bias = reinterpret_cast<float*>(smem + kBarrierBytes);
   uint8_t* stage_base = smem + kBarrierBytes + kBiasBytes;
-  const int b_tile_bytes = p.bn * kBK * 2;
-  const int stage_bytes = kATileBytes + b_tile_bytes;  // multiple of 1024 since bn % 16 == 0 -> bn*128 % 2048 == 0
+  const int b_rows = kTwo ? (p.bn >> 1) : p.bn;  // weight rows this CTA stages per K block
+  const int b_tile_bytes = b_rows * kBK * 2;
+  const int stage_bytes = kATileBytes + b_tile_bytes;  // multiple of 1024 (host checks b_rows % 8 == 0)
   uint8_t* s_out = stage_base + p.stages * stage_bytes;
   uint8_t* s_res = s_out + kEpiTileBytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const uint32_t rank = kTwo ? cluster_ctarank() : 0u;
+  const bool lead_cta = rank == 0;
+  // work items: (pixel tile | pixel-tile pair, n tile); both CTAs of a pair walk the same list
+  const int m_units = kTwo ? (p.m_tiles + 1) / 2 : p.m_tiles;
+  const int total_tiles = m_units * p.n_tiles;
+  const int work0 = kTwo ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int work_step = kTwo ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a0);
@@ -205,16 +217,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 128);
+      mbar_init(&tmem_empty[a], kTwo ? 256 : 128);  // pair mode: both CTAs' epilogue threads release the leader
     }
     mbar_init(res_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_base_slot, 512);
+    if (kTwo) tmem_alloc_2sm(tmem_base_slot, 512);
+    else tmem_alloc(tmem_base_slot, 512);
   }
   tc_fence_before();
   __syncthreads();
+  if (kTwo) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
@@ -223,9 +237,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = work0; tile < total_tiles; tile += work_step) {
         const int n_tile = tile % p.n_tiles;
-        const int m_tile = tile / p.n_tiles;
+        const int m_tile = kTwo ? 2 * (tile / p.n_tiles) + static_cast<int>(rank) : tile / p.n_tiles;
         int n0, y0, x0;
         tile_coords(p, m_tile, n0, y0, x0);
         int tap = 0, cc = 0;
@@ -233,22 +247,29 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = stage_base + stage * stage_bytes;
           uint8_t* sb = sa + kATileBytes;
-          mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
-          if (kb < p.kb0) {
-            int dy = 0, dx = 0;
-            if (p.taps == 9) {
-              dy = tap / 3 - 1;
-              dx = tap % 3 - 1;
-            }
-            tma_load_4d(sa, &map_a0, &full_bar[stage], cc * kBK, x0 + dx, y0 + dy, n0);
-            if (++cc == p.kb0_per_tap) {
-              cc = 0;
-              ++tap;
-            }
-          } else {
-            tma_load_4d(sa, &map_a1, &full_bar[stage], (kb - p.kb0) * kBK, x0, y0, n0);
+          int dy = 0, dx = 0;
+          const bool main_src = kb < p.kb0;
+          if (main_src && p.taps == 9) {
+            dy = tap / 3 - 1;
+            dx = tap % 3 - 1;
           }
-          tma_load_2d(sb, &map_b, &full_bar[stage], kb * kBK, n_tile * p.bn);
+          const int ck = main_src ? cc * kBK : (kb - p.kb0) * kBK;
+          const CUtensorMap* ma = main_src ? &map_a0 : &map_a1;
+          if (kTwo) {
+            // both CTAs' loads complete on the LEADER's barrier, which expects the bytes of the whole pair
+            if (lead_cta) mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(2 * stage_bytes));
+            const uint32_t fb = mapa_u32(&full_bar[stage], 0);
+            tma_load_4d_2sm(sa, ma, fb, ck, x0 + dx, y0 + dy, n0);
+            tma_load_2d_2sm(sb, &map_b, fb, kb * kBK, n_tile * p.bn + static_cast<int>(rank) * b_rows);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
+            tma_load_4d(sa, ma, &full_bar[stage], ck, x0 + dx, y0 + dy, n0);
+            tma_load_2d(sb, &map_b, &full_bar[stage], kb * kBK, n_tile * p.bn);
+          }
+          if (main_src && ++cc == p.kb0_per_tap) {
+            cc = 0;
+            ++tap;
+          }
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
@@ -258,13 +279,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_f16(kBM, static_cast<uint32_t>(p.bn));
+    if (lane == 0 && lead_cta) {
+      const uint32_t idesc = umma_idesc_f16(kTwo ? 2 * kBM : kBM, static_cast<uint32_t>(p.bn));
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = work0; tile < total_tiles; tile += work_step) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
@@ -277,16 +298,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             // advance 16 fp16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in (addr >> 4) units
-            umma_f16(d_tmem, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
-                     static_cast<uint32_t>((kb | k) != 0));
+            if (kTwo)
+              umma_f16_2sm(d_tmem, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
+                           static_cast<uint32_t>((kb | k) != 0));
+            else
+              umma_f16(d_tmem, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
+                       static_cast<uint32_t>((kb | k) != 0));
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
+          if (kTwo) umma_commit_2sm(&empty_bar[stage], 0x3);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete
+        // accumulator complete (signalled to both CTAs' epilogues in pair mode)
+        if (kTwo) umma_commit_2sm(&tmem_full[acc], 0x3);
+        else umma_commit(&tmem_full[acc]);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -299,6 +328,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     const int row = quarter * 32 + lane;   // row of the 128-row tile == pixel within the patch
     const int epi_tid = threadIdx.x - 64;  // 0..127
     const bool leader = epi_tid == 0;
+    // hand a drained accumulator back to the MMA issuer (pair mode: the issuer lives in the leader CTA)
+    auto release_accumulator = [&](uint64_t* bar) {
+      if (kTwo) mbar_arrive_cluster(mapa_u32(bar, 0));
+      else mbar_arrive(bar);
+    };
     const int patch_px = p.bh * p.bw;
     const int i_local = row / patch_px;
     const int rem = row - i_local * patch_px;
@@ -313,9 +347,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     uint32_t res_phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = work0; tile < total_tiles; tile += work_step) {
       const int n_tile = tile % p.n_tiles;
-      const int m_tile = tile / p.n_tiles;
+      const int m_tile = kTwo ? 2 * (tile / p.n_tiles) + static_cast<int>(rank) : tile / p.n_tiles;
       int n0, y0, x0;
       tile_coords(p, m_tile, n0, y0, x0);
       EpiCtx e;
@@ -389,7 +423,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           if (sub == nsub - 1) {
             // accumulator fully read: hand the TMEM buffer back to the MMA warp before the store phase
             tc_fence_before();
-            mbar_arrive(&tmem_empty[acc]);
+            release_accumulator(&tmem_empty[acc]);
           }
           // s_out is free once the previous TMA store has finished READING it
           if (leader) bulk_wait_read0();
@@ -450,13 +484,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                   cs[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
                 }
               }
+              if (m_tile < p.m_tiles) {
               float* sp = p.stats + (static_cast<size_t>(m_tile) * 4 + quarter) * p.stats_ld * 2;
               sp[(((col_base + c0) >> 2) + (lane & 15)) * 2 + (lane >> 4)] = cs[0];
+              }
             }
             fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
           }
           epi_barrier();  // (B) staging tile complete
-          if (leader && p.debug == 0) {
+          if (leader && p.debug == 0 && m_tile < p.m_tiles) {  // (an odd tile count leaves the last pair half empty)
             tma_store_4d(&map_out, s_out, col_base + c0, x0, y0, n0);
             bulk_commit();
           }
@@ -464,7 +500,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       }
       if (!p.tma_epi || p.debug == 1) {
         tc_fence_before();
-        mbar_arrive(&tmem_empty[acc]);
+        release_accumulator(&tmem_empty[acc]);
       }
       if (++acc == 2) {
         acc = 0;
@@ -476,9 +512,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
 
   tc_fence_before();
   __syncthreads();
+  if (kTwo) cluster_sync_all();  // the peer may still be arriving on this CTA's barriers / reading its TMEM half
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (kTwo) tmem_dealloc_2sm(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -534,6 +572,7 @@ int g_num_sms = 0;
 int g_debug_epilogue = 0;
 int g_force_bn = 0;
 int g_disable_tma_epi = 0;
+int g_two_cta_mode = 1;
 
 }  // namespace
 
@@ -541,6 +580,7 @@ void conv_debug_set(int key, int value) {
   if (key == 0) g_debug_epilogue = value;
   if (key == 1) g_force_bn = value;
   if (key == 2) g_disable_tma_epi = value;
+  if (key == 3) g_two_cta_mode = value;
 }
 
 // N tile: the largest divisor of n_pad (multiple of 16, <= 256) that still yields enough tiles to fill the SMs;
@@ -637,7 +677,10 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
   p.m_tiles = m_tiles;
   p.n_tiles = d->n_pad / bn;
   p.bn = bn;
-  const int stage_bytes = kATileBytes + bn * kBK * 2;
+  // CTA-pair mode whenever there are at least two pixel tiles and half a weight tile is a whole number of 8-row
+  // swizzle groups (bn % 16 == 0 always holds)
+  const bool two_cta = g_two_cta_mode != 0 && m_tiles >= 2 && (bn / 2) % 8 == 0 && g_num_sms >= 2;
+  const int stage_bytes = kATileBytes + (two_cta ? bn / 2 : bn) * kBK * 2;
   int stages = (kSmemBudget - kBarrierBytes - kBiasBytes - kEpiBytes - 1024) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   GD_REQUIRE(stages >= 2, "gd_conv_igemm: not enough shared memory for 2 stages");
@@ -675,7 +718,7 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
   } else {
     ma1 = ma0;
   }
-  rc = encode_weight_map(&mb, d->wpack, k_total, d->n_pad, bn);
+  rc = encode_weight_map(&mb, d->wpack, k_total, d->n_pad, two_cta ? bn / 2 : bn);
   if (rc) return rc;
   mout = ma0;
   mres = ma0;
@@ -695,12 +738,34 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
   const int smem_bytes = kSmemBudget;
   static bool attr_set = false;
   if (!attr_set) {
-    GD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    GD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    GD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_set = true;
   }
-  const int total_tiles = p.m_tiles * p.n_tiles;
-  const int grid = total_tiles < g_num_sms ? total_tiles : g_num_sms;
-  conv_igemm_kernel<<<grid, kThreads, smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(ma0, ma1, mb, mout, mres, p);
+  if (two_cta) {
+    // one cluster of 2 CTAs per pixel-tile pair; persistent over (pair, n tile) work items
+    const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
+    const int max_clusters = g_num_sms / 2;
+    const int clusters = pairs < max_clusters ? pairs : max_clusters;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    GD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true>, ma0, ma1, mb, mout, mres, p));
+  } else {
+    const int total_tiles = p.m_tiles * p.n_tiles;
+    const int grid = total_tiles < g_num_sms ? total_tiles : g_num_sms;
+    conv_igemm_kernel<false><<<grid, kThreads, smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(ma0, ma1, mb, mout,
+                                                                                                    mres, p);
+  }
   GD_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
   return 0;

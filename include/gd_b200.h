@@ -37,7 +37,8 @@ int gd_version(void);
 int64_t gd_launch_count(void);
 void gd_launch_count_reset(void);
 /* Measurement hooks (profiles/ only): key 0 = conv epilogue mode (0 normal, 1 barriers only, 2 TMEM loads only),
- * key 1 = force the conv N tile (0 = heuristic). */
+ * key 1 = force the conv N tile (0 = heuristic), key 2 = 1 disables the staged TMA-store epilogue, key 3 = 0 disables
+ * CTA-pair (cta_group::2) mode. */
 void gd_debug_set(int key, int value);
 
 /* ------------------------------------------------------------------------------------------------

@@ -139,3 +139,40 @@ def traj10_noise():
     th.manual_seed(TRAJ_SEED)
     init = th.randn(TRAJ_BATCH, 3, IMAGE, IMAGE)
     return init, [th.randn(TRAJ_BATCH, 3, IMAGE, IMAGE) for _ in range(TRAJ10_STEPS)]
+
+
+# ---- §8f rows already built: super-resolution input path and the fork's clip_feat conditioning ------------
+SR_SEED, FEAT_SEED = 21, 22
+SR_KW = dict(large_size=64, small_size=16, num_channels=64, num_res_blocks=1, learn_sigma=True, class_cond=True,
+             use_checkpoint=False, attention_resolutions="16,8", num_heads=4, num_head_channels=64,
+             num_heads_upsample=-1, use_scale_shift_norm=True, dropout=0.0, resblock_updown=True, use_fp16=False)
+SR_STRUCT = dict(num_res_blocks=1, channel_mult_len=4, head_dim=64, new_order=False)
+FEAT_KW = dict(UNET_KW, use_new_attention_order=False)  # create_model(..., conditioning="clip_feat")
+FEAT_STRUCT = dict(num_res_blocks=1, channel_mult_len=4, head_dim=64, new_order=False)
+
+
+def ref_sr_kwargs():
+    return dict(image_size=64, in_channels=3, model_channels=64, out_channels=6, num_res_blocks=1,
+                attention_resolutions=(4, 8), dropout=0.0, channel_mult=(1, 2, 3, 4), num_classes=1000,
+                use_checkpoint=False, use_fp16=False, num_heads=4, num_head_channels=64, num_heads_upsample=-1,
+                use_scale_shift_norm=True, resblock_updown=True)
+
+
+def ref_feat_kwargs():
+    kw = ref_unet_kwargs()
+    kw.update(num_classes=512, use_new_attention_order=False)
+    return kw
+
+
+def sr_inputs():
+    g = th.Generator().manual_seed(INPUT_SEED + 1)
+    x = th.randn(2, 3, IMAGE, IMAGE, generator=g)
+    low = th.rand(2, 3, 16, 16, generator=g) * 2 - 1
+    return x, th.tensor([500, 3]), th.tensor([1, 999]), low
+
+
+def feat_inputs():
+    g = th.Generator().manual_seed(INPUT_SEED + 2)
+    x = th.randn(2, 3, IMAGE, IMAGE, generator=g)
+    feat = th.randn(2, 1, 512, generator=g)
+    return x, th.tensor([10, 720]), feat / feat.norm(dim=-1, keepdim=True)

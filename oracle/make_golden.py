@@ -123,6 +123,17 @@ def models_golden():
 
     out["clf_grad"] = cond_fn(x, t, y=y).numpy()
 
+    # §8f rows: SuperResModel (bilinear low_res conditioning) and the fork's UNetModel_clip_feat
+    from guided_diffusion import unet_other as rother
+    sr = runet.SuperResModel(**cfg.ref_sr_kwargs())
+    sr.load_state_dict(make_state_dict({k: tuple(v.shape) for k, v in sr.state_dict().items()}, cfg.SR_SEED), strict=True)
+    xs_, ts_, ys_, low_ = cfg.sr_inputs()
+    out["sr_out"] = sr.eval()(xs_, ts_, low_res=low_, y=ys_).numpy()
+    fm = rother.UNetModel_clip_feat(**cfg.ref_feat_kwargs())
+    fm.load_state_dict(make_state_dict({k: tuple(v.shape) for k, v in fm.state_dict().items()}, cfg.FEAT_SEED), strict=True)
+    xf_, tf_, feat_ = cfg.feat_inputs()
+    out["feat_out"] = fm.eval()(xf_, tf_, clip_feat=feat_).numpy()
+
     # per-step update with a fixed fake model output (pure diffusion arithmetic)
     for name, kw in cfg.STEP_CASES.items():
         d = rsu.create_gaussian_diffusion(**kw["diffusion"])

@@ -207,3 +207,29 @@ def test_cpu_tensors_fail_loudly(lib, unet):
     cpu_model = su.create_model(**cfg.UNET_KW)
     with pytest.raises(GdError):
         cpu_model(x, t, y)
+
+
+def test_superres_model_matches_reference(lib, G):
+    """SuperResModel: bilinear (align_corners=False) low_res upsample + concat + 6-channel first conv (unet.py:667-681)."""
+    m = su.sr_create_model(**cfg.SR_KW)
+    _load(m, cfg.SR_SEED)
+    m.cuda().eval()
+    x, t, y, low = (v.cuda() for v in cfg.sr_inputs())
+    with th.no_grad():
+        out = m(x, t, low_res=low, y=y)
+    err = H.rel_err(out, th.from_numpy(G["sr_out"]).cuda())
+    print(f"SuperResModel vs reference golden: rel err {err:.3e}")
+    assert err < TOL
+
+
+def test_clip_feat_model_matches_reference(lib, G):
+    """The fork's UNetModel_clip_feat: label_emb = Linear-SiLU-Linear over a 512-d CLIP feature (unet_other.py:25-41)."""
+    m = su.create_model(**cfg.FEAT_KW, conditioning="clip_feat")
+    _load(m, cfg.FEAT_SEED)
+    m.cuda().eval()
+    x, t, feat = (v.cuda() for v in cfg.feat_inputs())
+    with th.no_grad():
+        out = m(x, t, clip_feat=feat)
+    err = H.rel_err(out, th.from_numpy(G["feat_out"]).cuda())
+    print(f"UNetModel_clip_feat vs reference golden: rel err {err:.3e}")
+    assert err < TOL
