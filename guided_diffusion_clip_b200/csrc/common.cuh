@@ -244,6 +244,17 @@ __device__ __forceinline__ Half8 float_to_half8(const float (&f)[8]) {
   return v;
 }
 __device__ __forceinline__ Half8 ld_half8(const __half* p) { return *reinterpret_cast<const Half8*>(p); }
+// streaming 16-byte load: read-only path, do not allocate in L1 (the GroupNorm kernels touch every byte exactly once)
+__device__ __forceinline__ Half8 ld_half8_stream(const __half* p) {
+  uint32_t a, b, c, d;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(a), "=r"(b), "=r"(c), "=r"(d)
+               : "l"(p));
+  Half8 v;
+  uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+  w[0] = a; w[1] = b; w[2] = c; w[3] = d;
+  return v;
+}
 __device__ __forceinline__ void st_half8(__half* p, const Half8& v) { *reinterpret_cast<Half8*>(p) = v; }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -204,6 +204,17 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, int ld, const floa
     __half* o = out + static_cast<size_t>(n) * hw_in * ld_out + cch * 8;
     const int p0 = chunk * px_per_chunk, p1 = min(hw_in, p0 + px_per_chunk);
     int p = p0 + pl;
+    for (; p + 7 * rep < p1; p += 8 * rep) {  // 8 independent 16-byte streaming loads in flight per thread
+      Half8 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = ld_half8_stream(xin + static_cast<size_t>(p + u * rep) * ld);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        float r[8];
+        norm_act<kSilu>(v[u], a, b, r);
+        st_half8(o + static_cast<size_t>(p + u * rep) * ld_out, float_to_half8(r));
+      }
+    }
     for (; p + 3 * rep < p1; p += 4 * rep) {
       Half8 v0 = ld_half8(xin + static_cast<size_t>(p) * ld);
       Half8 v1 = ld_half8(xin + static_cast<size_t>(p + rep) * ld);
@@ -347,7 +358,7 @@ __device__ __forceinline__ void load_bwd_affine(const float* mean_rstd, const fl
 }
 
 template <bool kSilu, int kMode>
-__global__ void gn_bwd_stats_kernel(const __half* __restrict__ x, int ld, const float* __restrict__ mean_rstd,
+__global__ void __launch_bounds__(256, 2) gn_bwd_stats_kernel(const __half* __restrict__ x, int ld, const float* __restrict__ mean_rstd,
                                     const float* __restrict__ gamma, const float* __restrict__ beta,
                                     const float* __restrict__ film, int film_ld, const __half* __restrict__ dy, int ld_dy,
                                     int h, int w, int c, int c8, int rep, int px_per_chunk,
@@ -383,8 +394,8 @@ __global__ void gn_bwd_stats_kernel(const __half* __restrict__ x, int ld, const 
       Half8 xv[4], dv[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        xv[u] = ld_half8(xin + static_cast<size_t>(p + u * rep) * ld);
-        dv[u] = ld_half8(dyn + static_cast<size_t>(p + u * rep) * ld_dy);
+        xv[u] = ld_half8_stream(xin + static_cast<size_t>(p + u * rep) * ld);
+        dv[u] = ld_half8_stream(dyn + static_cast<size_t>(p + u * rep) * ld_dy);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -412,7 +423,7 @@ __global__ void gn_bwd_stats_kernel(const __half* __restrict__ x, int ld, const 
 }
 
 template <bool kSilu, int kMode>
-__global__ void gn_bwd_apply_kernel(const __half* __restrict__ x, int ld, const float* __restrict__ mean_rstd,
+__global__ void __launch_bounds__(256, 2) gn_bwd_apply_kernel(const __half* __restrict__ x, int ld, const float* __restrict__ mean_rstd,
                                     const float* __restrict__ gamma, const float* __restrict__ beta,
                                     const float* __restrict__ film, int film_ld, const __half* __restrict__ dy, int ld_dy,
                                     const float* __restrict__ gsum, const __half* __restrict__ add, int ld_add,
@@ -452,9 +463,9 @@ __global__ void gn_bwd_apply_kernel(const __half* __restrict__ x, int ld, const 
       Half8 xv[4], dv[4], av[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        xv[u] = ld_half8(xin + static_cast<size_t>(p + u * rep) * ld);
-        dv[u] = ld_half8(dyn + static_cast<size_t>(p + u * rep) * ld_dy);
-        if (addn != nullptr) av[u] = ld_half8(addn + static_cast<size_t>(p + u * rep) * ld_add);
+        xv[u] = ld_half8_stream(xin + static_cast<size_t>(p + u * rep) * ld);
+        dv[u] = ld_half8_stream(dyn + static_cast<size_t>(p + u * rep) * ld_dy);
+        if (addn != nullptr) av[u] = ld_half8_stream(addn + static_cast<size_t>(p + u * rep) * ld_add);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -570,7 +581,7 @@ extern "C" int64_t gd_groupnorm_ws_floats(int32_t n, int32_t hw, int32_t c) {
 static int check_gn_common(const char* who, const void* x, int ld, int n, int hw, int c) {
   GD_REQUIRE(x != nullptr, "%s: null input", who);
   GD_REQUIRE(n > 0 && hw > 0, "%s: bad n/hw", who);
-  GD_REQUIRE(c > 0 && c % 32 == 0 && c <= 4096, "%s: channels must be a multiple of 32 (GroupNorm32), got %d", who, c);
+  GD_REQUIRE(c > 0 && c % 32 == 0 && c <= 2048, "%s: channels must be a multiple of 32 (GroupNorm32), got %d", who, c);
   GD_REQUIRE(ld >= c && ld % 8 == 0, "%s: bad ld %d for c %d", who, ld, c);
   return 0;
 }
