@@ -120,6 +120,8 @@ class GraphedStepper:
                         else (1000.0 / diffusion.num_timesteps if diffusion.rescale_timesteps else None))
         self.clip, self.ddim, self.eta = clip_denoised, ddim, eta
         self.graph: Optional[th.cuda.CUDAGraph] = None
+        self.overlap = os.environ.get("GD_B200_NO_OVERLAP", "0") != "1"
+        self._fork = th.cuda.Stream(device=dev)
         self._capture()
 
     def _body(self) -> None:
@@ -127,12 +129,25 @@ class GraphedStepper:
         ts = self.map[self.t_idx] if self.map is not None else self.t_idx
         ts = ts.float() * self.rescale if self.rescale is not None else ts
         self.unet.t_in.copy_(ts)
-        self.unet.prog.run()
         grad = None
-        if self.clf is not None:
-            self.clf.x_in.copy_(self.unet.x_in)
-            self.clf.t_in.copy_(ts)
-            grad = self.clf.guidance(self.clf.x_in, self.clf.t_in, self.y, self.scale)
+        if self.clf is not None and self.overlap:
+            # The classifier (fwd + bwd) and the UNet both depend only on (x_t, t): fork the classifier onto a
+            # second stream so its bandwidth-bound GroupNorm passes fill in beside the UNet's tensor-bound convs
+            # (and vice versa); join before the posterior kernel.  Captured as two branches of the step graph.
+            main = th.cuda.current_stream()
+            self._fork.wait_stream(main)
+            with th.cuda.stream(self._fork):
+                self.clf.x_in.copy_(self.unet.x_in)
+                self.clf.t_in.copy_(self.unet.t_in)
+                grad = self.clf.guidance(self.clf.x_in, self.clf.t_in, self.y, self.scale)
+            self.unet.prog.run()
+            main.wait_stream(self._fork)
+        else:
+            self.unet.prog.run()
+            if self.clf is not None:
+                self.clf.x_in.copy_(self.unet.x_in)
+                self.clf.t_in.copy_(ts)
+                grad = self.clf.guidance(self.clf.x_in, self.clf.t_in, self.y, self.scale)
         d._launch_posterior(x=self.unet.x_in, t=self.t_idx, model_out=self.unet.out, grad=grad, noise=self.noise,
                             sample=self.sample, pred_xstart=self.x0, clip_denoised=self.clip, ddim=self.ddim,
                             eta=self.eta)
