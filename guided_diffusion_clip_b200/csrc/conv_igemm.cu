@@ -68,6 +68,7 @@ struct ConvArgs {
   float* stats;  // optional GroupNorm partials [m_tiles*4][stats_ld][2] (sum, sum of squares per 4-channel chunk)
   int stats_ld;  // n_pad / 4
   int debug;    // 0 = normal; 1 = epilogue skipped (barriers only); 2 = TMEM loads only (timing experiments)
+  int dbg_a_div, dbg_b_div;  // timing experiments: load the A / B tile only every n-th K block (results are garbage)
 };
 
 __device__ __forceinline__ void tile_coords(const ConvArgs& p, int m_tile, int& n0, int& y0, int& x0) {
@@ -193,8 +194,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   uint8_t* s_out = stage_base + p.stages * stage_bytes;
   uint8_t* s_res = s_out + kEpiTileBytes;
 
-  const int warp = threadIdx.x >> 5;
+  // warp index via shuffle: the compiler then knows it is warp-uniform and keeps the role loops on the uniform path
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
+  const uint32_t smem_base_u32 = smem_u32(smem);
   const uint32_t rank = kTwo ? cluster_ctarank() : 0u;
   const bool lead_cta = rank == 0;
   // work items: (pixel tile | pixel-tile pair, n tile); both CTAs of a pair walk the same list
@@ -234,52 +237,66 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = work0; tile < total_tiles; tile += work_step) {
-        const int n_tile = tile % p.n_tiles;
-        const int m_tile = kTwo ? 2 * (tile / p.n_tiles) + static_cast<int>(rank) : tile / p.n_tiles;
-        int n0, y0, x0;
-        tile_coords(p, m_tile, n0, y0, x0);
-        int tap = 0, cc = 0;
-        for (int kb = 0; kb < p.kb_total; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = stage_base + stage * stage_bytes;
-          uint8_t* sb = sa + kATileBytes;
-          int dy = 0, dx = 0;
-          const bool main_src = kb < p.kb0;
-          if (main_src && p.taps == 9) {
-            dy = tap / 3 - 1;
-            dx = tap % 3 - 1;
-          }
-          const int ck = main_src ? cc * kBK : (kb - p.kb0) * kBK;
-          const CUtensorMap* ma = main_src ? &map_a0 : &map_a1;
+    // The whole warp walks the loop (warp-uniform control flow keeps addresses and coordinates in uniform
+    // registers); one elected lane issues the copies.
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = work0; tile < total_tiles; tile += work_step) {
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = kTwo ? 2 * (tile / p.n_tiles) + static_cast<int>(rank) : tile / p.n_tiles;
+      int n0, y0, x0;
+      tile_coords(p, m_tile, n0, y0, x0);
+      int tap = 0, cc = 0;
+      for (int kb = 0; kb < p.kb_total; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        __syncwarp();
+        uint8_t* sa = stage_base + stage * stage_bytes;
+        uint8_t* sb = sa + kATileBytes;
+        int dy = 0, dx = 0;
+        const bool main_src = kb < p.kb0;
+        if (main_src && p.taps == 9) {
+          dy = tap / 3 - 1;
+          dx = tap % 3 - 1;
+        }
+        const int ck = main_src ? cc * kBK : (kb - p.kb0) * kBK;
+        const CUtensorMap* ma = main_src ? &map_a0 : &map_a1;
+        const bool ld_a = p.dbg_a_div <= 1 || kb % p.dbg_a_div == 0;
+        const bool ld_b = p.dbg_b_div <= 1 || kb % p.dbg_b_div == 0;
+        const int tx = (ld_a ? kATileBytes : 0) + (ld_b ? b_tile_bytes : 0);
+        if (elect_one()) {
           if (kTwo) {
             // both CTAs' loads complete on the LEADER's barrier, which expects the bytes of the whole pair
-            if (lead_cta) mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(2 * stage_bytes));
+            if (lead_cta) {
+              if (tx) mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(2 * tx));
+              else mbar_arrive(&full_bar[stage]);
+            }
             const uint32_t fb = mapa_u32(&full_bar[stage], 0);
-            tma_load_4d_2sm(sa, ma, fb, ck, x0 + dx, y0 + dy, n0);
-            tma_load_2d_2sm(sb, &map_b, fb, kb * kBK, n_tile * p.bn + static_cast<int>(rank) * b_rows);
+            if (ld_a) tma_load_4d_2sm(sa, ma, fb, ck, x0 + dx, y0 + dy, n0);
+            if (ld_b) tma_load_2d_2sm(sb, &map_b, fb, kb * kBK, n_tile * p.bn + static_cast<int>(rank) * b_rows);
           } else {
-            mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
-            tma_load_4d(sa, ma, &full_bar[stage], ck, x0 + dx, y0 + dy, n0);
-            tma_load_2d(sb, &map_b, &full_bar[stage], kb * kBK, n_tile * p.bn);
+            if (tx) mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(tx));
+            else mbar_arrive(&full_bar[stage]);
+            if (ld_a) tma_load_4d(sa, ma, &full_bar[stage], ck, x0 + dx, y0 + dy, n0);
+            if (ld_b) tma_load_2d(sb, &map_b, &full_bar[stage], kb * kBK, n_tile * p.bn);
           }
-          if (main_src && ++cc == p.kb0_per_tap) {
-            cc = 0;
-            ++tap;
-          }
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        if (main_src && ++cc == p.kb0_per_tap) {
+          cc = 0;
+          ++tap;
+        }
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0 && lead_cta) {
+    // Warp-uniform loop, one elected lane issues: descriptors stay in uniform registers, so each tcgen05.mma is
+    // a single predicated instruction instead of a register->uniform "waterfall" loop (which made the issue
+    // thread, not the tensor pipe, the bound of every N<=256 tile).
+    if (lead_cta) {
       const uint32_t idesc = umma_idesc_f16(kTwo ? 2 * kBM : kBM, static_cast<uint32_t>(p.bn));
       int stage = 0;
       uint32_t phase = 0;
@@ -291,31 +308,37 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
         for (int kb = 0; kb < p.kb_total; ++kb) {
           mbar_wait(&full_bar[stage], phase);
+          __syncwarp();
           tc_fence_after();
-          const uint32_t sa = smem_u32(stage_base + stage * stage_bytes);
+          const uint32_t sa = smem_base_u32 + static_cast<uint32_t>(kBarrierBytes + kBiasBytes + stage * stage_bytes);
           const uint64_t a_desc = umma_smem_desc_sw128(sa);
           const uint64_t b_desc = umma_smem_desc_sw128(sa + kATileBytes);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            // advance 16 fp16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in (addr >> 4) units
-            if (kTwo)
-              umma_f16_2sm(d_tmem, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
-                           static_cast<uint32_t>((kb | k) != 0));
-            else
-              umma_f16(d_tmem, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
-                       static_cast<uint32_t>((kb | k) != 0));
+            for (int k = 0; k < kBK / 16; ++k) {
+              // advance 16 fp16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in (addr >> 4) units
+              if (kTwo)
+                umma_f16_2sm(d_tmem, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
+                             static_cast<uint32_t>((kb | k) != 0));
+              else
+                umma_f16(d_tmem, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
+                         static_cast<uint32_t>((kb | k) != 0));
+            }
+            // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
+            if (kTwo) umma_commit_2sm(&empty_bar[stage], 0x3);
+            else umma_commit(&empty_bar[stage]);
+            if (kb == p.kb_total - 1) {
+              // accumulator complete (signalled to both CTAs' epilogues in pair mode)
+              if (kTwo) umma_commit_2sm(&tmem_full[acc], 0x3);
+              else umma_commit(&tmem_full[acc]);
+            }
           }
-          // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
-          if (kTwo) umma_commit_2sm(&empty_bar[stage], 0x3);
-          else umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        // accumulator complete (signalled to both CTAs' epilogues in pair mode)
-        if (kTwo) umma_commit_2sm(&tmem_full[acc], 0x3);
-        else umma_commit(&tmem_full[acc]);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -573,6 +596,7 @@ int g_debug_epilogue = 0;
 int g_force_bn = 0;
 int g_disable_tma_epi = 0;
 int g_two_cta_mode = 1;
+int g_dbg_a_div = 0, g_dbg_b_div = 0;
 
 }  // namespace
 
@@ -581,6 +605,8 @@ void conv_debug_set(int key, int value) {
   if (key == 1) g_force_bn = value;
   if (key == 2) g_disable_tma_epi = value;
   if (key == 3) g_two_cta_mode = value;
+  if (key == 4) g_dbg_a_div = value;
+  if (key == 5) g_dbg_b_div = value;
 }
 
 // N tile: the largest divisor of n_pad (multiple of 16, <= 256) that still yields enough tiles to fill the SMs;
@@ -666,6 +692,8 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
 
   ConvArgs p;
   p.debug = g_debug_epilogue;
+  p.dbg_a_div = g_dbg_a_div;
+  p.dbg_b_div = g_dbg_b_div;
   p.n_img = d->n;
   p.h = d->h;
   p.w = d->w;

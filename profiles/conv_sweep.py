@@ -74,7 +74,8 @@ if __name__ == "__main__":
     ap.add_argument("--only", default="", help="substring filter on the shape name")
     args = ap.parse_args()
     if args.only:
-        SHAPES[:] = [s for s in SHAPES if args.only in s[0]]
+        SHAPES[:] = [s for s in SHAPES if any(s[0] == f or (f.endswith("*") and s[0].startswith(f[:-1]))
+                                              for f in args.only.split(","))]
     lib = L.load()
     results = []
     for bn in [int(v) for v in args.bn.split(",")]:
