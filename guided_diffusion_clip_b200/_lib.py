@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgd_b200.so")
+# GD_B200_LIB: alternative build of the same ABI (A/B timing experiments only)
+LIB_PATH = os.environ.get("GD_B200_LIB") or os.path.join(_HERE, "libgd_b200.so")
 
 # enums (keep in sync with include/gd_b200.h)
 RES_NONE, RES_SAME, RES_UPSAMPLE2, RES_AVGPOOL2 = 0, 1, 2, 3

@@ -171,7 +171,10 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // relaxed: the only thing ordered through this arrive is TMEM traffic, which the tcgen05 fences on both sides
+  // order; a .release here costs a MEMBAR that waits for every outstanding global store of the thread (7-10% of
+  // the epilogue's stall samples in profiles/ncu_conv_r01f)
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA loads issued by either CTA of a pair; completion bytes are signalled on the barrier at `bar_cluster_addr`
 // (the leader CTA's barrier, in the shared::cluster window)

@@ -34,12 +34,14 @@ constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kATileBytes = kBM * kBK * 2;  // 16 KiB
 constexpr int kMaxStages = 8;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;  // warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 epilogue
+constexpr int kEpiThreads = 256;
 constexpr int kSmemBudget = 227 * 1024;
 constexpr int kBarrierBytes = 1024;
 constexpr int kBiasBytes = 1024;            // 256 floats
-constexpr int kEpiTileBytes = kBM * 64 * 2; // 16 KiB: 128 rows x 64 fp16, SWIZZLE_128B
-constexpr int kEpiBytes = 2 * kEpiTileBytes;  // output staging + residual staging
+constexpr int kEpiCols = 32;                          // columns per epilogue sub-tile
+constexpr int kEpiTileBytes = kBM * kEpiCols * 2;     // 8 KiB: 128 rows x 32 fp16, SWIZZLE_64B
+constexpr int kEpiBytes = 4 * kEpiTileBytes;          // per epilogue group: output staging + residual staging
 
 struct ConvArgs {
   // geometry
@@ -68,7 +70,6 @@ struct ConvArgs {
   float* stats;  // optional GroupNorm partials [m_tiles*4][stats_ld][2] (sum, sum of squares per 4-channel chunk)
   int stats_ld;  // n_pad / 4
   int debug;    // 0 = normal; 1 = epilogue skipped (barriers only); 2 = TMEM loads only (timing experiments)
-  int dbg_a_div, dbg_b_div;  // timing experiments: load the A / B tile only every n-th K block (results are garbage)
 };
 
 __device__ __forceinline__ void tile_coords(const ConvArgs& p, int m_tile, int& n0, int& y0, int& x0) {
@@ -90,11 +91,46 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// named barrier of one epilogue group (4 warps); ids 1 and 2
+__device__ __forceinline__ void epi_barrier(int group) { asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory"); }
 
-// 16-byte chunk `chunk` of row `row` inside a [rows][128 B] tile laid out with the 128-byte swizzle
-__device__ __forceinline__ uint8_t* sw128(uint8_t* tile, int row, int chunk) {
-  return tile + row * 128 + ((chunk ^ (row & 7)) << 4);
+// 16-byte chunk `chunk` (0..3) of row `row` inside a [rows][64 B] tile laid out with the 64-byte swizzle
+__device__ __forceinline__ uint8_t* sw64(uint8_t* tile, int row, int chunk) {
+  return tile + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4);
+}
+
+// Fast-epilogue arithmetic of one thread's 32 columns: accumulator + bias (+ residual) -> fp16 -> swizzled staging
+// row; optional GroupNorm partial sums per 4-channel chunk (taken from the fp32 values: the difference to the
+// fp16-rounded ones is O(2^-12 / sqrt(count)) of the mean, far below the fp16 activation noise).  Straight-line
+// per variant: runtime flags inside the unrolled loop cost instruction-cache misses and branch stalls.
+template <bool kRes, bool kStats>
+__device__ __forceinline__ void epi_compute32(const uint32_t (&v)[32], const float4 (&bv)[8], const Half8 (&rv)[4],
+                                              uint8_t* so, int row, float (&cs)[16]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float f[8];
+    f[0] = __uint_as_float(v[8 * q + 0]) + bv[2 * q].x;
+    f[1] = __uint_as_float(v[8 * q + 1]) + bv[2 * q].y;
+    f[2] = __uint_as_float(v[8 * q + 2]) + bv[2 * q].z;
+    f[3] = __uint_as_float(v[8 * q + 3]) + bv[2 * q].w;
+    f[4] = __uint_as_float(v[8 * q + 4]) + bv[2 * q + 1].x;
+    f[5] = __uint_as_float(v[8 * q + 5]) + bv[2 * q + 1].y;
+    f[6] = __uint_as_float(v[8 * q + 6]) + bv[2 * q + 1].z;
+    f[7] = __uint_as_float(v[8 * q + 7]) + bv[2 * q + 1].w;
+    if (kRes) {
+      float t[8];
+      half8_to_float(rv[q], t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += t[j];
+    }
+    *reinterpret_cast<Half8*>(sw64(so, row, q)) = float_to_half8(f);
+    if (kStats) {
+      cs[2 * q] = (f[0] + f[1]) + (f[2] + f[3]);
+      cs[2 * q + 1] = (f[4] + f[5]) + (f[6] + f[7]);
+      cs[8 + 2 * q] = fmaf(f[3], f[3], fmaf(f[2], f[2], fmaf(f[1], f[1], f[0] * f[0])));
+      cs[8 + 2 * q + 1] = fmaf(f[7], f[7], fmaf(f[6], f[6], fmaf(f[5], f[5], f[4] * f[4])));
+    }
+  }
 }
 
 struct EpiCtx {
@@ -179,20 +215,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                   const __grid_constant__ CUtensorMap map_res, const ConvArgs p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [barriers 1 KiB][bias 1 KiB][stage 0: A | B] ... [out staging 16 KiB][residual staging 16 KiB]
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // align by OFFSETTING the shared-space pointer (an integer round trip would demote every later access to
+  // generic LD/ST instead of LDS/STS)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tmem_full = empty_bar + kMaxStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* res_bar = tmem_empty + 2;
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
-  float* s_bias = reinterpret_cast<float*>(smem + kBarrierBytes);
+  uint64_t* res_bar = tmem_empty + 2;  // one per epilogue group
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(res_bar + 2);
   uint8_t* stage_base = smem + kBarrierBytes + kBiasBytes;
   const int b_rows = kTwo ? (p.bn >> 1) : p.bn;  // weight rows this CTA stages per K block
   const int b_tile_bytes = b_rows * kBK * 2;
   const int stage_bytes = kATileBytes + b_tile_bytes;  // multiple of 1024 (host checks b_rows % 8 == 0)
   uint8_t* s_out = stage_base + p.stages * stage_bytes;
-  uint8_t* s_res = s_out + kEpiTileBytes;
+  uint8_t* s_res = s_out + 2 * kEpiTileBytes;
 
   // warp index via shuffle: the compiler then knows it is warp-uniform and keeps the role loops on the uniform path
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
@@ -220,9 +257,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], kTwo ? 256 : 128);  // pair mode: both CTAs' epilogue threads release the leader
+      mbar_init(&tmem_empty[a], kTwo ? 2 * kEpiThreads : kEpiThreads);  // pair mode: both CTAs' epilogue threads release the leader
     }
-    mbar_init(res_bar, 1);
+    mbar_init(&res_bar[0], 1);
+    mbar_init(&res_bar[1], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -239,55 +277,55 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     // ------------------------------------------------------------------ TMA producer
     // The whole warp walks the loop (warp-uniform control flow keeps addresses and coordinates in uniform
     // registers); one elected lane issues the copies.
+    // K order: main operand tap by tap (ky, kx), 64 channels per block, then the fused 1x1-skip operand.  The loops
+    // are nested so that the per-block body is just: wait, expect, two copies.
+    const int stages = p.stages, kb0_per_tap = p.kb0_per_tap, n_tiles = p.n_tiles, bn = p.bn;
+    const int ntap0 = p.taps, nblk1 = p.kb_total - p.kb0;
+    const uint32_t full0_cluster = kTwo ? mapa_u32(&full_bar[0], 0) : 0u;  // the leader's full_bar[0]
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = work0; tile < total_tiles; tile += work_step) {
-      const int n_tile = tile % p.n_tiles;
-      const int m_tile = kTwo ? 2 * (tile / p.n_tiles) + static_cast<int>(rank) : tile / p.n_tiles;
+      const int n_tile = tile % n_tiles;
+      const int m_tile = kTwo ? 2 * (tile / n_tiles) + static_cast<int>(rank) : tile / n_tiles;
       int n0, y0, x0;
       tile_coords(p, m_tile, n0, y0, x0);
-      int tap = 0, cc = 0;
-      for (int kb = 0; kb < p.kb_total; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        __syncwarp();
-        uint8_t* sa = stage_base + stage * stage_bytes;
-        uint8_t* sb = sa + kATileBytes;
-        int dy = 0, dx = 0;
-        const bool main_src = kb < p.kb0;
-        if (main_src && p.taps == 9) {
-          dy = tap / 3 - 1;
-          dx = tap % 3 - 1;
-        }
-        const int ck = main_src ? cc * kBK : (kb - p.kb0) * kBK;
-        const CUtensorMap* ma = main_src ? &map_a0 : &map_a1;
-        const bool ld_a = p.dbg_a_div <= 1 || kb % p.dbg_a_div == 0;
-        const bool ld_b = p.dbg_b_div <= 1 || kb % p.dbg_b_div == 0;
-        const int tx = (ld_a ? kATileBytes : 0) + (ld_b ? b_tile_bytes : 0);
-        if (elect_one()) {
-          if (kTwo) {
-            // both CTAs' loads complete on the LEADER's barrier, which expects the bytes of the whole pair
-            if (lead_cta) {
-              if (tx) mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(2 * tx));
-              else mbar_arrive(&full_bar[stage]);
+      const int b_row0 = n_tile * bn + (kTwo ? static_cast<int>(rank) * b_rows : 0);
+      int kcol = 0;  // K coordinate of the weight tile
+      for (int src = 0; src < 2; ++src) {
+        const CUtensorMap* ma = src == 0 ? &map_a0 : &map_a1;
+        const int ntap = src == 0 ? ntap0 : (nblk1 > 0 ? 1 : 0);
+        const int nblk = src == 0 ? kb0_per_tap : nblk1;
+        int dy = (src == 0 && ntap0 == 9) ? -1 : 0;
+        int dx = dy;
+        for (int tap = 0; tap < ntap; ++tap) {
+          const int cx = x0 + dx, cy = y0 + dy;
+          for (int cc = 0; cc < nblk; ++cc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            __syncwarp();
+            if (elect_one()) {
+              uint8_t* sa = stage_base + stage * stage_bytes;
+              if (kTwo) {
+                // both CTAs' loads complete on the LEADER's barrier, which expects the bytes of the whole pair
+                if (lead_cta) mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(2 * stage_bytes));
+                const uint32_t fb = full0_cluster + static_cast<uint32_t>(stage) * 8u;
+                tma_load_4d_2sm(sa, ma, fb, cc * kBK, cx, cy, n0);
+                tma_load_2d_2sm(sa + kATileBytes, &map_b, fb, kcol, b_row0);
+              } else {
+                mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
+                tma_load_4d(sa, ma, &full_bar[stage], cc * kBK, cx, cy, n0);
+                tma_load_2d(sa + kATileBytes, &map_b, &full_bar[stage], kcol, b_row0);
+              }
             }
-            const uint32_t fb = mapa_u32(&full_bar[stage], 0);
-            if (ld_a) tma_load_4d_2sm(sa, ma, fb, ck, x0 + dx, y0 + dy, n0);
-            if (ld_b) tma_load_2d_2sm(sb, &map_b, fb, kb * kBK, n_tile * p.bn + static_cast<int>(rank) * b_rows);
-          } else {
-            if (tx) mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(tx));
-            else mbar_arrive(&full_bar[stage]);
-            if (ld_a) tma_load_4d(sa, ma, &full_bar[stage], ck, x0 + dx, y0 + dy, n0);
-            if (ld_b) tma_load_2d(sb, &map_b, &full_bar[stage], kb * kBK, n_tile * p.bn);
+            kcol += kBK;
+            if (++stage == stages) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
-        }
-        __syncwarp();
-        if (main_src && ++cc == p.kb0_per_tap) {
-          cc = 0;
-          ++tap;
-        }
-        if (++stage == p.stages) {
-          stage = 0;
-          phase ^= 1;
+          if (++dx == 2) {
+            dx = -1;
+            ++dy;
+          }
         }
       }
     }
@@ -302,11 +340,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      const int stages = p.stages, kb_total = p.kb_total;
       for (int tile = work0; tile < total_tiles; tile += work_step) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
-        for (int kb = 0; kb < p.kb_total; ++kb) {
+        for (int kb = 0; kb < kb_total; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           __syncwarp();
           tc_fence_after();
@@ -327,14 +366,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
             if (kTwo) umma_commit_2sm(&empty_bar[stage], 0x3);
             else umma_commit(&empty_bar[stage]);
-            if (kb == p.kb_total - 1) {
+            if (kb == kb_total - 1) {
               // accumulator complete (signalled to both CTAs' epilogues in pair mode)
               if (kTwo) umma_commit_2sm(&tmem_full[acc], 0x3);
               else umma_commit(&tmem_full[acc]);
             }
           }
-          __syncwarp();
-          if (++stage == p.stages) {
+          if (++stage == stages) {
             stage = 0;
             phase ^= 1;
           }
@@ -349,8 +387,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     // ------------------------------------------------------------------ epilogue (warps 2..5)
     const int quarter = warp & 3;          // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;   // row of the 128-row tile == pixel within the patch
-    const int epi_tid = threadIdx.x - 64;  // 0..127
-    const bool leader = epi_tid == 0;
+    // Two independent epilogue groups (warps 2..5 and 6..9, one warp per TMEM lane quarter each) take alternate
+    // 32-column sub-tiles of every accumulator, each with its own staging buffers, residual barrier and named
+    // barrier: while one group waits (TMEM load, residual, TMA store read-out) the other computes.
+    const int group = (warp - 2) >> 2;
+    const bool leader = (threadIdx.x - 64 - group * 128) == 0;
+    uint8_t* so = s_out + group * kEpiTileBytes;
+    uint8_t* sr = s_res + group * kEpiTileBytes;
+    uint64_t* rbar = &res_bar[group];
     // hand a drained accumulator back to the MMA issuer (pair mode: the issuer lives in the leader CTA)
     auto release_accumulator = [&](uint64_t* bar) {
       if (kTwo) mbar_arrive_cluster(mapa_u32(bar, 0));
@@ -384,13 +428,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       const int col_base = n_tile * p.bn;
       const int rx0 = p.res_mode == GD_RES_UPSAMPLE2 ? (x0 >> 1) : x0;
       const int ry0 = p.res_mode == GD_RES_UPSAMPLE2 ? (y0 >> 1) : y0;
-      if (p.tma_epi) {
-        // stage this tile's bias; prefetch the first residual sub-tile while the mainloop is still running
-        for (int j = epi_tid; j < p.bn; j += 128) s_bias[j] = p.bias != nullptr ? __ldg(p.bias + col_base + j) : 0.f;
-        if (leader && res_tma) {
-          mbar_arrive_expect_tx(res_bar, res_bytes);
-          tma_load_4d(s_res, &map_res, res_bar, col_base, rx0, ry0, n0);
-        }
+      const int nsub = p.bn >> 5;  // 32-column sub-tiles; this group takes sub = group, group + 2, ...
+      if (leader && res_tma) {
+        // prefetch this group's first residual sub-tile while the mainloop is still running (the group consumed
+        // its residual buffer before the last barrier of the previous tile)
+        mbar_arrive_expect_tx(rbar, res_bytes);
+        tma_load_4d(sr, &map_res, rbar, col_base + group * kEpiCols, rx0, ry0, n0);
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -399,35 +442,39 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       if (p.debug == 1) {
         // timing experiment: no epilogue work at all
       } else if (!p.tma_epi) {
-        int c0 = 0;
-        for (; c0 + 32 <= p.bn; c0 += 32) epi_chunk_direct<32>(p, t_row + static_cast<uint32_t>(c0), col_base + c0, e);
-        if (c0 + 16 <= p.bn) epi_chunk_direct<16>(p, t_row + static_cast<uint32_t>(c0), col_base + c0, e);
+        for (int j = group; j < nsub; j += 2)
+          epi_chunk_direct<32>(p, t_row + static_cast<uint32_t>(j * 32), col_base + j * 32, e);
+        if ((p.bn & 16) != 0 && group == (nsub & 1))
+          epi_chunk_direct<16>(p, t_row + static_cast<uint32_t>(nsub * 32), col_base + nsub * 32, e);
       } else {
-        epi_barrier();  // s_bias visible to all epilogue threads
-        const int nsub = p.bn >> 6;
-        for (int sub = 0; sub < nsub; ++sub) {
-          const int c0 = sub * 64;
-          uint32_t v[64];
-          tmem_ld_x32(t_row + static_cast<uint32_t>(c0), *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-          tmem_ld_x32(t_row + static_cast<uint32_t>(c0 + 32), *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-          Half8 rv[8];
+        for (int sub = group; sub < nsub; sub += 2) {
+          const int ch = sub * kEpiCols;  // first column of this sub-tile within the N tile
+          uint32_t v[32];
+          tmem_ld_x32(t_row + static_cast<uint32_t>(ch), v);
+          // bias: the same 128 bytes for every thread -> broadcast loads through L1
+          float4 bv[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            bv[q] = p.bias != nullptr ? __ldg(reinterpret_cast<const float4*>(p.bias + col_base + ch) + q)
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+          Half8 rv[4];
           if (res_tma) {
-            mbar_wait(res_bar, res_phase);
+            mbar_wait(rbar, res_phase);
             res_phase ^= 1;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) rv[q] = *reinterpret_cast<const Half8*>(sw128(s_res, res_row, q));
+            for (int q = 0; q < 4; ++q) rv[q] = *reinterpret_cast<const Half8*>(sw64(sr, res_row, q));
           } else if (p.res_mode == GD_RES_AVGPOOL2 && e.valid && p.debug == 0) {
             // residual lives at double resolution (unet.py:136,241): direct global reads, fp32 average -> fp16
-            float racc[64];
+            float racc[32];
 #pragma unroll
-            for (int j = 0; j < 64; ++j) racc[j] = 0.f;
+            for (int j = 0; j < 32; ++j) racc[j] = 0.f;
 #pragma unroll
             for (int s4 = 0; s4 < 4; ++s4) {
               const size_t rpix = (static_cast<size_t>(e.img) * (p.h * 2) + (2 * e.y + (s4 >> 1))) * (p.w * 2) +
                                   (2 * e.x + (s4 & 1));
-              const __half* rp = p.res + rpix * p.ld_res + col_base + c0;
+              const __half* rp = p.res + rpix * p.ld_res + col_base + ch;
 #pragma unroll
-              for (int q = 0; q < 8; ++q) {
+              for (int q = 0; q < 4; ++q) {
                 float t[8];
                 half8_to_float(ld_half8(rp + 8 * q), t);
 #pragma unroll
@@ -435,7 +482,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
               }
             }
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
+            for (int q = 0; q < 4; ++q) {
               float t[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) t[j] = 0.25f * racc[8 * q + j];
@@ -443,80 +490,57 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             }
           }
           tmem_ld_wait();
-          if (sub == nsub - 1) {
-            // accumulator fully read: hand the TMEM buffer back to the MMA warp before the store phase
+          if (sub + 2 >= nsub) {
+            // this thread has read its last columns of the accumulator: hand the TMEM buffer back to the MMA warp
             tc_fence_before();
             release_accumulator(&tmem_empty[acc]);
           }
-          // s_out is free once the previous TMA store has finished READING it
+          // the staging tile is free once the group's previous TMA store has finished READING it
           if (leader) bulk_wait_read0();
-          epi_barrier();  // (A) s_out reusable; every thread has consumed s_res
-          if (leader && res_tma && sub + 1 < nsub) {
-            mbar_arrive_expect_tx(res_bar, res_bytes);
-            tma_load_4d(s_res, &map_res, res_bar, col_base + c0 + 64, rx0, ry0, n0);
+          epi_barrier(group);  // (A) staging tile reusable; every thread of the group has consumed the residual tile
+          if (leader && res_tma && sub + 2 < nsub) {
+            mbar_arrive_expect_tx(rbar, res_bytes);
+            tma_load_4d(sr, &map_res, rbar, col_base + ch + 2 * kEpiCols, rx0, ry0, n0);
           }
           if (p.debug == 0) {
+            float cs[16];  // [0,8): per-4-channel-chunk sums of this row, [8,16): sums of squares
             const bool has_res = p.res_mode != GD_RES_NONE;
-            float cs[32];  // [0,16): per-4-channel-chunk sums of this row, [16,32): sums of squares
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              float f[8];
-              const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c0 + 8 * q);
-              const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c0 + 8 * q + 4);
-              f[0] = __uint_as_float(v[8 * q + 0]) + b0.x;
-              f[1] = __uint_as_float(v[8 * q + 1]) + b0.y;
-              f[2] = __uint_as_float(v[8 * q + 2]) + b0.z;
-              f[3] = __uint_as_float(v[8 * q + 3]) + b0.w;
-              f[4] = __uint_as_float(v[8 * q + 4]) + b1.x;
-              f[5] = __uint_as_float(v[8 * q + 5]) + b1.y;
-              f[6] = __uint_as_float(v[8 * q + 6]) + b1.z;
-              f[7] = __uint_as_float(v[8 * q + 7]) + b1.w;
-              if (has_res) {
-                float t[8];
-                half8_to_float(rv[q], t);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] += t[j];
-              }
-              if (p.out_scale != 1.0f) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] *= p.out_scale;
-              }
-              const Half8 hv = float_to_half8(f);
-              *reinterpret_cast<Half8*>(sw128(s_out, row, q)) = hv;
-              if (p.stats != nullptr) {
-                // GroupNorm statistics of the STORED (fp16-rounded) values; rows outside the image contribute 0
-                float r[8];
-                half8_to_float(hv, r);
-                const float m = e.valid ? 1.0f : 0.0f;
-                cs[2 * q] = m * ((r[0] + r[1]) + (r[2] + r[3]));
-                cs[2 * q + 1] = m * ((r[4] + r[5]) + (r[6] + r[7]));
-                cs[16 + 2 * q] = m * ((r[0] * r[0] + r[1] * r[1]) + (r[2] * r[2] + r[3] * r[3]));
-                cs[16 + 2 * q + 1] = m * ((r[4] * r[4] + r[5] * r[5]) + (r[6] * r[6] + r[7] * r[7]));
-              }
+            if (p.stats != nullptr) {
+              if (has_res) epi_compute32<true, true>(v, bv, rv, so, row, cs);
+              else epi_compute32<false, true>(v, bv, rv, so, row, cs);
+            } else {
+              if (has_res) epi_compute32<true, false>(v, bv, rv, so, row, cs);
+              else epi_compute32<false, false>(v, bv, rv, so, row, cs);
             }
             if (p.stats != nullptr) {
-              // reduce the 32 values over the warp's 32 rows with a halving butterfly (31 shuffles): lane L ends up
-              // holding the warp total of value L, then one coalesced 128-byte store per warp
+              if (!e.valid) {  // rows outside the image contribute 0
 #pragma unroll
-              for (int off = 16; off >= 1; off >>= 1) {
+                for (int i = 0; i < 16; ++i) cs[i] = 0.f;
+              }
+              // reduce the 16 values over the warp's 32 rows: a halving butterfly (8+4+2+1 shuffles) leaves value
+              // (lane >> 1) in each lane pair, one more exchange completes it; even lanes store
+#pragma unroll
+              for (int off = 16, n = 8; off >= 2; off >>= 1, n >>= 1) {
                 const bool hi = (lane & off) != 0;
 #pragma unroll
-                for (int i = 0; i < off; ++i) {
-                  const float send = hi ? cs[i] : cs[i + off];
-                  const float keep = hi ? cs[i + off] : cs[i];
+                for (int i = 0; i < n; ++i) {
+                  const float send = hi ? cs[i] : cs[i + n];
+                  const float keep = hi ? cs[i + n] : cs[i];
                   cs[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
                 }
               }
-              if (m_tile < p.m_tiles) {
-              float* sp = p.stats + (static_cast<size_t>(m_tile) * 4 + quarter) * p.stats_ld * 2;
-              sp[(((col_base + c0) >> 2) + (lane & 15)) * 2 + (lane >> 4)] = cs[0];
+              cs[0] += __shfl_xor_sync(0xffffffffu, cs[0], 1);
+              if (m_tile < p.m_tiles && (lane & 1) == 0) {
+                const int idx = lane >> 1;  // 0..7: chunk sums, 8..15: chunk sums of squares
+                float* sp = p.stats + (static_cast<size_t>(m_tile) * 4 + quarter) * p.stats_ld * 2;
+                sp[(((col_base + ch) >> 2) + (idx & 7)) * 2 + (idx >> 3)] = cs[0];
               }
             }
             fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
           }
-          epi_barrier();  // (B) staging tile complete
+          epi_barrier(group);  // (B) staging tile complete
           if (leader && p.debug == 0 && m_tile < p.m_tiles) {  // (an odd tile count leaves the last pair half empty)
-            tma_store_4d(&map_out, s_out, col_base + c0, x0, y0, n0);
+            tma_store_4d(&map_out, so, col_base + ch, x0, y0, n0);
             bulk_commit();
           }
         }
@@ -561,16 +585,18 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int encode_act_map(CUtensorMap* m, const void* base, int c, int ld, int n, int h, int w, int bi, int bh, int bw) {
+// box_c = 64 (mainloop operand tiles, SWIZZLE_128B) or 32 (epilogue staging tiles, SWIZZLE_64B)
+int encode_act_map(CUtensorMap* m, const void* base, int c, int ld, int n, int h, int w, int bi, int bh, int bw,
+                   int box_c = kBK) {
   EncodeTiledFn enc = get_encode_fn();
   GD_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled driver entry point unavailable");
   cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
   cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)w * ld * 2, (cuuint64_t)h * w * ld * 2};
-  cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bi};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bi};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_c == kBK ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   GD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation) failed: %d (c=%d ld=%d n=%d h=%d w=%d)", (int)r, c,
              ld, n, h, w);
   return 0;
@@ -596,7 +622,6 @@ int g_debug_epilogue = 0;
 int g_force_bn = 0;
 int g_disable_tma_epi = 0;
 int g_two_cta_mode = 1;
-int g_dbg_a_div = 0, g_dbg_b_div = 0;
 
 }  // namespace
 
@@ -605,8 +630,6 @@ void conv_debug_set(int key, int value) {
   if (key == 1) g_force_bn = value;
   if (key == 2) g_disable_tma_epi = value;
   if (key == 3) g_two_cta_mode = value;
-  if (key == 4) g_dbg_a_div = value;
-  if (key == 5) g_dbg_b_div = value;
 }
 
 // N tile: the largest divisor of n_pad (multiple of 16, <= 256) that still yields enough tiles to fill the SMs;
@@ -692,8 +715,6 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
 
   ConvArgs p;
   p.debug = g_debug_epilogue;
-  p.dbg_a_div = g_dbg_a_div;
-  p.dbg_b_div = g_dbg_b_div;
   p.n_img = d->n;
   p.h = d->h;
   p.w = d->w;
@@ -728,7 +749,7 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
   p.out_scale = d->out_scale == 0.0f ? 1.0f : d->out_scale;
   // staged TMA-store epilogue: fp16 NHWC, whole 64-channel sub-tiles, 16-byte aligned rows; an upsampled residual
   // additionally needs an even patch
-  p.tma_epi = (!g_disable_tma_epi && d->out_mode == GD_OUT_NHWC_F16 && d->cout % 64 == 0 && bn % 64 == 0 &&
+  p.tma_epi = (!g_disable_tma_epi && d->out_scale == 1.0f && d->out_mode == GD_OUT_NHWC_F16 && d->cout % 64 == 0 && bn % 64 == 0 &&
                d->ld_out % 8 == 0 && (reinterpret_cast<uintptr_t>(d->out) % 16 == 0) &&
                !(d->res_mode == GD_RES_UPSAMPLE2 && (bw % 2 || bh % 2)))
                   ? 1
@@ -751,13 +772,13 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
   mout = ma0;
   mres = ma0;
   if (p.tma_epi) {
-    rc = encode_act_map(&mout, d->out, d->cout, d->ld_out, d->n, d->h, d->w, bi, bh, bw);
+    rc = encode_act_map(&mout, d->out, d->cout, d->ld_out, d->n, d->h, d->w, bi, bh, bw, kEpiCols);
     if (rc) return rc;
     if (d->res_mode == GD_RES_SAME) {
-      rc = encode_act_map(&mres, d->res, d->cout, d->ld_res, d->n, d->h, d->w, bi, bh, bw);
+      rc = encode_act_map(&mres, d->res, d->cout, d->ld_res, d->n, d->h, d->w, bi, bh, bw, kEpiCols);
       if (rc) return rc;
     } else if (d->res_mode == GD_RES_UPSAMPLE2) {
-      rc = encode_act_map(&mres, d->res, d->cout, d->ld_res, d->n, d->h / 2, d->w / 2, bi, bh / 2, bw / 2);
+      rc = encode_act_map(&mres, d->res, d->cout, d->ld_res, d->n, d->h / 2, d->w / 2, bi, bh / 2, bw / 2, kEpiCols);
       if (rc) return rc;
     }
   }

@@ -29,7 +29,12 @@ SHAPES = [
     ("8^2 2048->1024", 8, 8, 2048, 1024, 9, 0, L.RES_NONE),
     ("32^2 qkv 512->1536", 8, 32, 512, 1536, 1, 0, L.RES_NONE),
     ("256^2 128->128 (clf)", 8, 256, 128, 128, 9, 0, L.RES_NONE),
+    ("256^2 128->128 +res (clf)", 8, 256, 128, 128, 9, 0, L.RES_SAME),
+    ("256^2 1x1 64->256 (first conv)", 8, 256, 64, 256, 1, 0, L.RES_NONE),
 ]
+
+
+WITH_STATS = False  # --stats: also request the fused GroupNorm partial statistics (as the UNet's convs do)
 
 
 def run(shape, reps=8):
@@ -51,6 +56,9 @@ def run(shape, reps=8):
     if res is not None:
         d.res, d.ld_res, d.res_mode = res.data_ptr(), cout, res_mode
     d.out, d.ld_out, d.out_mode, d.out_scale = out.data_ptr(), cout, L.OUT_NHWC_F16, 1.0
+    if WITH_STATS and cout % 64 == 0:
+        stats = th.empty(((n * h * h + 127) // 128 * 4, cout // 4, 2), device="cuda")
+        d.stats_out = stats.data_ptr()
     stream = C.c_void_p(th.cuda.current_stream().cuda_stream)
     evs = []
     for i in range(reps + 2):
@@ -72,7 +80,9 @@ if __name__ == "__main__":
     ap.add_argument("--modes", default="0,1,2")
     ap.add_argument("--bn", default="0")
     ap.add_argument("--only", default="", help="substring filter on the shape name")
+    ap.add_argument("--stats", action="store_true")
     args = ap.parse_args()
+    WITH_STATS = args.stats
     if args.only:
         SHAPES[:] = [s for s in SHAPES if any(s[0] == f or (f.endswith("*") and s[0].startswith(f[:-1]))
                                               for f in args.only.split(","))]

@@ -52,5 +52,35 @@ def raw(path):
         print()
 
 
+
+
+def source(path, which=0, top=45):
+    """Top SASS instructions by warp-stall samples of the `which`-th kernel in the report (needs -lineinfo capture)."""
+    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    blocks, cur = [], None
+    for r in csv.reader(out.splitlines()):
+        if r and r[0] == "Kernel Name":
+            cur = {"name": r[1], "rows": [], "hdr": None}
+            blocks.append(cur)
+        elif cur is not None and cur["hdr"] is None:
+            cur["hdr"] = r
+        elif cur is not None:
+            cur["rows"].append(r)
+    b = blocks[which]
+    h = b["hdr"]
+    si = h.index("# Samples")
+    stall_cols = [i for i, c in enumerate(h) if c.startswith("stall_") and "Not Issued" not in c]
+    tot = sum(int(r[si] or 0) for r in b["rows"])
+    print("kernel:", b["name"][:90], "total samples", tot)
+    order = sorted(range(len(b["rows"])), key=lambda i: -int(b["rows"][i][si] or 0))[:top]
+    for i in sorted(order):
+        r = b["rows"][i]
+        st = sorted(((int(r[c] or 0), h[c][6:]) for c in stall_cols), reverse=True)[:2]
+        print(f"{i:6d} {int(r[si]):7d} {100 * int(r[si]) / max(tot, 1):5.1f}%  {r[1].strip()[:70]:70s} {st}")
+
+
 if __name__ == "__main__":
-    {"launches": launches, "raw": raw}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "source":
+        source(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 0, int(sys.argv[4]) if len(sys.argv) > 4 else 45)
+    else:
+        {"launches": launches, "raw": raw}[sys.argv[1]](sys.argv[2])
