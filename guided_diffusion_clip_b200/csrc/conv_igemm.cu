@@ -33,7 +33,8 @@ namespace {
 constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kATileBytes = kBM * kBK * 2;  // 16 KiB
-constexpr int kMaxStages = 8;
+constexpr int kMaxA = 8;   // activation-ring slots (barrier array size)
+constexpr int kMaxB = 16;  // weight-ring slots
 constexpr int kThreads = 320;  // warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 epilogue
 constexpr int kEpiThreads = 256;
 constexpr int kSmemBudget = 227 * 1024;
@@ -50,7 +51,10 @@ struct ConvArgs {
   int patches_x, patches_y;    // per image (group)
   int m_tiles, n_tiles;
   int bn;                      // N tile
-  int stages;
+  // mainloop rings: activation slots and weight slots are pipelined independently
+  int halo;          // 1: one activation slot = (BH+2) x BW pixel halo tile shared by the 3 ky taps of one kx
+  int a_slot_bytes;  // halo: (BH+2)*BW*128, else 16 KiB
+  int n_a, n_b;      // ring depths
   // K blocks
   int kb0_per_tap;             // C0 / 64
   int taps;                    // 9 or 1
@@ -82,10 +86,19 @@ __device__ __forceinline__ void tile_coords(const ConvArgs& p, int m_tile, int& 
   x0 = px * p.bw;
 }
 
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-               ::"l"(m), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
+// Output tiles are written once and not re-read by this kernel: store them with an evict-first L2 policy so they do
+// not displace the activation lines the other 8 taps are about to re-read.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3,
+                                             uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5}], [%1], %6;"
+      ::"l"(m), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
+      : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -214,21 +227,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                   const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out,
                   const __grid_constant__ CUtensorMap map_res, const ConvArgs p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [barriers 1 KiB][bias 1 KiB][stage 0: A | B] ... [out staging 16 KiB][residual staging 16 KiB]
+  // carve: [barriers 1 KiB][spare 1 KiB][activation ring][weight ring][out staging 2 x 8 KiB][residual staging 2 x 8 KiB]
   // align by OFFSETTING the shared-space pointer (an integer round trip would demote every later access to
   // generic LD/ST instead of LDS/STS)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
-  uint64_t* empty_bar = full_bar + kMaxStages;
-  uint64_t* tmem_full = empty_bar + kMaxStages;
+  uint64_t* full_a = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty_a = full_a + kMaxA;
+  uint64_t* full_b = empty_a + kMaxA;
+  uint64_t* empty_b = full_b + kMaxB;
+  uint64_t* tmem_full = empty_b + kMaxB;
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* res_bar = tmem_empty + 2;  // one per epilogue group
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(res_bar + 2);
-  uint8_t* stage_base = smem + kBarrierBytes + kBiasBytes;
+  uint8_t* a_ring = smem + kBarrierBytes + kBiasBytes;
   const int b_rows = kTwo ? (p.bn >> 1) : p.bn;  // weight rows this CTA stages per K block
-  const int b_tile_bytes = b_rows * kBK * 2;
-  const int stage_bytes = kATileBytes + b_tile_bytes;  // multiple of 1024 (host checks b_rows % 8 == 0)
-  uint8_t* s_out = stage_base + p.stages * stage_bytes;
+  const int b_tile_bytes = b_rows * kBK * 2;     // multiple of 1024 (host checks b_rows % 8 == 0)
+  uint8_t* b_ring = a_ring + p.n_a * p.a_slot_bytes;
+  uint8_t* s_out = b_ring + p.n_b * b_tile_bytes;
   uint8_t* s_res = s_out + 2 * kEpiTileBytes;
 
   // warp index via shuffle: the compiler then knows it is warp-uniform and keeps the role loops on the uniform path
@@ -251,9 +266,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       tma_prefetch_desc(&map_out);
       tma_prefetch_desc(&map_res);
     }
-    for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+    for (int s = 0; s < p.n_a; ++s) {
+      mbar_init(&full_a[s], 1);
+      mbar_init(&empty_a[s], 1);
+    }
+    for (int s = 0; s < p.n_b; ++s) {
+      mbar_init(&full_b[s], 1);
+      mbar_init(&empty_b[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
@@ -273,58 +292,93 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
+  // K schedule shared by the producer and the MMA issuer.  Per 64-channel block of the main operand:
+  //   halo mode (3x3, one image per tile): 3 activation groups (kx = 0..2), each ONE (BH+2) x BW halo tile that
+  //     serves the 3 ky taps as row-shifted views (ky * BW * 128 bytes) -> 3 activation copies instead of 9;
+  //   plain 3x3: 9 groups of one tap; 1x1: one group.  Then the fused 1x1-skip operand: one group per block.
+  // Every tap of every group consumes one weight slot.
+  const int n_a = p.n_a, n_b = p.n_b, a_slot = p.a_slot_bytes;
+  const int kb0_per_tap = p.kb0_per_tap, ntap0 = p.taps, nblk1 = p.kb_total - p.kb0, c0_total = p.kb0_per_tap * kBK;
+  const bool halo = p.halo != 0;
+  const int ngrp0 = halo ? 3 : ntap0;  // groups per channel block of the main operand
+  const int nt0 = halo ? 3 : 1;        // taps per group
+  const uint32_t tap_stride = static_cast<uint32_t>(p.bw) * 128u;  // smem bytes between ky views of a halo tile
+
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     // The whole warp walks the loop (warp-uniform control flow keeps addresses and coordinates in uniform
     // registers); one elected lane issues the copies.
-    // K order: main operand tap by tap (ky, kx), 64 channels per block, then the fused 1x1-skip operand.  The loops
-    // are nested so that the per-block body is just: wait, expect, two copies.
-    const int stages = p.stages, kb0_per_tap = p.kb0_per_tap, n_tiles = p.n_tiles, bn = p.bn;
-    const int ntap0 = p.taps, nblk1 = p.kb_total - p.kb0;
-    const uint32_t full0_cluster = kTwo ? mapa_u32(&full_bar[0], 0) : 0u;  // the leader's full_bar[0]
-    int stage = 0;
-    uint32_t phase = 0;
+    const int n_tiles = p.n_tiles, bn = p.bn;
+    const uint32_t full_a0_cluster = kTwo ? mapa_u32(&full_a[0], 0) : 0u;  // the leader's barriers
+    const uint32_t full_b0_cluster = kTwo ? mapa_u32(&full_b[0], 0) : 0u;
+    const uint32_t halo_bytes = static_cast<uint32_t>(a_slot);
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
     for (int tile = work0; tile < total_tiles; tile += work_step) {
       const int n_tile = tile % n_tiles;
       const int m_tile = kTwo ? 2 * (tile / n_tiles) + static_cast<int>(rank) : tile / n_tiles;
       int n0, y0, x0;
       tile_coords(p, m_tile, n0, y0, x0);
       const int b_row0 = n_tile * bn + (kTwo ? static_cast<int>(rank) * b_rows : 0);
-      int kcol = 0;  // K coordinate of the weight tile
       for (int src = 0; src < 2; ++src) {
-        const CUtensorMap* ma = src == 0 ? &map_a0 : &map_a1;
-        const int ntap = src == 0 ? ntap0 : (nblk1 > 0 ? 1 : 0);
-        const int nblk = src == 0 ? kb0_per_tap : nblk1;
-        int dy = (src == 0 && ntap0 == 9) ? -1 : 0;
-        int dx = dy;
-        for (int tap = 0; tap < ntap; ++tap) {
-          const int cx = x0 + dx, cy = y0 + dy;
-          for (int cc = 0; cc < nblk; ++cc) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
+        const bool main_src = src == 0;
+        const CUtensorMap* ma = main_src ? &map_a0 : &map_a1;
+        const int nblk = main_src ? kb0_per_tap : nblk1;
+        const int ngrp = main_src ? ngrp0 : 1;
+        const int nt = main_src ? nt0 : 1;
+        const uint32_t a_bytes = (main_src && halo) ? halo_bytes : static_cast<uint32_t>(kATileBytes);
+        for (int cb = 0; cb < nblk; ++cb) {
+          for (int g = 0; g < ngrp; ++g) {
+            int cx = x0, cy = y0, kcol, kstep = 0;
+            if (main_src && halo) {  // group = kx; taps ky = 0..2 -> weight columns (ky*3 + kx)*C0
+              cx = x0 + g - 1;
+              cy = y0 - 1;
+              kcol = g * c0_total + cb * kBK;
+              kstep = 3 * c0_total;
+            } else if (main_src) {  // group = tap (or the only tap of a 1x1)
+              if (ntap0 == 9) {
+                cx = x0 + g % 3 - 1;
+                cy = y0 + g / 3 - 1;
+              }
+              kcol = g * c0_total + cb * kBK;
+            } else {
+              kcol = p.kb0 * kBK + cb * kBK;
+            }
+            mbar_wait(&empty_a[sa], pa ^ 1);
             __syncwarp();
             if (elect_one()) {
-              uint8_t* sa = stage_base + stage * stage_bytes;
+              uint8_t* dst = a_ring + sa * a_slot;
               if (kTwo) {
                 // both CTAs' loads complete on the LEADER's barrier, which expects the bytes of the whole pair
-                if (lead_cta) mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(2 * stage_bytes));
-                const uint32_t fb = full0_cluster + static_cast<uint32_t>(stage) * 8u;
-                tma_load_4d_2sm(sa, ma, fb, cc * kBK, cx, cy, n0);
-                tma_load_2d_2sm(sa + kATileBytes, &map_b, fb, kcol, b_row0);
+                if (lead_cta) mbar_arrive_expect_tx(&full_a[sa], 2 * a_bytes);
+                tma_load_4d_2sm(dst, ma, full_a0_cluster + static_cast<uint32_t>(sa) * 8u, cb * kBK, cx, cy, n0);
               } else {
-                mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
-                tma_load_4d(sa, ma, &full_bar[stage], cc * kBK, cx, cy, n0);
-                tma_load_2d(sa + kATileBytes, &map_b, &full_bar[stage], kcol, b_row0);
+                mbar_arrive_expect_tx(&full_a[sa], a_bytes);
+                tma_load_4d(dst, ma, &full_a[sa], cb * kBK, cx, cy, n0);
               }
             }
-            kcol += kBK;
-            if (++stage == stages) {
-              stage = 0;
-              phase ^= 1;
+            if (++sa == n_a) {
+              sa = 0;
+              pa ^= 1;
             }
-          }
-          if (++dx == 2) {
-            dx = -1;
-            ++dy;
+            for (int t = 0; t < nt; ++t) {
+              mbar_wait(&empty_b[sb], pb ^ 1);
+              __syncwarp();
+              if (elect_one()) {
+                uint8_t* dst = b_ring + sb * b_tile_bytes;
+                if (kTwo) {
+                  if (lead_cta) mbar_arrive_expect_tx(&full_b[sb], static_cast<uint32_t>(2 * b_tile_bytes));
+                  tma_load_2d_2sm(dst, &map_b, full_b0_cluster + static_cast<uint32_t>(sb) * 8u, kcol + t * kstep, b_row0);
+                } else {
+                  mbar_arrive_expect_tx(&full_b[sb], static_cast<uint32_t>(b_tile_bytes));
+                  tma_load_2d(dst, &map_b, &full_b[sb], kcol + t * kstep, b_row0);
+                }
+              }
+              if (++sb == n_b) {
+                sb = 0;
+                pb ^= 1;
+              }
+            }
           }
         }
       }
@@ -336,45 +390,61 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     // thread, not the tensor pipe, the bound of every N<=256 tile).
     if (lead_cta) {
       const uint32_t idesc = umma_idesc_f16(kTwo ? 2 * kBM : kBM, static_cast<uint32_t>(p.bn));
-      int stage = 0;
-      uint32_t phase = 0;
+      const uint32_t a_ring_u32 = smem_base_u32 + static_cast<uint32_t>(kBarrierBytes + kBiasBytes);
+      const uint32_t b_ring_u32 = a_ring_u32 + static_cast<uint32_t>(n_a * a_slot);
+      const int groups_main = kb0_per_tap * ngrp0;
+      const int groups_total = groups_main + nblk1;
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      const int stages = p.stages, kb_total = p.kb_total;
       for (int tile = work0; tile < total_tiles; tile += work_step) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
-        for (int kb = 0; kb < kb_total; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          __syncwarp();
-          tc_fence_after();
-          const uint32_t sa = smem_base_u32 + static_cast<uint32_t>(kBarrierBytes + kBiasBytes + stage * stage_bytes);
-          const uint64_t a_desc = umma_smem_desc_sw128(sa);
-          const uint64_t b_desc = umma_smem_desc_sw128(sa + kATileBytes);
-          if (elect_one()) {
+        for (int grp = 0; grp < groups_total; ++grp) {
+          const int nt = grp < groups_main ? nt0 : 1;
+          mbar_wait(&full_a[sa], pa);
+          const uint32_t a_base = a_ring_u32 + static_cast<uint32_t>(sa * a_slot);
+          for (int t = 0; t < nt; ++t) {
+            mbar_wait(&full_b[sb], pb);
+            __syncwarp();
+            tc_fence_after();
+            const uint64_t a_desc = umma_smem_desc_sw128(a_base + static_cast<uint32_t>(t) * tap_stride);
+            const uint64_t b_desc = umma_smem_desc_sw128(b_ring_u32 + static_cast<uint32_t>(sb * b_tile_bytes));
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < kBK / 16; ++k) {
-              // advance 16 fp16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in (addr >> 4) units
-              if (kTwo)
-                umma_f16_2sm(d_tmem, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
-                             static_cast<uint32_t>((kb | k) != 0));
-              else
-                umma_f16(d_tmem, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
-                         static_cast<uint32_t>((kb | k) != 0));
+              for (int k = 0; k < kBK / 16; ++k) {
+                // advance 16 fp16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in (addr >> 4) units
+                const uint32_t accumulate = static_cast<uint32_t>((grp | t | k) != 0);
+                if (kTwo)
+                  umma_f16_2sm(d_tmem, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
+                               accumulate);
+                else
+                  umma_f16(d_tmem, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
+                           accumulate);
+              }
+              // free the weight slot (in both CTAs of a pair) once these MMAs have read it; after a group's last
+              // tap also the activation slot, after the tile's last tap signal the accumulator
+              if (kTwo) umma_commit_2sm(&empty_b[sb], 0x3);
+              else umma_commit(&empty_b[sb]);
+              if (t == nt - 1) {
+                if (kTwo) umma_commit_2sm(&empty_a[sa], 0x3);
+                else umma_commit(&empty_a[sa]);
+                if (grp == groups_total - 1) {
+                  if (kTwo) umma_commit_2sm(&tmem_full[acc], 0x3);
+                  else umma_commit(&tmem_full[acc]);
+                }
+              }
             }
-            // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
-            if (kTwo) umma_commit_2sm(&empty_bar[stage], 0x3);
-            else umma_commit(&empty_bar[stage]);
-            if (kb == kb_total - 1) {
-              // accumulator complete (signalled to both CTAs' epilogues in pair mode)
-              if (kTwo) umma_commit_2sm(&tmem_full[acc], 0x3);
-              else umma_commit(&tmem_full[acc]);
+            if (++sb == n_b) {
+              sb = 0;
+              pb ^= 1;
             }
           }
-          if (++stage == stages) {
-            stage = 0;
-            phase ^= 1;
+          if (++sa == n_a) {
+            sa = 0;
+            pa ^= 1;
           }
         }
         if (++acc == 2) {
@@ -411,6 +481,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                             ? (i_local * (p.bh >> 1) + (y_local >> 1)) * (p.bw >> 1) + (x_local >> 1)
                             : row;
     const uint32_t res_bytes = p.res_mode == GD_RES_UPSAMPLE2 ? kEpiTileBytes / 4 : kEpiTileBytes;
+    const uint64_t store_policy = l2_policy_evict_first();
     uint32_t res_phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -502,7 +573,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             mbar_arrive_expect_tx(rbar, res_bytes);
             tma_load_4d(sr, &map_res, rbar, col_base + ch + 2 * kEpiCols, rx0, ry0, n0);
           }
-          if (p.debug == 0) {
+          if (p.debug == 0 || p.debug == 3) {  // 3 = everything but the TMA store (timing experiments)
             float cs[16];  // [0,8): per-4-channel-chunk sums of this row, [8,16): sums of squares
             const bool has_res = p.res_mode != GD_RES_NONE;
             if (p.stats != nullptr) {
@@ -540,7 +611,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           }
           epi_barrier(group);  // (B) staging tile complete
           if (leader && p.debug == 0 && m_tile < p.m_tiles) {  // (an odd tile count leaves the last pair half empty)
-            tma_store_4d(&map_out, so, col_base + ch, x0, y0, n0);
+            tma_store_4d(&map_out, so, col_base + ch, x0, y0, n0, store_policy);
             bulk_commit();
           }
         }
@@ -622,6 +693,7 @@ int g_debug_epilogue = 0;
 int g_force_bn = 0;
 int g_disable_tma_epi = 0;
 int g_two_cta_mode = 1;
+int g_halo_mode = 1;
 
 }  // namespace
 
@@ -630,6 +702,7 @@ void conv_debug_set(int key, int value) {
   if (key == 1) g_force_bn = value;
   if (key == 2) g_disable_tma_epi = value;
   if (key == 3) g_two_cta_mode = value;
+  if (key == 4) g_halo_mode = value;
 }
 
 // N tile: the largest divisor of n_pad (multiple of 16, <= 256) that still yields enough tiles to fill the SMs;
@@ -729,11 +802,29 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
   // CTA-pair mode whenever there are at least two pixel tiles and half a weight tile is a whole number of 8-row
   // swizzle groups (bn % 16 == 0 always holds)
   const bool two_cta = g_two_cta_mode != 0 && m_tiles >= 2 && (bn / 2) % 8 == 0 && g_num_sms >= 2;
-  const int stage_bytes = kATileBytes + (two_cta ? bn / 2 : bn) * kBK * 2;
-  int stages = (kSmemBudget - kBarrierBytes - kBiasBytes - kEpiBytes - 1024) / stage_bytes;
-  if (stages > kMaxStages) stages = kMaxStages;
-  GD_REQUIRE(stages >= 2, "gd_conv_igemm: not enough shared memory for 2 stages");
-  p.stages = stages;
+  // halo mode: a 3x3 conv whose 128-pixel tile is BH whole rows x BW (multiple of 8) pixels of ONE image
+  const bool halo = g_halo_mode != 0 && d->taps == 9 && bi == 1 && bw % 8 == 0 && bw * bh == 128;
+  const int b_tile = (two_cta ? bn / 2 : bn) * kBK * 2;
+  const int a_slot = halo ? (bh + 2) * bw * kBK * 2 : kATileBytes;
+  const int ring_budget = kSmemBudget - kBarrierBytes - kBiasBytes - kEpiBytes - 1024;
+  int n_a, n_b;
+  if (halo) {
+    n_a = 3;
+    n_b = (ring_budget - n_a * a_slot) / b_tile;
+    if (n_b < 5) {
+      n_a = 2;
+      n_b = (ring_budget - n_a * a_slot) / b_tile;
+    }
+  } else {
+    n_a = n_b = ring_budget / (a_slot + b_tile);
+  }
+  if (n_a > kMaxA) n_a = kMaxA;
+  if (n_b > kMaxB) n_b = kMaxB;
+  GD_REQUIRE(n_a >= 2 && n_b >= 2, "gd_conv_igemm: not enough shared memory for the operand rings");
+  p.halo = halo ? 1 : 0;
+  p.a_slot_bytes = a_slot;
+  p.n_a = n_a;
+  p.n_b = n_b;
   p.kb0_per_tap = d->c0 / 64;
   p.taps = d->taps;
   p.kb0 = d->taps * p.kb0_per_tap;
@@ -759,7 +850,7 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
   p.stats_ld = d->n_pad / 4;
 
   CUtensorMap ma0, ma1, mb, mout, mres;
-  int rc = encode_act_map(&ma0, d->a0, d->c0, d->ld0, d->n, d->h, d->w, bi, bh, bw);
+  int rc = encode_act_map(&ma0, d->a0, d->c0, d->ld0, d->n, d->h, d->w, bi, halo ? bh + 2 : bh, bw);
   if (rc) return rc;
   if (d->a1) {
     rc = encode_act_map(&ma1, d->a1, c1, d->ld1, d->n, d->h, d->w, bi, bh, bw);
