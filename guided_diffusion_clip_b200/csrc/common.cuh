@@ -41,8 +41,19 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 
 // x * sigmoid(x) with the approximate-division intrinsic (2 ulp): the IEEE division's slow path costs a branch per
 // element in the bandwidth-bound GroupNorm kernels
-__device__ __forceinline__ float sigmoid_f(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
-__device__ __forceinline__ float silu_f(float v) { return v * sigmoid_f(v); }
+// One MUFU op per element: sigmoid(v) = 0.5 * tanh(v / 2) + 0.5 with tanh.approx.f32 (max rel. error 2^-11, the
+// same size as the fp16 rounding of the result).  The exp + reciprocal form costs two MUFU ops and made the fused
+// GroupNorm+SiLU kernels MUFU-bound instead of HBM-bound (profiles/gn_sweep_r01: bwd 64% -> with/without SiLU).
+__device__ __forceinline__ float tanh_approx(float v) {
+  float r;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ float sigmoid_f(float v) { return fmaf(0.5f, tanh_approx(0.5f * v), 0.5f); }
+__device__ __forceinline__ float silu_f(float v) {
+  const float h = 0.5f * v;
+  return fmaf(h, tanh_approx(h), h);
+}
 
 // ---- mbarrier --------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

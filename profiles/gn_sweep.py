@@ -29,7 +29,16 @@ def timeit(fn, reps=10):
     return ms[len(ms) // 2]
 
 
+BIG = [(64, 256, 256), (64, 256, 128), (64, 128, 256), (64, 64, 512)]  # bench batch: tensors far larger than L2
+SILU = 1
+
+
 def main():
+    global SHAPES, SILU
+    if "--big" in sys.argv:
+        SHAPES = BIG
+    if "--nosilu" in sys.argv:
+        SILU = 0
     lib = L.load()
     peak = 6447.0
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -54,12 +63,12 @@ def main():
         def f_apply():
             k[0] ^= 1
             L.check(lib.gd_groupnorm_apply(vp(xs[k[0]]), c, vp(stats), vp(gamma), vp(beta), vp(film), 2 * c, vp(y), c, n,
-                                           s, s, c, 1, L.GN_SAME, None, 0, st))
+                                           s, s, c, SILU, L.GN_SAME, None, 0, st))
 
         def f_bwd():
             k[0] ^= 1
             L.check(lib.gd_groupnorm_bwd(vp(xs[k[0]]), c, vp(stats), vp(gamma), vp(beta), vp(film), 2 * c, vp(dy), c, None,
-                                         0, 0, vp(y), c, vp(ws), n, s, s, c, 1, L.GN_SAME, st))
+                                         0, 0, vp(y), c, vp(ws), n, s, s, c, SILU, L.GN_SAME, st))
 
         f_stats()
         nbytes = n * s * s * c * 2

@@ -27,6 +27,21 @@ def describe(name, args):
         tag = f"conv {d.h}x{d.w} K={k} (C0={d.c0} taps={d.taps} C1={d.c1}) -> {d.cout} res={d.res_mode} out={d.out_mode}" \
               f"{' +stats' if d.stats_out else ''}"
         return tag, flops
+    def val(a):
+        return a.value if hasattr(a, "value") else a
+    if name == "gd_groupnorm_apply":
+        n, h, w, c, silu, mode = (val(a) for a in args[9:15])
+        aux = bool(val(args[15]))
+        out_px = {0: 1.0, 1: 0.25, 2: 4.0}.get(mode, 1.0)  # GD_GN_SAME / AVGPOOL2 / UPSAMPLE2
+        nbytes = n * h * w * c * 2.0 * (1.0 + out_px + (0.25 if aux else 0.0))
+        return f"gn_apply {h}x{w} C={c} mode={mode} silu={silu} film={bool(val(args[5]))} aux={aux}", -nbytes
+    if name == "gd_groupnorm_bwd":
+        n, h, w, c, silu, mode = (val(a) for a in args[15:21])
+        out_px = {0: 1.0, 1: 0.25, 2: 4.0}.get(mode, 1.0)
+        has_add = bool(val(args[9]))
+        # two passes read x and dy; second pass writes dx (+ reads add)
+        nbytes = n * h * w * c * 2.0 * (2.0 + 2.0 * out_px + 1.0 + (1.0 if has_add else 0.0))
+        return f"gn_bwd {h}x{w} C={c} mode={mode} add={has_add}", -nbytes
     return name, 0.0
 
 
@@ -88,6 +103,6 @@ if __name__ == "__main__":
             e[2] += fl
         print(f"== {phase}: {len(rows)} calls, {tot:.2f} ms (sum of isolated launches), batch {batch}")
         for tag, (cnt, ms, fl) in sorted(agg.items(), key=lambda kv: -kv[1][1])[: a.top]:
-            tf = f" {fl / ms / 1e9:7.0f} TF" if fl else ""
+            tf = f" {fl / ms / 1e9:7.0f} TF" if fl > 0 else (f" {-fl / ms / 1e6:7.0f} GB/s" if fl < 0 else "")
             print(f"  {ms:8.3f} ms {100 * ms / tot:5.1f}%  n={cnt:3d}{tf}  {tag}")
         print(json.dumps({"phase": phase, "total_ms": round(tot, 3)}))
