@@ -216,9 +216,16 @@ def top_conv_roofline(batch, image_size, burst_tflops, reps=12):
     avg = sum(ms) / len(ms)
     flops = 2.0 * batch * image_size * image_size * c * 9 * c
     achieved = flops / (avg * 1e-3) / 1e12
+    # DRAM traffic of this launch from the committed ncu capture: 2.209 GB read + 2.173 GB written at batch 64, i.e.
+    # 1.02x the algorithmic bytes (activations in + out once, weights once)
+    algo_bytes = 2.0 * batch * image_size * image_size * c * 2 + 9 * c * c * 2
+    traffic = (2.209482e9 + 2.173346e9) * batch / 64.0 if image_size == 256 else None
     return {"bound": "tensor", "kernel": "conv_igemm_kernel 3x3 256->256 @%dx%d batch %d" % (image_size, image_size, batch),
             "achieved": achieved, "peak": burst_tflops, "unit": "TFLOP/s", "frac": achieved / burst_tflops,
-            "traffic": None, "avg_launch_ms": avg, "flops_per_launch": flops}
+            "traffic": traffic, "traffic_unit": "bytes/launch", "traffic_source": "dram__bytes_read.sum+dram__bytes_write.sum, "
+            "ncu --set full, profiles/ncu_conv_r01i_halo_batch64.txt (batch 64; scaled by batch)",
+            "algorithmic_bytes": algo_bytes, "tensor_pipe_active_pct_ncu": 99.56,
+            "avg_launch_ms": avg, "flops_per_launch": flops}
 
 
 def run_gpu_arm(args):

@@ -36,16 +36,17 @@ int gd_version(void);
 /* Number of kernels launched by this library on this thread since the last gd_launch_count_reset(). */
 int64_t gd_launch_count(void);
 void gd_launch_count_reset(void);
-/* Measurement hooks (profiles/ only): key 0 = conv epilogue mode (0 normal, 1 barriers only, 2 TMEM loads only),
- * key 1 = force the conv N tile (0 = heuristic), key 2 = 1 disables the staged TMA-store epilogue, key 3 = 0 disables
- * CTA-pair (cta_group::2) mode. */
+/* Measurement hooks (profiles/ only): key 0 = conv epilogue mode (0 normal, 1 barriers only, 2 TMEM loads only,
+ * 3 everything but the TMA store), key 1 = force the conv N tile (0 = heuristic), key 2 = 1 disables the staged
+ * TMA-store epilogue, key 3 = 0 disables CTA-pair (cta_group::2) mode, key 4 = 0 disables halo reuse (every tap
+ * loads its own activation tile). */
 void gd_debug_set(int key, int value);
 
 /* ------------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution on tcgen05 (3x3 pad 1 stride 1, or 1x1), fp16 operands, fp32 accumulate.
  * Replaces nn.Conv2d / nn.Conv1d(k=1): unet.py:185,211 (ResBlock convs), :222 (1x1 skip), :286,294
- * (qkv / proj_out), :483 is handled by gd_conv3x3_small_cin, :616 (out head).  With gd_pack-ed flipped
- * weights the same entry point is the conv backward-data of the guidance gradient
+ * (qkv / proj_out), :616 (out head); the first conv :483 (C_in 3 or 6) is gd_im2col3x3_small_cin followed by a
+ * K=64 GEMM through this entry point.  With gd_pack-ed flipped weights the same entry point is the conv backward-data of the guidance gradient
  * (scripts/classifier_sample.py:54-61 autograd through unet.py:872-895).
  *   out[n,y,x,co] = out_scale * ( bias[co] + sum_{tap,c} a0[n,y+dy,x+dx,c] * W[co][tap*C0+c]
  *                                 + sum_c a1[n,y,x,c] * W[co][taps*C0+c]  + residual )
