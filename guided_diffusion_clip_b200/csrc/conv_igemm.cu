@@ -34,7 +34,7 @@ constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kATileBytes = kBM * kBK * 2;  // 16 KiB
 constexpr int kMaxA = 8;   // activation-ring slots (barrier array size)
-constexpr int kMaxB = 16;  // weight-ring slots
+constexpr int kMaxB = 32;  // weight-ring slots
 constexpr int kThreads = 320;  // warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 epilogue
 constexpr int kEpiThreads = 256;
 constexpr int kSmemBudget = 227 * 1024;
@@ -809,11 +809,21 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
   const int ring_budget = kSmemBudget - kBarrierBytes - kBiasBytes - kEpiBytes - 1024;
   int n_a, n_b;
   if (halo) {
-    n_a = 3;
-    n_b = (ring_budget - n_a * a_slot) / b_tile;
-    if (n_b < 5) {
-      n_a = 2;
-      n_b = (ring_budget - n_a * a_slot) / b_tile;
+    // every activation slot feeds 3 taps: pick the split that keeps the most taps in flight (narrow N tiles are
+    // latency-bound on the 20 KiB halo copies unless many of them are outstanding)
+    int best = -1;
+    n_a = 2;
+    n_b = 2;
+    for (int na = 2; na <= kMaxA; ++na) {
+      int nb = (ring_budget - na * a_slot) / b_tile;
+      if (nb > kMaxB) nb = kMaxB;
+      if (nb < 2) break;
+      const int in_flight = 3 * na < nb ? 3 * na : nb;
+      if (in_flight > best) {
+        best = in_flight;
+        n_a = na;
+        n_b = nb;
+      }
     }
   } else {
     n_a = n_b = ring_budget / (a_slot + b_tile);

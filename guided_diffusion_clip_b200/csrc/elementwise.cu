@@ -233,34 +233,49 @@ __global__ void embedding_gather_kernel(const float* __restrict__ table, const i
 // First conv (input_blocks.0.0, unet.py:483,741): C_in is 3 (or 6 for super-resolution), far too thin for a K block.
 // The fp32 NCHW input is expanded to an fp16 NHWC im2col tensor with 64 channels, k = (ky*3+kx)*cin + ci (zero padded),
 // and the conv then runs as a 1x1 problem with K = 64 on the tcgen05 kernel (engine.pack_conv_in packs the weights the
-// same way).  One thread per pixel writes one 128-byte row.
+// same way).
 // ---------------------------------------------------------------------------------------------
 __global__ void im2col3x3_small_cin_kernel(const float* __restrict__ x, __half* __restrict__ out, int ld_out, int n,
                                            int cin, int h, int w) {
-  const size_t hw = static_cast<size_t>(h) * w;
-  const size_t total = static_cast<size_t>(n) * hw;
-  for (size_t p = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; p < total;
-       p += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int img = static_cast<int>(p / hw);
-    const int rem = static_cast<int>(p - static_cast<size_t>(img) * hw);
-    const int y = rem / w, xx = rem - y * w;
-    __half vals[64];
+  // 8 threads per pixel, one 16-byte chunk (8 of the 64 K columns) each: a warp writes 4 whole 128-byte rows, so
+  // the stores are fully coalesced; the fp32 NCHW reads of neighbouring pixels hit L1.  The grid stride is a
+  // multiple of 8, so a thread keeps its chunk: the (tap, channel) decode of its 8 columns is hoisted out of the
+  // loop and the loop body is 32-bit index arithmetic only (the host bounds n*h*w*8 < 2^31).
+  const unsigned hw = static_cast<unsigned>(h) * static_cast<unsigned>(w);
+  const unsigned total = static_cast<unsigned>(n) * hw * 8u;
+  const unsigned tid0 = blockIdx.x * blockDim.x + threadIdx.x;
+  const int q = static_cast<int>(tid0 & 7u);
+  int dy[8], dx[8];
+  unsigned plane[8];  // channel plane offset of column j; dy = 2 marks a zero (padding) column
 #pragma unroll
-    for (int j = 0; j < 64; ++j) vals[j] = __float2half_rn(0.f);
-    for (int ky = 0; ky < 3; ++ky) {
-      const int yy = y + ky - 1;
-      if (yy < 0 || yy >= h) continue;
-      for (int kx = 0; kx < 3; ++kx) {
-        const int xc = xx + kx - 1;
-        if (xc < 0 || xc >= w) continue;
-        for (int ci = 0; ci < cin; ++ci)
-          vals[(ky * 3 + kx) * cin + ci] =
-              __float2half_rn(__ldg(x + (static_cast<size_t>(img) * cin + ci) * hw + static_cast<size_t>(yy) * w + xc));
-      }
+  for (int j = 0; j < 8; ++j) {
+    const int k = 8 * q + j;
+    if (k < 9 * cin) {
+      const int tap = k / cin, ci = k - tap * cin;
+      dy[j] = tap / 3 - 1;
+      dx[j] = tap - (tap / 3) * 3 - 1;
+      plane[j] = static_cast<unsigned>(ci) * hw;
+    } else {
+      dy[j] = 2;
+      dx[j] = 0;
+      plane[j] = 0;
     }
-    Half8* o = reinterpret_cast<Half8*>(out + p * ld_out);
+  }
+  for (unsigned i = tid0; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned p = i >> 3;
+    const unsigned img = p / hw;
+    const unsigned rem = p - img * hw;
+    const int y = static_cast<int>(rem / static_cast<unsigned>(w));
+    const int xx = static_cast<int>(rem) - y * w;
+    const float* xi = x + static_cast<size_t>(img) * cin * hw;
+    float f[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) o[q] = *reinterpret_cast<const Half8*>(&vals[8 * q]);
+    for (int j = 0; j < 8; ++j) {
+      const int yy = y + dy[j], xc = xx + dx[j];
+      const bool ok = dy[j] != 2 && yy >= 0 && yy < h && xc >= 0 && xc < w;
+      f[j] = ok ? __ldg(xi + plane[j] + static_cast<unsigned>(yy * w + xc)) : 0.f;
+    }
+    st_half8(out + static_cast<size_t>(p) * ld_out + 8 * q, float_to_half8(f));
   }
 }
 
@@ -433,7 +448,8 @@ extern "C" int gd_im2col3x3_small_cin(const float* x, void* out, int32_t ld_out,
   GD_REQUIRE(cin >= 1 && cin * 9 <= 64, "gd_im2col3x3_small_cin: cin*9 must fit one 64-wide K block, got cin=%d", cin);
   GD_REQUIRE(ld_out >= 64 && ld_out % 8 == 0, "gd_im2col3x3_small_cin: bad ld_out %d", ld_out);
   const size_t total = static_cast<size_t>(n) * h * w;
-  im2col3x3_small_cin_kernel<<<grid_for(total, 128, 148 * 32), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  GD_REQUIRE(total * 8 < (1ull << 31), "gd_im2col3x3_small_cin: n*h*w too large (%zu)", total);
+  im2col3x3_small_cin_kernel<<<grid_for(total * 8, 256, 148 * 32), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       x, reinterpret_cast<__half*>(out), ld_out, n, cin, h, w);
   GD_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
