@@ -39,6 +39,10 @@ CASES = [
     (1, 16, 16, 512, 128, 9),    # 72 K blocks -> smem ring wraps many times
     (8, 64, 64, 128, 128, 9),    # 256 tiles > 148 SMs: persistent loop + accumulator ping-pong
     (2, 4, 4, 64, 64, 9),        # 4x4 images: 8 images per tile
+    (1, 16, 32, 64, 64, 9),      # non-square, halo tiles: 2 patches across
+    (2, 32, 16, 128, 128, 9),    # non-square the other way; one patch across, 4 down
+    (1, 20, 24, 64, 64, 9),      # neither H nor W a multiple of the 16x8 patch: halo rows and columns run off the image
+    (1, 16, 16, 320, 64, 9),     # 5 channel blocks: the 3-slot activation ring wraps out of step with the weight ring
 ]
 
 

@@ -233,3 +233,46 @@ def test_clip_feat_model_matches_reference(lib, G):
     err = H.rel_err(out, th.from_numpy(G["feat_out"]).cuda())
     print(f"UNetModel_clip_feat vs reference golden: rel err {err:.3e}")
     assert err < TOL
+
+
+def test_full_size_guided_step_properties(lib):
+    """BASELINE configs[1] at FULL size (UNet-256 553.8 M params + classifier-256, random init): properties that do
+    not need the CPU oracle (a full-size CPU step takes minutes) —
+    * batch independence: sample 0 of a batch-2 step equals the same sample stepped alone, bit for bit (every
+      kernel's reduction order is per-sample), for the model output, the guidance gradient and x_{t-1};
+    * finiteness, a non-zero guidance gradient and the clamp of pred_xstart to [-1, 1]
+      (gaussian_diffusion.py:291-296)."""
+    import bench
+    from guided_diffusion_clip_b200.engine import UNetPlan
+    dev = th.device("cuda", 0)
+    model, diffusion = su.create_model_and_diffusion(**bench.unet_kwargs(256))
+    bench.randomize_(model, 1234)
+    model.to(dev).convert_to_fp16()
+    model.eval()
+    classifier = su.create_classifier(**bench.clf_kwargs(256))
+    bench.randomize_(classifier, 4321)
+    classifier.to(dev).convert_to_fp16()
+    classifier.eval()
+    g = th.Generator(device="cuda").manual_seed(5)
+    x2 = th.randn((2, 3, 256, 256), generator=g, device=dev)
+    y2 = th.tensor([3, 977], device=dev)
+    t2 = th.tensor([120, 120], device=dev)
+    cond = ClassifierGuidance(classifier, 1.0)
+    mf = ModelFn(model, True)
+
+    def step(x, t, y):
+        out = diffusion.p_sample(mf, x, t, cond_fn=cond, model_kwargs={"y": y})
+        eps = model(x, diffusion._scale_timesteps(t) if hasattr(diffusion, "_scale_timesteps") else t, y)
+        grad = cond(x, t, y=y)
+        return out["sample"], out["pred_xstart"], eps, grad
+
+    s2, x02, e2, g2 = step(x2, t2, y2)
+    s1, x01, e1, g1 = step(x2[:1].clone(), t2[:1], y2[:1])
+    th.cuda.synchronize()
+    for a in (s2, x02, e2, g2):
+        assert th.isfinite(a).all()
+    assert float(x02.abs().max()) <= 1.0
+    assert th.equal(e2[:1], e1), "model output depends on the batch it is computed in"
+    assert th.equal(g2[:1], g1), "guidance gradient depends on the batch it is computed in"
+    assert th.equal(x02[:1], x01)
+    assert float(g2.abs().max()) > 0.0
