@@ -276,3 +276,66 @@ def test_full_size_guided_step_properties(lib):
     assert th.equal(g2[:1], g1), "guidance gradient depends on the batch it is computed in"
     assert th.equal(x02[:1], x01)
     assert float(g2.abs().max()) > 0.0
+
+
+def test_full_size_upsampler_128_to_512_properties(lib):
+    """BASELINE configs[3] at FULL size: 128->512 SuperResModel (192 ch, attention at 32/16; unet.py:667-681 bilinear
+    low_res conditioning) — finite output of the right shape and batch independence, bit for bit."""
+    dev = th.device("cuda", 0)
+    kw = su.sr_model_and_diffusion_defaults()
+    kw.update(large_size=512, small_size=128, num_channels=192, num_res_blocks=2, attention_resolutions="32,16",
+              num_head_channels=64, class_cond=True, learn_sigma=True, resblock_updown=True, use_scale_shift_norm=True,
+              use_fp16=True, timestep_respacing="250")
+    model, diffusion = su.sr_create_model_and_diffusion(**kw)
+    import bench
+    bench.randomize_(model, 99)
+    model.to(dev).convert_to_fp16()
+    model.eval()
+    g = th.Generator(device="cuda").manual_seed(6)
+    x = th.randn((2, 3, 512, 512), generator=g, device=dev)
+    low = th.rand((2, 3, 128, 128), generator=g, device=dev) * 2 - 1
+    t = th.tensor([400, 400], device=dev)
+    y = th.tensor([1, 2], device=dev)
+    with th.no_grad():
+        o2 = model(x, t, low_res=low, y=y)
+        o1 = model(x[:1].clone(), t[:1], low_res=low[:1].clone(), y=y[:1])
+    th.cuda.synchronize()
+    assert o2.shape == (2, 6, 512, 512) and th.isfinite(o2).all() and float(o2.abs().max()) > 0
+    assert th.equal(o2[:1], o1)
+    out = diffusion.p_sample(model, x, th.tensor([100, 100], device=dev), model_kwargs={"low_res": low, "y": y})
+    assert th.isfinite(out["sample"]).all() and float(out["pred_xstart"].abs().max()) <= 1.0
+
+
+def test_full_size_512_classifier_guided_ddim_step(lib):
+    """BASELINE configs[4] at FULL size: 512x512 class-cond ADM (channel_mult 0.5,1,1,2,2,4,4, script_util.py:149-161)
+    with use_fp16=False master weights + classifier-512 guidance (scale 4.0), one DDIM-25 step: finite outputs,
+    non-zero guidance, batch independence of eps and of the guidance gradient."""
+    import bench
+    dev = th.device("cuda", 0)
+    kw = bench.unet_kwargs(512)
+    kw.update(use_fp16=False, timestep_respacing="ddim25")
+    model, diffusion = su.create_model_and_diffusion(**kw)
+    bench.randomize_(model, 7)
+    model.to(dev).eval()
+    ckw = bench.clf_kwargs(512)
+    ckw.update(classifier_use_fp16=False)
+    classifier = su.create_classifier(**ckw)
+    bench.randomize_(classifier, 8)
+    classifier.to(dev).eval()
+    cond = ClassifierGuidance(classifier, 4.0)
+    mf = ModelFn(model, True)
+    g = th.Generator(device="cuda").manual_seed(9)
+    x = th.randn((2, 3, 512, 512), generator=g, device=dev)
+    y = th.tensor([5, 6], device=dev)
+    t = th.tensor([12, 12], device=dev)
+    out = diffusion.ddim_sample(mf, x, t, cond_fn=cond, model_kwargs={"y": y})
+    g2 = cond(x, t, y=y)
+    g1 = cond(x[:1].clone(), t[:1], y=y[:1])
+    e2 = model(x, t, y)
+    e1 = model(x[:1].clone(), t[:1], y[:1])
+    th.cuda.synchronize()
+    # (condition_score re-derives pred_xstart from the guided eps WITHOUT clamping, gaussian_diffusion.py:383-392,
+    #  so only finiteness is asserted for it)
+    assert th.isfinite(out["sample"]).all() and th.isfinite(out["pred_xstart"]).all()
+    assert float(g2.abs().max()) > 0 and th.equal(g2[:1], g1)
+    assert e2.shape == (2, 6, 512, 512) and th.equal(e2[:1], e1)
