@@ -54,6 +54,7 @@ SIGNATURES = {
     "gd_launch_count": (i64, []),
     "gd_launch_count_reset": (None, []),
     "gd_debug_set": (None, [C.c_int, C.c_int]),
+    "gd_bw_probe": (C.c_int, [i32, i32, vp, vp, i64, vp]),
     "gd_conv_igemm": (C.c_int, [C.POINTER(ConvDesc), vp]),
     "gd_conv_stats_rows": (i64, [i32, i32, i32, C.POINTER(i32)]),
     "gd_groupnorm_finalize_partials": (C.c_int, [vp, i32, i32, vp, i32, i32, i32, i32, i32, f32, vp, vp]),

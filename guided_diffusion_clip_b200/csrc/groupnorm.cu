@@ -26,15 +26,18 @@ struct Geo {
   int px_per_chunk;
 };
 
-// CTAs per image: ~16 pixels per thread lane on big tensors, but never fewer CTAs than ~4 per SM in total (small
-// 8x8 / 16x16 layers are latency-bound otherwise) as long as every lane still gets >= 2 pixels.
+// CTAs per image: ~64 pixels per thread lane on big tensors (the per-CTA affine set-up is ~70 scalar instructions
+// and a dozen dependent loads; at 16 pixels per lane the sustained, power-capped bandwidth was 10-25 % lower:
+// profiles/gn_geo_probe.py), but never fewer CTAs than ~4 per SM in total (small 8x8 / 16x16 layers are
+// latency-bound otherwise) as long as every lane still gets >= 2 pixels.
+constexpr int kPxPerLane = 64;
 Geo make_geo(int c, int hw, int n, int max_chunks) {
   Geo g;
   g.c8 = c / 8;
   g.rep = 256 / g.c8;
   if (g.rep < 1) g.rep = 1;
   g.threads = g.c8 * g.rep;
-  int chunks = (hw + g.rep * 16 - 1) / (g.rep * 16);
+  int chunks = (hw + g.rep * kPxPerLane - 1) / (g.rep * kPxPerLane);
   const int want = (4 * 148 + n - 1) / n;
   if (chunks < want) chunks = want;
   const int max_by_work = hw / (g.rep * 2);

@@ -41,6 +41,9 @@ void gd_launch_count_reset(void);
  * TMA-store epilogue, key 3 = 0 disables CTA-pair (cta_group::2) mode, key 4 = 0 disables halo reuse (every tap
  * loads its own activation tile). */
 void gd_debug_set(int key, int value);
+/* Measurement hook (profiles/bw_probe.py): stream `bytes` from src to dst. structure 0 = one-shot flat grid, k>0 =
+ * persistent grid-stride with k CTAs per SM; math 0 = copy, 1 = fp16->fp32 FMA->fp16, 2 = + SiLU (GroupNorm's arithmetic). */
+int gd_bw_probe(int32_t structure, int32_t math, const void* src, void* dst, int64_t bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution on tcgen05 (3x3 pad 1 stride 1, or 1x1), fp16 operands, fp32 accumulate.
