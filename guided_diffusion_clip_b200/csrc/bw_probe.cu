@@ -48,6 +48,22 @@ __global__ void probe_stride_kernel(const __half* __restrict__ src, __half* __re
   for (; i < chunks; i += stride) st_half8(dst + i * 8, probe_math<kMath>(ld_half8_stream(src + i * 8)));
 }
 
+// GroupNorm-like: 256-thread CTA owns a contiguous region and walks it in `iters` rounds of 8 loads -> 8 stores per
+// thread (thread t of round r touches chunk base + (r*8 + u)*256 + t)
+template <int kMath>
+__global__ void probe_chunked_kernel(const __half* __restrict__ src, __half* __restrict__ dst, size_t chunks, int iters) {
+  const size_t base = static_cast<size_t>(blockIdx.x) * 256 * 8 * iters + threadIdx.x;
+  for (int r = 0; r < iters; ++r) {
+    const size_t b = base + static_cast<size_t>(r) * 8 * 256;
+    if (b + 7 * 256 >= chunks) return;
+    Half8 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = ld_half8_stream(src + (b + u * 256) * 8);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) st_half8(dst + (b + u * 256) * 8, probe_math<kMath>(v[u]));
+  }
+}
+
 }  // namespace
 }  // namespace gd
 
@@ -58,7 +74,13 @@ extern "C" int gd_bw_probe(int32_t structure, int32_t math, const void* src, voi
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const __half* s = reinterpret_cast<const __half*>(src);
   __half* d = reinterpret_cast<__half*>(dst);
-  if (structure == 0) {
+  if (structure < 0) {
+    const int iters = -structure;
+    const unsigned grid = static_cast<unsigned>((chunks + 256 * 8 * iters - 1) / (256 * 8 * iters));
+    if (math == 0) probe_chunked_kernel<0><<<grid, 256, 0, st>>>(s, d, chunks, iters);
+    else if (math == 1) probe_chunked_kernel<1><<<grid, 256, 0, st>>>(s, d, chunks, iters);
+    else probe_chunked_kernel<2><<<grid, 256, 0, st>>>(s, d, chunks, iters);
+  } else if (structure == 0) {
     const unsigned grid = static_cast<unsigned>((chunks + 511) / 512);
     if (math == 0) probe_flat_kernel<0><<<grid, 128, 0, st>>>(s, d, chunks);
     else if (math == 1) probe_flat_kernel<1><<<grid, 128, 0, st>>>(s, d, chunks);

@@ -41,7 +41,8 @@ void gd_launch_count_reset(void);
  * TMA-store epilogue, key 3 = 0 disables CTA-pair (cta_group::2) mode, key 4 = 0 disables halo reuse (every tap
  * loads its own activation tile). */
 void gd_debug_set(int key, int value);
-/* Measurement hook (profiles/bw_probe.py): stream `bytes` from src to dst. structure 0 = one-shot flat grid, k>0 =
+/* Measurement hook (profiles/bw_probe.py): stream `bytes` from src to dst. structure 0 = one-shot flat grid, -k = 256-thread
+ * CTAs owning a contiguous region walked in k rounds of 8 loads/stores per thread, k>0 =
  * persistent grid-stride with k CTAs per SM; math 0 = copy, 1 = fp16->fp32 FMA->fp16, 2 = + SiLU (GroupNorm's arithmetic). */
 int gd_bw_probe(int32_t structure, int32_t math, const void* src, void* dst, int64_t bytes, void* stream);
 

@@ -26,7 +26,7 @@ def run(structure, math, hot, reps=8):
     for _ in range(reps):
         e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
         e0.record()
-        if structure < 0:
+        if structure == -1000:
             y.copy_(x)
         else:
             L.check(lib.gd_bw_probe(structure, math, C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), N * 2, st))
@@ -37,9 +37,10 @@ def run(structure, math, hot, reps=8):
     return 2 * N * 2 / (ms[len(ms) // 2] * 1e-3) / 1e9
 
 
-for structure in (-1, 0, 3, 6, 8):
-    for math in ((0,) if structure < 0 else (0, 1, 2)):
-        row = {"structure": {-1: "torch copy_", 0: "flat one-shot"}.get(structure, f"grid-stride {structure} CTA/SM"),
+for structure in (-1000, 0, -1, -2, -8, -32, 3):
+    for math in ((0,) if structure == -1000 else (0, 2)):
+        row = {"structure": {-1000: "torch copy_", 0: "flat one-shot 128thr x4"}.get(
+                   structure, f"grid-stride {structure} CTA/SM" if structure > 0 else f"chunked 256thr, {-structure} rounds of 8"),
                "math": ["copy", "fma", "fma+silu"][math]}
         for hot in (False, True):
             row["hot_GBs" if hot else "idle_GBs"] = round(run(structure, math, hot))
