@@ -73,6 +73,7 @@ struct ConvArgs {
   int tma_epi;  // 1 = staged TMA-store epilogue
   float* stats;  // optional GroupNorm partials [m_tiles*4][stats_ld][2] (sum, sum of squares per 4-channel chunk)
   int stats_ld;  // n_pad / 4
+  int stats_per_tile;  // 1: one partial row per 128-pixel tile (tile inside one image); 4: one per 32-pixel quarter
   int debug;    // 0 = normal; 1 = epilogue skipped (barriers only); 2 = TMEM loads only (timing experiments)
 };
 
@@ -239,6 +240,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* res_bar = tmem_empty + 2;  // one per epilogue group
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(res_bar + 2);
+  float* s_stat = reinterpret_cast<float*>(smem + kBarrierBytes);  // [2 groups][4 quarters][16] parked GN partial sums
   uint8_t* a_ring = smem + kBarrierBytes + kBiasBytes;
   const int b_rows = kTwo ? (p.bn >> 1) : p.bn;  // weight rows this CTA stages per K block
   const int b_tile_bytes = b_rows * kBK * 2;     // multiple of 1024 (host checks b_rows % 8 == 0)
@@ -462,6 +464,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     // barrier: while one group waits (TMEM load, residual, TMA store read-out) the other computes.
     const int group = (warp - 2) >> 2;
     const bool leader = (threadIdx.x - 64 - group * 128) == 0;
+    const bool first_warp = ((warp - 2) & 3) == 0;  // the warp that holds the group's leader thread
     uint8_t* so = s_out + group * kEpiTileBytes;
     uint8_t* sr = s_res + group * kEpiTileBytes;
     uint64_t* rbar = &res_bar[group];
@@ -601,15 +604,30 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                 }
               }
               cs[0] += __shfl_xor_sync(0xffffffffu, cs[0], 1);
-              if (m_tile < p.m_tiles && (lane & 1) == 0) {
-                const int idx = lane >> 1;  // 0..7: chunk sums, 8..15: chunk sums of squares
-                float* sp = p.stats + (static_cast<size_t>(m_tile) * 4 + quarter) * p.stats_ld * 2;
-                sp[(((col_base + ch) >> 2) + (idx & 7)) * 2 + (idx >> 3)] = cs[0];
+              const int idx = lane >> 1;  // 0..7: chunk sums, 8..15: chunk sums of squares
+              if (p.stats_per_tile == 4) {
+                if (m_tile < p.m_tiles && (lane & 1) == 0) {
+                  float* sp = p.stats + (static_cast<size_t>(m_tile) * 4 + quarter) * p.stats_ld * 2;
+                  sp[(((col_base + ch) >> 2) + (idx & 7)) * 2 + (idx >> 3)] = cs[0];
+                }
+              } else if ((lane & 1) == 0) {
+                // the tile lies inside one image: park the quarter's sums, the group's first warp adds the four
+                // after the barrier below -> 4x fewer partial rows for gd_groupnorm_finalize_partials to read
+                s_stat[(group * 4 + quarter) * 16 + idx] = cs[0];
               }
             }
             fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
           }
           epi_barrier(group);  // (B) staging tile complete
+          if (p.stats != nullptr && p.stats_per_tile == 1 && p.debug == 0 && first_warp && lane < 16 &&
+              m_tile < p.m_tiles) {
+            // fixed summation order over the quarters -> bitwise reproducible; the next sub-tile's parked values are
+            // written only after this warp has passed the group's next barrier (A)
+            const float* q4 = s_stat + group * 64 + lane;
+            const float tot = (q4[0] + q4[16]) + (q4[32] + q4[48]);
+            float* sp = p.stats + static_cast<size_t>(m_tile) * p.stats_ld * 2;
+            sp[(((col_base + ch) >> 2) + (lane & 7)) * 2 + (lane >> 3)] = tot;
+          }
           if (leader && p.debug == 0 && m_tile < p.m_tiles) {  // (an odd tile count leaves the last pair half empty)
             tma_store_4d(&map_out, so, col_base + ch, x0, y0, n0, store_policy);
             bulk_commit();
@@ -858,6 +876,7 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
   GD_REQUIRE(!want_stats || p.tma_epi, "gd_conv_igemm: fused statistics need the staged epilogue (aligned fp16 output)");
   p.stats = d->stats_out;
   p.stats_ld = d->n_pad / 4;
+  p.stats_per_tile = bi == 1 ? 1 : 4;
 
   CUtensorMap ma0, ma1, mb, mout, mres;
   int rc = encode_act_map(&ma0, d->a0, d->c0, d->ld0, d->n, d->h, d->w, bi, halo ? bh + 2 : bh, bw);
@@ -929,6 +948,8 @@ extern "C" int64_t gd_conv_stats_rows(int32_t n, int32_t h, int32_t w, int32_t* 
   }
   const int tiles_per_group = ((w + bw - 1) / bw) * ((h + bh - 1) / bh);
   const int groups = (n + bi - 1) / bi;
-  if (rows_per_image) *rows_per_image = tiles_per_group * 4 / bi;
-  return static_cast<int64_t>(groups) * tiles_per_group * 4;
+  // a tile that lies inside one image (bi == 1) emits ONE partial row, otherwise one per 32-pixel quarter
+  const int per_tile = bi == 1 ? 1 : 4;
+  if (rows_per_image) *rows_per_image = tiles_per_group * per_tile / bi;
+  return static_cast<int64_t>(groups) * tiles_per_group * per_tile;
 }

@@ -524,6 +524,7 @@ gn_finalize_partials_kernel(const float* __restrict__ p0, int c0, int ld0, const
   const int cpg = (c0 + c1) / kGroups;
   const int ch_lo = g * cpg, ch_hi = ch_lo + cpg;
   double s = 0.0, ss = 0.0;
+#pragma unroll 4  // independent loads of 4 rows in flight (the kernel is pure latency)
   for (int r = tid; r < rows_per_image; r += 128) {
     const size_t row = static_cast<size_t>(n) * rows_per_image + r;
     for (int ch = ch_lo; ch < ch_hi; ch += 4) {

@@ -72,12 +72,13 @@ typedef struct gd_conv_desc {
   int32_t bn; /* N tile, 0 = auto */
   float out_scale; /* 0 is treated as 1 */
   /* Optional fused GroupNorm statistics of the stored output (consumed by gd_groupnorm_finalize_partials):
-   * fp32 [gd_conv_stats_rows(n,h,w)][n_pad/4][2] = per (32-pixel row block, 4-channel chunk) sum and sum of squares.
+   * fp32 [gd_conv_stats_rows(n,h,w)][n_pad/4][2] = per (row block, 4-channel chunk) sum and sum of squares; a row block
+   * is a 128-pixel tile when the tile lies inside one image, else a 32-pixel quarter of it.
    * Requires fp16 NHWC output, cout % 64 == 0 and h*w >= 32 per image; NULL = not produced. */
   float* stats_out;
 } gd_conv_desc;
 int gd_conv_igemm(const gd_conv_desc* desc, void* stream);
-/* Geometry of the fused statistics: number of 32-pixel row blocks the conv writes (rows of stats_out), and how many
+/* Geometry of the fused statistics: number of row blocks the conv writes (rows of stats_out), and how many
  * consecutive rows belong to one image (rows_per_image * n == rows).  Returns 0 rows if the geometry is ineligible. */
 int64_t gd_conv_stats_rows(int32_t n, int32_t h, int32_t w, int32_t* rows_per_image);
 /* mean / rstd of GroupNorm32 over a tensor whose channels come from one or two conv outputs (a skip concatenation,
