@@ -43,6 +43,8 @@ CASES = [
     (2, 32, 16, 128, 128, 9),    # non-square the other way; one patch across, 4 down
     (1, 20, 24, 64, 64, 9),      # neither H nor W a multiple of the 16x8 patch: halo rows and columns run off the image
     (1, 16, 16, 320, 64, 9),     # 5 channel blocks: the 3-slot activation ring wraps out of step with the weight ring
+    (2, 16, 8, 64, 128, 9),      # 8-pixel-wide images: halo tile 18 rows x 8 pixels, 1024-byte tap stride
+    (5, 32, 32, 64, 64, 9),      # odd tile count: the last CTA pair is half empty
 ]
 
 
