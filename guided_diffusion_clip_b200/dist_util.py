@@ -139,3 +139,36 @@ def save_npz(out_dir: str, arr: np.ndarray, label_arr: Optional[np.ndarray] = No
     else:
         np.savez(path, arr, label_arr)
     return path
+
+
+def load_data_for_worker(base_samples: str, batch_size: int, class_cond: bool, rank_: Optional[int] = None,
+                         world: Optional[int] = None):
+    """Low-resolution conditioning stream of the upsampler (scripts/super_res_sample.py:77-100).
+
+    Reads the base sampler's npz (`arr_0` uint8 NHWC, `arr_1` labels) and yields, forever, dicts with
+    `low_res` float32 NCHW in [-1, 1] (`uint8 / 127.5 - 1`) and, if class-conditional, `y` int64.  Rank r takes the
+    base samples r, r+W, r+2W, ... and starts over at r when the file is exhausted; a partially filled batch is
+    carried into the next pass (the reference never resets its buffer), so batch k of rank r is the same on every
+    run.  The tensors are CPU tensors, exactly as in the reference; move them with `.to(dist_util.dev())`."""
+    with np.load(base_samples) as obj:
+        image_arr = obj["arr_0"]
+        label_arr = obj["arr_1"] if class_cond else None
+    r = rank() if rank_ is None else rank_
+    w = world_size() if world is None else world
+    if len(image_arr) <= r:
+        raise ValueError(f"base_samples holds {len(image_arr)} images, none for rank {r} of {w}")
+    images: List[np.ndarray] = []
+    labels: List[np.ndarray] = []
+    while True:
+        for i in range(r, len(image_arr), w):
+            images.append(image_arr[i])
+            if class_cond:
+                labels.append(label_arr[i])
+            if len(images) < batch_size:
+                continue
+            batch = th.from_numpy(np.stack(images)).float() / 127.5 - 1.0
+            out = {"low_res": batch.permute(0, 3, 1, 2)}
+            if class_cond:
+                out["y"] = th.from_numpy(np.stack(labels))
+            yield out
+            images, labels = [], []

@@ -200,3 +200,30 @@ def test_product_never_imports_oracle():
                     src = f.read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
                 assert "/root/reference" not in src, fn
+
+
+def test_upsampler_low_res_stream_is_rank_strided(tmp_path):
+    """super_res_sample.py:77-100: rank r reads base samples r, r+W, ...; batches wrap around the file with the
+    partial batch carried over; low_res = uint8/127.5 - 1 in NCHW; labels follow the same order (bit-exact)."""
+    import itertools
+    from guided_diffusion_clip_b200 import dist_util
+    n = 7
+    rng = np.random.RandomState(3)
+    arr = rng.randint(0, 256, size=(n, 4, 4, 3)).astype(np.uint8)
+    lab = np.arange(100, 100 + n).astype(np.int64)
+    path = str(tmp_path / "base.npz")
+    np.savez(path, arr, lab)
+    for world, r, bs in ((2, 0, 3), (2, 1, 3), (3, 2, 2), (1, 0, 4)):
+        mine = list(range(r, n, world))
+        order = list(itertools.islice(itertools.cycle(mine), 4 * bs))
+        gen = dist_util.load_data_for_worker(path, bs, True, rank_=r, world=world)
+        for k in range(4):
+            b = next(gen)
+            idx = order[k * bs:(k + 1) * bs]
+            assert b["y"].dtype == th.int64 and b["y"].tolist() == lab[idx].tolist()
+            want = th.from_numpy(arr[idx]).float() / 127.5 - 1.0
+            assert b["low_res"].shape == (bs, 3, 4, 4) and th.equal(b["low_res"], want.permute(0, 3, 1, 2))
+    gen = dist_util.load_data_for_worker(path, 2, False, rank_=0, world=1)
+    assert set(next(gen).keys()) == {"low_res"}
+    with pytest.raises(ValueError):
+        next(dist_util.load_data_for_worker(path, 2, True, rank_=9, world=10))
