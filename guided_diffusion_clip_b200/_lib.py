@@ -66,6 +66,15 @@ SIGNATURES = {
                                    i32, i32, i32, vp]),
     "gd_attention_fwd": (C.c_int, [vp, i32, vp, i32, vp, i32, i32, i32, i32, vp]),
     "gd_attention_bwd": (C.c_int, [vp, i32, vp, i32, vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "gd_attention_fwd_masked": (C.c_int, [vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, vp]),
+    "gd_attention_bwd_masked": (C.c_int, [vp, i32, vp, i32, vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "gd_layernorm_fwd": (C.c_int, [vp, i32, vp, vp, f32, vp, i32, vp, i32, i32, vp]),
+    "gd_layernorm_bwd": (C.c_int, [vp, i32, vp, vp, vp, i32, vp, i32, vp, i32, i32, i32, vp]),
+    "gd_quickgelu_fwd": (C.c_int, [vp, i32, vp, i32, i32, i32, vp]),
+    "gd_quickgelu_bwd": (C.c_int, [vp, i32, vp, i32, vp, i32, i32, i32, vp]),
+    "gd_clip_preprocess_fwd": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
+    "gd_clip_preprocess_bwd": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, i32, i32, f32, vp]),
+    "gd_clip_head": (C.c_int, [vp, i32, vp, vp, i32, f32, f32, vp, vp, i32, i32, i32, i32, vp]),
     "gd_timestep_embedding": (C.c_int, [vp, vp, i32, i32, vp]),
     "gd_linear_f32": (C.c_int, [vp, i32, vp, vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, vp]),
     "gd_embedding_gather": (C.c_int, [vp, vp, vp, i32, i32, i32, vp]),

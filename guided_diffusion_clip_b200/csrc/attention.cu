@@ -92,7 +92,7 @@ __device__ __forceinline__ HeadPtrs head_ptrs(const __half* qkv_n, int head, int
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 attn_fwd_kernel(const __half* __restrict__ qkv, int ld_qkv, __half* __restrict__ out, int ld_out,
-                float* __restrict__ lse, int t, int heads, int order) {
+                float* __restrict__ lse, int t, int t_valid, int heads, int order) {
   __shared__ __align__(128) __half sQ[kBQ * kD];
   __shared__ __align__(128) __half sK[2][kBKV * kD];
   __shared__ __align__(128) __half sV[2][kBKV * kD];
@@ -106,7 +106,7 @@ attn_fwd_kernel(const __half* __restrict__ qkv, int ld_qkv, __half* __restrict__
   load_tile_async(sV[0], hp.v, ld_qkv, tid);
   cp_async_commit();
 
-  const int nkv = t / kBKV;
+  const int nkv = (t_valid + kBKV - 1) / kBKV;  // key blocks beyond the valid length are never touched
   // Q fragments (A operand) for the 4 k-steps, loaded once
   uint32_t qf[4][4];
   float o[8][4];
@@ -156,6 +156,13 @@ attn_fwd_kernel(const __half* __restrict__ qkv, int ld_qkv, __half* __restrict__
         mma16816(s[2 * jp], qf[kk], kf[0], kf[1]);
         mma16816(s[2 * jp + 1], qf[kk], kf[2], kf[3]);
       }
+    }
+    if ((kv + 1) * kBKV > t_valid) {  // padded keys (sequence padded to a multiple of 64): score -inf
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (kv * kBKV + j * 8 + (lane & 3) * 2 + (e & 1) >= t_valid) s[j][e] = -INFINITY;
     }
     // online softmax over this 64-key block; rows r0 = lane/4 and r0+8
     float mx[2] = {-INFINITY, -INFINITY};
@@ -273,7 +280,7 @@ __global__ void attn_delta_kernel(const __half* __restrict__ out, int ld_out, co
 __global__ void __launch_bounds__(128)
 attn_bwd_dkv_kernel(const __half* __restrict__ qkv, int ld_qkv, const __half* __restrict__ dout, int ld_dout,
                     const float* __restrict__ lse, const float* __restrict__ delta, __half* __restrict__ dqkv,
-                    int ld_dqkv, int t, int heads, int order) {
+                    int ld_dqkv, int t, int t_valid, int heads, int order) {
   // 32 KiB of tiles: buffer 1 of the Q/dO ring first stages this CTA's K and V (read once into registers).
   __shared__ __align__(128) __half sQ[2][kBQ * kD];
   __shared__ __align__(128) __half sdO[2][kBQ * kD];
@@ -361,8 +368,11 @@ attn_bwd_dkv_kernel(const __half* __restrict__ qkv, int ld_qkv, const __half* __
       const int q0 = j * 8 + (lane & 3) * 2;
       const float l0 = sLse[buf][q0], l1 = sLse[buf][q0 + 1];
       const float d0 = sDelta[buf][q0], d1 = sDelta[buf][q0 + 1];
-      const float p0 = __expf(st[j][0] * 0.125f - l0), p1 = __expf(st[j][1] * 0.125f - l1);
-      const float p2 = __expf(st[j][2] * 0.125f - l0), p3 = __expf(st[j][3] * 0.125f - l1);
+      // rows of S^T are keys: (lane >> 2) and +8 within this warp's 16; padded keys have probability 0
+      const int key0 = kb * kBKV + warp * 16 + (lane >> 2);
+      const bool v0 = key0 < t_valid, v1 = key0 + 8 < t_valid;
+      const float p0 = v0 ? __expf(st[j][0] * 0.125f - l0) : 0.f, p1 = v0 ? __expf(st[j][1] * 0.125f - l1) : 0.f;
+      const float p2 = v1 ? __expf(st[j][2] * 0.125f - l0) : 0.f, p3 = v1 ? __expf(st[j][3] * 0.125f - l1) : 0.f;
       st[j][0] = p0; st[j][1] = p1; st[j][2] = p2; st[j][3] = p3;
       dpt[j][0] = p0 * (dpt[j][0] - d0) * 0.125f;
       dpt[j][1] = p1 * (dpt[j][1] - d1) * 0.125f;
@@ -417,7 +427,7 @@ attn_bwd_dkv_kernel(const __half* __restrict__ qkv, int ld_qkv, const __half* __
 __global__ void __launch_bounds__(128)
 attn_bwd_dq_kernel(const __half* __restrict__ qkv, int ld_qkv, const __half* __restrict__ dout, int ld_dout,
                    const float* __restrict__ lse, const float* __restrict__ delta, __half* __restrict__ dqkv,
-                   int ld_dqkv, int t, int heads, int order) {
+                   int ld_dqkv, int t, int t_valid, int heads, int order) {
   __shared__ __align__(128) __half sQ[kBQ * kD];
   __shared__ __align__(128) __half sdO[kBQ * kD];
   __shared__ __align__(128) __half sK[2][kBKV * kD];
@@ -445,7 +455,7 @@ attn_bwd_dq_kernel(const __half* __restrict__ qkv, int ld_qkv, const __half* __r
   for (int j = 0; j < 8; ++j)
 #pragma unroll
     for (int e = 0; e < 4; ++e) dq[j][e] = 0.f;
-  const int nkv = t / kBKV;
+  const int nkv = (t_valid + kBKV - 1) / kBKV;
   for (int kv = 0; kv < nkv; ++kv) {
     const int buf = kv & 1;
     if (kv + 1 < nkv) {
@@ -490,8 +500,10 @@ attn_bwd_dq_kernel(const __half* __restrict__ qkv, int ld_qkv, const __half* __r
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float p0 = __expf(s[j][0] * 0.125f - lse0), p1 = __expf(s[j][1] * 0.125f - lse0);
-      const float p2 = __expf(s[j][2] * 0.125f - lse1), p3 = __expf(s[j][3] * 0.125f - lse1);
+      const int key = kv * kBKV + j * 8 + (lane & 3) * 2;  // columns are keys; padded keys have probability 0
+      const bool v0 = key < t_valid, v1 = key + 1 < t_valid;
+      const float p0 = v0 ? __expf(s[j][0] * 0.125f - lse0) : 0.f, p1 = v1 ? __expf(s[j][1] * 0.125f - lse0) : 0.f;
+      const float p2 = v0 ? __expf(s[j][2] * 0.125f - lse1) : 0.f, p3 = v1 ? __expf(s[j][3] * 0.125f - lse1) : 0.f;
       dp[j][0] = p0 * (dp[j][0] - del0) * 0.125f;
       dp[j][1] = p1 * (dp[j][1] - del0) * 0.125f;
       dp[j][2] = p2 * (dp[j][2] - del1) * 0.125f;
@@ -541,24 +553,31 @@ int check_attn(const char* who, int ld_qkv, int n, int t, int heads, int order) 
 
 using namespace gd;
 
-extern "C" int gd_attention_fwd(const void* qkv, int32_t ld_qkv, void* out, int32_t ld_out, float* lse, int32_t n,
-                                int32_t t, int32_t heads, int32_t order, void* stream) {
+extern "C" int gd_attention_fwd_masked(const void* qkv, int32_t ld_qkv, void* out, int32_t ld_out, float* lse, int32_t n,
+                                       int32_t t, int32_t t_valid, int32_t heads, int32_t order, void* stream) {
   GD_REQUIRE(qkv && out, "gd_attention_fwd: null pointer");
   if (int rc = check_attn("gd_attention_fwd", ld_qkv, n, t, heads, order)) return rc;
+  GD_REQUIRE(t_valid > 0 && t_valid <= t, "gd_attention_fwd: valid length %d outside (0, %d]", t_valid, t);
   GD_REQUIRE(ld_out >= heads * kD && ld_out % 2 == 0, "gd_attention_fwd: bad ld_out %d", ld_out);
   dim3 grid(t / kBQ, heads, n);
   attn_fwd_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __half*>(qkv), ld_qkv, reinterpret_cast<__half*>(out), ld_out, lse, t, heads, order);
+      reinterpret_cast<const __half*>(qkv), ld_qkv, reinterpret_cast<__half*>(out), ld_out, lse, t, t_valid, heads, order);
   GD_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
   return 0;
 }
 
-extern "C" int gd_attention_bwd(const void* qkv, int32_t ld_qkv, const void* out, int32_t ld_out, const void* dout,
-                                int32_t ld_dout, const float* lse, float* delta_ws, void* dqkv, int32_t ld_dqkv,
-                                int32_t n, int32_t t, int32_t heads, int32_t order, void* stream) {
+extern "C" int gd_attention_fwd(const void* qkv, int32_t ld_qkv, void* out, int32_t ld_out, float* lse, int32_t n,
+                                int32_t t, int32_t heads, int32_t order, void* stream) {
+  return gd_attention_fwd_masked(qkv, ld_qkv, out, ld_out, lse, n, t, t, heads, order, stream);
+}
+
+extern "C" int gd_attention_bwd_masked(const void* qkv, int32_t ld_qkv, const void* out, int32_t ld_out, const void* dout,
+                                       int32_t ld_dout, const float* lse, float* delta_ws, void* dqkv, int32_t ld_dqkv,
+                                       int32_t n, int32_t t, int32_t t_valid, int32_t heads, int32_t order, void* stream) {
   GD_REQUIRE(qkv && out && dout && lse && delta_ws && dqkv, "gd_attention_bwd: null pointer");
   if (int rc = check_attn("gd_attention_bwd", ld_qkv, n, t, heads, order)) return rc;
+  GD_REQUIRE(t_valid > 0 && t_valid <= t, "gd_attention_bwd: valid length %d outside (0, %d]", t_valid, t);
   GD_REQUIRE(ld_dqkv >= 3 * heads * kD && ld_dqkv % 8 == 0 && ld_dout % 8 == 0 && ld_out % 2 == 0,
              "gd_attention_bwd: bad strides");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -570,12 +589,19 @@ extern "C" int gd_attention_bwd(const void* qkv, int32_t ld_qkv, const void* out
   dim3 grid(t / 64, heads, n);
   attn_bwd_dkv_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const __half*>(qkv), ld_qkv,
                                             reinterpret_cast<const __half*>(dout), ld_dout, lse, delta_ws,
-                                            reinterpret_cast<__half*>(dqkv), ld_dqkv, t, heads, order);
+                                            reinterpret_cast<__half*>(dqkv), ld_dqkv, t, t_valid, heads, order);
   GD_CHECK_CUDA(cudaGetLastError());
   attn_bwd_dq_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const __half*>(qkv), ld_qkv,
                                            reinterpret_cast<const __half*>(dout), ld_dout, lse, delta_ws,
-                                           reinterpret_cast<__half*>(dqkv), ld_dqkv, t, heads, order);
+                                           reinterpret_cast<__half*>(dqkv), ld_dqkv, t, t_valid, heads, order);
   GD_CHECK_CUDA(cudaGetLastError());
   count_launch(3);
   return 0;
+}
+
+extern "C" int gd_attention_bwd(const void* qkv, int32_t ld_qkv, const void* out, int32_t ld_out, const void* dout,
+                                int32_t ld_dout, const float* lse, float* delta_ws, void* dqkv, int32_t ld_dqkv,
+                                int32_t n, int32_t t, int32_t heads, int32_t order, void* stream) {
+  return gd_attention_bwd_masked(qkv, ld_qkv, out, ld_out, dout, ld_dout, lse, delta_ws, dqkv, ld_dqkv, n, t, t, heads,
+                                 order, stream);
 }

@@ -128,6 +128,45 @@ int gd_attention_bwd(const void* qkv, int32_t ld_qkv, const void* out, int32_t l
                      int32_t ld_dout, const float* lse, float* delta_ws, void* dqkv, int32_t ld_dqkv, int32_t n,
                      int32_t t, int32_t heads, int32_t order, void* stream);
 
+/* Same kernels for a sequence padded to t (multiple of 64) of which only the first t_valid tokens exist (ViT: 197 of
+ * 256): keys >= t_valid get probability 0 in the forward and in both gradient kernels; padded query rows are computed
+ * like any other row and are ignored by the caller. */
+int gd_attention_fwd_masked(const void* qkv, int32_t ld_qkv, void* out, int32_t ld_out, float* lse, int32_t n, int32_t t,
+                            int32_t t_valid, int32_t heads, int32_t order, void* stream);
+int gd_attention_bwd_masked(const void* qkv, int32_t ld_qkv, const void* out, int32_t ld_out, const void* dout,
+                            int32_t ld_dout, const float* lse, float* delta_ws, void* dqkv, int32_t ld_dqkv, int32_t n,
+                            int32_t t, int32_t t_valid, int32_t heads, int32_t order, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * CLIP ViT image-encoder guidance (BASELINE configs[2]; SURVEY §8c spec — the reference repository has no CLIP code,
+ * the architecture is openai/CLIP's as implemented by transformers.CLIPVisionModelWithProjection, quick_gelu).
+ * Token tensors: fp16 [rows][c] with a row stride ld (rows = n * t_pad).  GEMMs of the encoder go through
+ * gd_conv_igemm (taps = 1), attention through gd_attention_*_masked.
+ * ---------------------------------------------------------------------------------------------- */
+/* LayerNorm over c (<= 2048, multiple of 8) per row, eps as given (CLIP: 1e-5); mean_rstd [rows][2] optional. */
+int gd_layernorm_fwd(const void* x, int32_t ld, const float* gamma, const float* beta, float eps, void* out,
+                     int32_t ld_out, float* mean_rstd, int32_t rows, int32_t c, void* stream);
+/* dx = dLN/dx^T dy (+ add): add is an optional fp16 tensor of dx's shape (the residual branch's gradient). */
+int gd_layernorm_bwd(const void* x, int32_t ld, const float* mean_rstd, const float* gamma, const void* dy, int32_t ld_dy,
+                     const void* add, int32_t ld_add, void* dx, int32_t ld_dx, int32_t rows, int32_t c, void* stream);
+/* QuickGELU x * sigmoid(1.702 x) and its derivative applied to dy. */
+int gd_quickgelu_fwd(const void* x, int32_t ld, void* out, int32_t ld_out, int32_t rows, int32_t c, void* stream);
+int gd_quickgelu_bwd(const void* x, int32_t ld, const void* dy, int32_t ld_dy, void* dx, int32_t ld_dx, int32_t rows,
+                     int32_t c, void* stream);
+/* x fp32 NCHW [n,3,hin,win] in [-1,1] -> (x+1)/2 -> bilinear resize to size x size (align_corners=False) -> CLIP
+ * mean/std -> patches fp16 [n][t_pad][3*patch*patch] (row stride ld): token 1 + py*g + px, k = c*P*P + dy*P + dx;
+ * token 0 (class slot) and tokens > g*g are written as zeros.  _bwd is the exact transpose, times out_scale. */
+int gd_clip_preprocess_fwd(const float* x, void* patches, int32_t ld, int32_t n, int32_t hin, int32_t win, int32_t size,
+                           int32_t patch, int32_t t_pad, void* stream);
+int gd_clip_preprocess_bwd(const void* dpatches, int32_t ld, float* dx, int32_t n, int32_t hin, int32_t win, int32_t size,
+                           int32_t patch, int32_t t_pad, float out_scale, void* stream);
+/* Similarity head on the post-LayerNorm class token f (fp16 rows, stride ld_f): e = Wp f (Wp fp32 [p][h]),
+ * sim[n] = scale * <e/|e|, text_n> (text fp32, row stride text_stride; 0 = one shared row), and
+ * df = grad_scale * d sim / d f (fp16 rows, stride ld_df).  sim or df may be NULL. */
+int gd_clip_head(const void* f, int32_t ld_f, const float* wproj, const float* text, int32_t text_stride, float scale,
+                 float grad_scale, float* sim, void* df, int32_t ld_df, int32_t n, int32_t h, int32_t p, void* stream);
+
+
 /* ------------------------------------------------------------------------------------------------
  * Small fp32 pieces.
  * ---------------------------------------------------------------------------------------------- */

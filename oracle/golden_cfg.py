@@ -176,3 +176,40 @@ def feat_inputs():
     x = th.randn(2, 3, IMAGE, IMAGE, generator=g)
     feat = th.randn(2, 1, 512, generator=g)
     return x, th.tensor([10, 720]), feat / feat.norm(dim=-1, keepdim=True)
+
+
+# ---- §8f row 2: CLIP ViT image-encoder guidance (spec: SURVEY §8c; stand-in reference: transformers CLIP) ----------
+CLIP_SEED = 31
+CLIP_TINY = dict(hidden_size=128, intermediate_size=512, num_hidden_layers=2, num_attention_heads=2, image_size=64,
+                 patch_size=16, projection_dim=64)
+CLIP_INPUT = 80          # sampler resolution fed to the guidance: 80 -> 64 exercises the bilinear resize (scale 1.25)
+CLIP_SCALE = 10.0
+
+
+def clip_state_dict(shapes):
+    """Seeded weights in the transformers key layout: LayerNorm weights around 1, biases / class token small,
+    matrices ~ N(0, 1/fan_in), positions ~ N(0, 0.02)."""
+    g = th.Generator().manual_seed(CLIP_SEED)
+    sd = {}
+    for name, shape in shapes.items():
+        shape = tuple(shape)
+        if "norm" in name and name.endswith("weight"):
+            v = 1.0 + 0.1 * th.randn(shape, generator=g)
+        elif name.endswith("position_embedding.weight"):
+            v = 0.02 * th.randn(shape, generator=g)
+        elif len(shape) == 1:
+            v = 0.1 * th.randn(shape, generator=g)
+        else:
+            fan_in = 1
+            for s in shape[1:]:
+                fan_in *= s
+            v = th.randn(shape, generator=g) / fan_in ** 0.5
+        sd[name] = v
+    return sd
+
+
+def clip_inputs():
+    g = th.Generator().manual_seed(INPUT_SEED + 3)
+    x = th.randn(2, 3, CLIP_INPUT, CLIP_INPUT, generator=g).clamp(-1, 1)
+    txt = th.randn(2, CLIP_TINY["projection_dim"], generator=g)
+    return x, txt / txt.norm(dim=-1, keepdim=True)
