@@ -170,3 +170,47 @@ def test_clip_vit_b16_full_size_runs(lib):
     g1 = cond(x[:1].clone(), None)
     assert th.isfinite(g4).all() and float(g4.abs().max()) > 0
     assert H.rel_err(g4[:1], g1) < 1e-3
+
+
+def test_clip_guided_ddim_steps_match_oracle(lib, enc):
+    """BASELINE configs[2] in miniature: unconditional ADM + CLIP guidance, the first 5 steps of a DDIM-50 chain
+    through the public ddim_sample_loop_progressive API against the CPU oracle (UNet oracle pinned to the reference,
+    CLIP oracle pinned to transformers, tables pinned bit-exact)."""
+    from guided_diffusion_clip_b200 import script_util as su
+    from oracle import oracle_diffusion as od
+    from oracle import oracle_models as om
+    m, clip_sd = enc
+    kw = dict(cfg.UNET_KW, class_cond=False)
+    unet = su.create_model(**kw)
+    usd = om.make_state_dict({k: tuple(v.shape) for k, v in unet.state_dict().items()}, cfg.UNET_SEED + 100)
+    unet.load_state_dict(usd, strict=True)
+    unet.cuda().eval()
+    diffusion = su.create_gaussian_diffusion(steps=1000, learn_sigma=True, noise_schedule="linear",
+                                             timestep_respacing="ddim50")
+    _, txt = cfg.clip_inputs()
+    scale = 20.0 * cfg.CLIP_SCALE
+    g = th.Generator().manual_seed(77)
+    init = th.randn(2, 3, cfg.IMAGE, cfg.IMAGE, generator=g)
+    steps = 5
+    cond = gclip.CLIPGuidance(m, txt.cuda(), scale)
+    gen = diffusion.ddim_sample_loop_progressive(unet, init.shape, noise=init.cuda(), cond_fn=cond, model_kwargs={},
+                                                 device="cuda", eta=0.0)
+    got = None
+    for k, o in enumerate(gen):
+        got = o
+        if k + 1 == steps:
+            break
+    tab = od.Tables(schedule="linear", steps=1000, respacing="ddim50", learn_sigma=True)
+    ckw = dict(heads=cfg.CLIP_TINY["num_attention_heads"], layers=cfg.CLIP_TINY["num_hidden_layers"],
+               patch=cfg.CLIP_TINY["patch_size"], image_size=cfg.CLIP_TINY["image_size"])
+    img = init.clone()
+    with th.no_grad():
+        for i in list(reversed(range(tab.T)))[:steps]:
+            tt = th.full((2,), tab.timestep_map[i])
+            mo = om.unet_forward(usd, img, tt, None, **cfg.UNET_STRUCT)
+            gr = oc.guidance(clip_sd, img, txt, scale, **ckw)
+            r = tab.ddim_sample(mo, img, i, th.zeros_like(img), gr, eta=0.0)
+            img = r["sample"]
+    err = H.rel_err(got["sample"].cpu(), img)
+    print(f"CLIP-guided DDIM, {steps} steps: rel err {err:.3e}")
+    assert err < TOL
