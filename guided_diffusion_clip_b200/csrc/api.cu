@@ -17,9 +17,13 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches += n; }
 void conv_debug_set(int key, int value);
+void attn_debug_set(int value);
 }  // namespace gd
 
-extern "C" void gd_debug_set(int key, int value) { gd::conv_debug_set(key, value); }
+extern "C" void gd_debug_set(int key, int value) {
+  if (key == 5) gd::attn_debug_set(value);
+  else gd::conv_debug_set(key, value);
+}
 
 extern "C" const char* gd_last_error(void) { return gd::g_err; }
 extern "C" int gd_version(void) { return GD_B200_ABI_VERSION; }

@@ -14,6 +14,10 @@
 
 namespace gd {
 void count_launch(int n = 1);
+// attention_tc.cu: tcgen05 / TMEM / TMA forward for sequence lengths that are a multiple of 128
+bool attn_fwd_tc_applicable(const void* qkv, int ld_qkv, const void* out, int ld_out, int t);
+int attn_fwd_tc_launch(const void* qkv, int ld_qkv, void* out, int ld_out, float* lse, int n, int t, int t_valid,
+                       int heads, int order, cudaStream_t stream);
 namespace {
 
 constexpr int kD = 64;
@@ -559,7 +563,10 @@ extern "C" int gd_attention_fwd_masked(const void* qkv, int32_t ld_qkv, void* ou
   if (int rc = check_attn("gd_attention_fwd", ld_qkv, n, t, heads, order)) return rc;
   GD_REQUIRE(t_valid > 0 && t_valid <= t, "gd_attention_fwd: valid length %d outside (0, %d]", t_valid, t);
   GD_REQUIRE(ld_out >= heads * kD && ld_out % 2 == 0, "gd_attention_fwd: bad ld_out %d", ld_out);
-  dim3 grid(t / kBQ, heads, n);
+  if (attn_fwd_tc_applicable(qkv, ld_qkv, out, ld_out, t))
+    return attn_fwd_tc_launch(qkv, ld_qkv, out, ld_out, lse, n, t, t_valid, heads, order,
+                              reinterpret_cast<cudaStream_t>(stream));
+  dim3 grid(t / kBQ, heads, n);  // 64-token sequences (8x8 resolution): warp-level mma.sync kernel
   attn_fwd_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __half*>(qkv), ld_qkv, reinterpret_cast<__half*>(out), ld_out, lse, t, t_valid, heads, order);
   GD_CHECK_CUDA(cudaGetLastError());

@@ -258,3 +258,44 @@ def test_attention_pool_head(lib):
     err = H.rel_err(dh.permute(0, 3, 1, 2), hmap.grad)
     print(f"attnpool bwd rel err {err:.3e}")
     assert err < 3e-3
+
+
+@pytest.mark.parametrize("t,t_valid", [(128, 128), (256, 129), (256, 197), (256, 255), (384, 300), (1024, 1024)])
+@pytest.mark.parametrize("new_order", [False, True])
+def test_attention_tcgen05_forward_matches_fp32_and_mma_sync(lib, t, t_valid, new_order):
+    """The tcgen05 / TMEM forward (sequence lengths that are multiples of 128) against a plain fp32 softmax(QK^T/8)V of
+    the valid tokens, and against the warp-level mma.sync kernel of the same ABI call (gd_debug_set key 5 = 0), for both
+    qkv channel orders, full and masked key ranges, with qkv / out rows strided inside wider buffers."""
+    g = th.Generator().manual_seed(100 + t + t_valid)
+    n, heads = 3, 3
+    c = heads * 64
+    ld_qkv, ld_out = 3 * c + 64, c + 8
+    qkv = (th.randn(n, t, ld_qkv, generator=g) * 1.5).cuda().half()
+    order = L.QKV_NEW if new_order else L.QKV_LEGACY
+    outs, lses = [], []
+    for enable in (1, 0):
+        lib.gd_debug_set(5, enable)
+        out = th.zeros(n, t, ld_out, device="cuda", dtype=th.float16)
+        lse = th.zeros(n, heads, t, device="cuda")
+        try:
+            L.check(lib.gd_attention_fwd_masked(H.vp(qkv), ld_qkv, H.vp(out), ld_out, H.vp(lse), n, t, t_valid, heads, order,
+                                                H.stream()))
+            th.cuda.synchronize()
+        finally:
+            lib.gd_debug_set(5, 1)
+        outs.append(out)
+        lses.append(lse)
+    x = qkv.float()[:, :t_valid, :3 * c]
+    if new_order:
+        q, k, v = (z.reshape(n, t_valid, heads, 64).transpose(1, 2) for z in x.chunk(3, dim=-1))
+    else:
+        q, k, v = (z.squeeze(3).transpose(1, 2) for z in x.reshape(n, t_valid, heads, 3, 64).split(1, dim=3))
+    s = q @ k.transpose(-1, -2) / 8.0
+    ref = (th.softmax(s, dim=-1) @ v).transpose(1, 2).reshape(n, t_valid, c)
+    ref_lse = th.logsumexp(s, dim=-1)
+    e_tc = H.rel_err(outs[0][:, :t_valid, :c], ref)
+    e_mma = H.rel_err(outs[1][:, :t_valid, :c], ref)
+    print(f"attn tc t={t} valid={t_valid} new={new_order}: rel err tcgen05 {e_tc:.3e}, mma.sync {e_mma:.3e}")
+    assert e_tc < 3e-3 and e_mma < 3e-3
+    assert float((lses[0][:, :, :t_valid] - ref_lse).abs().max()) < 2e-3
+    assert float(outs[0][:, :, c:].abs().max()) == 0.0  # nothing written outside the head columns
