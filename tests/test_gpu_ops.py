@@ -270,7 +270,11 @@ def test_attention_tcgen05_forward_matches_fp32_and_mma_sync(lib, t, t_valid, ne
     n, heads = 3, 3
     c = heads * 64
     ld_qkv, ld_out = 3 * c + 64, c + 8
-    qkv = (th.randn(n, t, ld_qkv, generator=g) * 1.5).cuda().half()
+    qkv = th.randn(n, t, ld_qkv, generator=g) * 1.5
+    # later key tiles get larger and larger keys, so the running row maximum jumps by far more than the kernel's
+    # lazy-rescale threshold (2^8) from tile to tile and the TMEM rescale of the output accumulator is exercised
+    qkv[:, :, :3 * c] *= (1.0 + 2.0 * (th.arange(t) // 128).float() * (th.arange(t) % 3 == 0).float())[None, :, None]
+    qkv = qkv.cuda().half()
     order = L.QKV_NEW if new_order else L.QKV_LEGACY
     outs, lses = [], []
     for enable in (1, 0):
