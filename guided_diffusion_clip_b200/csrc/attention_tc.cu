@@ -315,10 +315,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __half* __restri
       l_run += ((rs[0][0] + rs[0][1]) + (rs[1][0] + rs[1][1])) + ((rs[2][0] + rs[2][1]) + (rs[3][0] + rs[3][1]));
       tc_fence_before();
       fence_proxy_async_smem();
-      mbar_arrive(p_full);
-      // consume PV_{j-1}'s completion (issued a whole step ago: no stall), so that every phase of o_full is observed
-      // in order and P buffer (j+1) & 1 is known to be free at the next step
+      // Observe PV_{j-1}'s completion (issued a whole step ago: no stall) BEFORE releasing P_j: once p_full is
+      // complete PV_j may finish too, and a parity wait that is two phases behind would never return.  It also tells
+      // the next step that P buffer (j+1) & 1 is free.
       if (j > 0) mbar_wait(o_full, static_cast<uint32_t>((j - 1) & 1));
+      mbar_arrive(p_full);
     }
     // all key tiles accumulated
     mbar_wait(o_full, static_cast<uint32_t>((nkv - 1) & 1));
