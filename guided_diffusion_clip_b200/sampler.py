@@ -98,15 +98,27 @@ class GraphedStepper:
     def __init__(self, diffusion, model, cond_fn, shape, device, y, uses_y, clip_denoised, ddim, eta):
         n, c, h, w = shape
         self.diffusion = diffusion
-        from .engine import UNetPlan, norm_device
+        from .engine import ClassifierPlan, UNetPlan, norm_device
         device = norm_device(device)
-        self.unet = model._plan_for(("unet", n, h, w, str(device)), lambda: UNetPlan(model, n, h, w, device))
-        self.clf = None
-        self.scale = 0.0
-        if cond_fn is not None:
-            self.clf = cond_fn.classifier.plan(n, h, w, th.device(device))
-            self.scale = cond_fn.classifier_scale
         dev = th.device(device)
+        # Samples are independent, so the batch can be cut into `split` contiguous parts that run as independent
+        # branches of the step graph: one part's bandwidth-bound GroupNorm passes then overlap another part's
+        # tensor-bound convolutions (GD_B200_SPLIT; 1 = one part).
+        split = max(1, int(os.environ.get("GD_B200_SPLIT", "1")))
+        if n % split != 0:
+            split = 1
+        m = n // split
+        self.scale = cond_fn.classifier_scale if cond_fn is not None else 0.0
+        self.parts = []
+        for i in range(split):
+            tag = () if i == 0 else (i,)
+            unet = model._plan_for(("unet", m, h, w, str(device)) + tag, lambda: UNetPlan(model, m, h, w, device))
+            clf = None
+            if cond_fn is not None:
+                cm = cond_fn.classifier
+                clf = cm._plan_for(("clf", m, h, w, str(device)) + tag, lambda: ClassifierPlan(cm, m, h, w, device))
+            self.parts.append((slice(i * m, (i + 1) * m), unet, clf, th.cuda.Stream(device=dev), th.cuda.Stream(device=dev)))
+        self.unet, self.clf = self.parts[0][1], self.parts[0][2]
         self.t_idx = th.zeros((n,), dtype=th.int64, device=dev)
         self.noise = th.empty(shape, dtype=th.float32, device=dev)
         self.sample = th.empty(shape, dtype=th.float32, device=dev)
@@ -114,47 +126,60 @@ class GraphedStepper:
         self.y = y.to(device=dev, dtype=th.int64).contiguous().clone() if isinstance(y, th.Tensor) else None
         self.uses_y = uses_y
         if uses_y:
-            self.unet.cond_in.copy_(self.y)
+            for sl, unet, _, _, _ in self.parts:
+                unet.cond_in.copy_(self.y[sl])
         self.map = diffusion.map_tensor(dev) if hasattr(diffusion, "map_tensor") else None
         self.rescale = (1000.0 / diffusion.original_num_steps if (self.map is not None and diffusion.rescale_timesteps)
                         else (1000.0 / diffusion.num_timesteps if diffusion.rescale_timesteps else None))
         self.clip, self.ddim, self.eta = clip_denoised, ddim, eta
         self.graph: Optional[th.cuda.CUDAGraph] = None
         self.overlap = os.environ.get("GD_B200_NO_OVERLAP", "0") != "1"
-        self._fork = th.cuda.Stream(device=dev)
         self._capture()
 
-    def _body(self) -> None:
+    def _part(self, ts, sl, unet, clf, fork) -> None:
+        """One part of the batch on the current stream (+ its classifier on `fork`)."""
         d = self.diffusion
-        ts = self.map[self.t_idx] if self.map is not None else self.t_idx
-        ts = ts.float() * self.rescale if self.rescale is not None else ts
-        self.unet.t_in.copy_(ts)
+        unet.t_in.copy_(ts[sl])
+        y = self.y[sl] if self.y is not None else None
         grad = None
-        if self.clf is not None and self.overlap:
+        if clf is not None and self.overlap:
             # The classifier (fwd + bwd) and the UNet both depend only on (x_t, t): fork the classifier onto a
             # second stream so its bandwidth-bound GroupNorm passes fill in beside the UNet's tensor-bound convs
             # (and vice versa); join before the posterior kernel.  Captured as two branches of the step graph.
-            main = th.cuda.current_stream()
-            self._fork.wait_stream(main)
-            with th.cuda.stream(self._fork):
-                self.clf.x_in.copy_(self.unet.x_in)
-                self.clf.t_in.copy_(self.unet.t_in)
-                grad = self.clf.guidance(self.clf.x_in, self.clf.t_in, self.y, self.scale)
-            self.unet.prog.run()
-            main.wait_stream(self._fork)
+            cur = th.cuda.current_stream()
+            fork.wait_stream(cur)
+            with th.cuda.stream(fork):
+                clf.x_in.copy_(unet.x_in)
+                clf.t_in.copy_(unet.t_in)
+                grad = clf.guidance(clf.x_in, clf.t_in, y, self.scale)
+            unet.prog.run()
+            cur.wait_stream(fork)
         else:
-            self.unet.prog.run()
-            if self.clf is not None:
-                self.clf.x_in.copy_(self.unet.x_in)
-                self.clf.t_in.copy_(ts)
-                grad = self.clf.guidance(self.clf.x_in, self.clf.t_in, self.y, self.scale)
-        d._launch_posterior(x=self.unet.x_in, t=self.t_idx, model_out=self.unet.out, grad=grad, noise=self.noise,
-                            sample=self.sample, pred_xstart=self.x0, clip_denoised=self.clip, ddim=self.ddim,
+            unet.prog.run()
+            if clf is not None:
+                clf.x_in.copy_(unet.x_in)
+                clf.t_in.copy_(unet.t_in)
+                grad = clf.guidance(clf.x_in, clf.t_in, y, self.scale)
+        d._launch_posterior(x=unet.x_in, t=self.t_idx[sl], model_out=unet.out, grad=grad, noise=self.noise[sl],
+                            sample=self.sample[sl], pred_xstart=self.x0[sl], clip_denoised=self.clip, ddim=self.ddim,
                             eta=self.eta)
+
+    def _body(self) -> None:
+        ts = self.map[self.t_idx] if self.map is not None else self.t_idx
+        ts = ts.float() * self.rescale if self.rescale is not None else ts
+        main = th.cuda.current_stream()
+        for _, _, _, side, _ in self.parts[1:]:
+            side.wait_stream(main)
+        for i, (sl, unet, clf, side, fork) in enumerate(self.parts):
+            with th.cuda.stream(main if i == 0 else side):
+                self._part(ts, sl, unet, clf, fork)
+        for _, _, _, side, _ in self.parts[1:]:
+            main.wait_stream(side)
 
     def _capture(self) -> None:
         # warm-up on a side stream (sets function attributes, resolves driver entry points), then capture
-        self.unet.x_in.zero_()
+        for _, unet, _, _, _ in self.parts:
+            unet.x_in.zero_()
         self.noise.zero_()
         side = th.cuda.Stream()
         side.wait_stream(th.cuda.current_stream())
@@ -168,9 +193,11 @@ class GraphedStepper:
 
     @property
     def launches_per_step(self) -> int:
-        n = self.unet.prog.launches + 1
-        if self.clf is not None:
-            n += self.clf.fwd.launches + self.clf.bwd.launches + 1
+        n = 0
+        for _, unet, clf, _, _ in self.parts:
+            n += unet.prog.launches + 1
+            if clf is not None:
+                n += clf.fwd.launches + clf.bwd.launches + 1
         return n
 
     def step(self, img: th.Tensor, t: th.Tensor, noise: Optional[th.Tensor] = None,
@@ -178,8 +205,10 @@ class GraphedStepper:
         if labels is not None and self.y is not None:
             self.y.copy_(labels)
             if self.uses_y:
-                self.unet.cond_in.copy_(self.y)
-        self.unet.x_in.copy_(img)
+                for sl, unet, _, _, _ in self.parts:
+                    unet.cond_in.copy_(self.y[sl])
+        for sl, unet, _, _, _ in self.parts:
+            unet.x_in.copy_(img[sl])
         self.t_idx.copy_(t)
         if noise is None:
             self.noise.normal_()

@@ -33,6 +33,8 @@ SHAPES = [
     ("256^2 1x1 64->256 (first conv)", 8, 256, 64, 256, 1, 0, L.RES_NONE),
     ("256^2 256->256 batch 64", 64, 256, 256, 256, 9, 0, L.RES_NONE),   # bench.py's roofline kernel
     ("256^2 128->128 batch 64 (clf)", 64, 256, 128, 128, 9, 0, L.RES_NONE),
+    ("256^2 1x1 64->256 batch 64 (first conv)", 64, 256, 64, 256, 1, 0, L.RES_NONE),
+    ("256^2 1x1 64->128 batch 64 (clf first conv)", 64, 256, 64, 128, 1, 0, L.RES_NONE),
 ]
 
 

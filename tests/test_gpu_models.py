@@ -339,3 +339,29 @@ def test_full_size_512_classifier_guided_ddim_step(lib):
     assert th.isfinite(out["sample"]).all() and th.isfinite(out["pred_xstart"]).all()
     assert float(g2.abs().max()) > 0 and th.equal(g2[:1], g1)
     assert e2.shape == (2, 6, 512, 512) and th.equal(e2[:1], e1)
+
+
+def test_split_batch_step_graph_is_bit_identical(lib, unet, clf, monkeypatch):
+    """GD_B200_SPLIT=2 runs the two halves of the batch as independent branches of the step graph (own plans, own
+    streams).  Samples are independent, so three guided steps must reproduce the single-part graph bit for bit."""
+    model, _ = unet
+    classifier, _ = clf
+    y = cfg.traj_labels().cuda()
+    init, zs = cfg.traj10_noise()
+    outs = []
+    for split in ("1", "2"):
+        monkeypatch.setenv("GD_B200_SPLIT", split)
+        monkeypatch.setenv("GD_B200_NO_GRAPH", "0")
+        d = su.create_gaussian_diffusion(steps=1000, learn_sigma=True, noise_schedule="linear", timestep_respacing="250")
+        cond = ClassifierGuidance(classifier, cfg.CLF_SCALE)
+        model_fn = ModelFn(model, True)
+        img = init.cuda()
+        st = GraphedStepper.cached(d, model_fn, cond, tuple(img.shape), img.device, {"y": y}, True, False, 0.0)
+        assert st is not None and len(st.parts) == int(split)
+        with th.no_grad():
+            for k in range(3):
+                t = th.full((img.shape[0],), d.num_timesteps - 1 - k, dtype=th.int64, device="cuda")
+                out = d._sample_step(model_fn, img, t, True, None, cond, {"y": y}, False, 0.0, noise=zs[k].cuda())
+                img = out["sample"]
+        outs.append((img.clone(), out["pred_xstart"].clone()))
+    assert th.equal(outs[0][0], outs[1][0]) and th.equal(outs[0][1], outs[1][1])
