@@ -84,6 +84,7 @@ SIGNATURES = {
     "gd_logsoftmax_select_bwd": (C.c_int, [vp, vp, vp, i32, i32, f32, vp]),
     "gd_posterior_step": (C.c_int, [C.POINTER(PosteriorDesc), vp]),
     "gd_to_uint8_nhwc": (C.c_int, [vp, vp, i32, i32, i32, i32, vp]),
+    "gd_tap_gather3x3": (C.c_int, [vp, i32, vp, vp, i32, i32, i32, i32, C.c_float, vp]),
     "gd_nchw_f32_to_nhwc_f16": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, vp]),
     "gd_nhwc_f16_to_nchw_f32": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, vp]),
     "gd_bilinear_upsample_nchw": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),

@@ -456,6 +456,75 @@ extern "C" int gd_im2col3x3_small_cin(const float* x, void* out, int32_t ld_out,
   return 0;
 }
 
+namespace gd {
+namespace {
+// CTA = 8 x 32 output pixels of one image.  Its (8+2) x (32+2) halo of ytap rows (64 fp16 = 32 words each) is staged in
+// shared memory with 16-byte global loads (rows padded to 33 words: the word-wise stores of a warp and the later
+// reads of 32 horizontally adjacent pixels are both bank-conflict free), then every thread sums its 9 taps x cout
+// values from there; pixels outside the image are staged as zeros = the conv's zero padding.  fp32 NCHW stores are
+// coalesced along x.
+constexpr int kTgW = 32, kTgH = 8, kTgRow = 33;
+template <int kCout>
+__global__ void __launch_bounds__(kTgW * kTgH)
+tap_gather3x3_kernel(const __half* __restrict__ ytap, int ld, const float* __restrict__ bias, float* __restrict__ out,
+                     int h, int w, float out_scale) {
+  __shared__ uint32_t tile[(kTgH + 2) * (kTgW + 2) * kTgRow];
+  const int n = blockIdx.z, y0 = blockIdx.y * kTgH, x0 = blockIdx.x * kTgW;
+  const size_t plane = static_cast<size_t>(h) * w;
+  constexpr int kChunks = (9 * kCout * 2 + 15) / 16;  // 16-byte chunks that hold the 9*cout useful halves
+  for (int i = threadIdx.x; i < (kTgH + 2) * (kTgW + 2) * kChunks; i += kTgW * kTgH) {
+    const int r = i / kChunks, c = i - r * kChunks;
+    const int yy = y0 + r / (kTgW + 2) - 1, xx = x0 + r % (kTgW + 2) - 1;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (yy >= 0 && yy < h && xx >= 0 && xx < w)
+      v = __ldg(reinterpret_cast<const uint4*>(ytap + (static_cast<size_t>(n) * plane + static_cast<size_t>(yy) * w + xx) * ld) + c);
+    uint32_t* dst = tile + r * kTgRow + 4 * c;
+    dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x % kTgW, ty = threadIdx.x / kTgW;
+  const int x = x0 + tx, y = y0 + ty;
+  if (x >= w || y >= h) return;
+  float acc[kCout];
+#pragma unroll
+  for (int c = 0; c < kCout; ++c) acc[c] = bias != nullptr ? __ldg(bias + c) : 0.f;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const uint32_t* src = tile + ((ty + t / 3) * (kTgW + 2) + tx + t % 3) * kTgRow;
+#pragma unroll
+    for (int c = 0; c < kCout; ++c) {
+      const int hidx = t * kCout + c;
+      const uint32_t wv = src[hidx >> 1];
+      const __half hv = __ushort_as_half(static_cast<unsigned short>((hidx & 1) ? (wv >> 16) : (wv & 0xffffu)));
+      acc[c] += __half2float(hv);
+    }
+  }
+  float* o = out + static_cast<size_t>(n) * kCout * plane + static_cast<size_t>(y) * w + x;
+#pragma unroll
+  for (int c = 0; c < kCout; ++c) o[c * plane] = acc[c] * out_scale;
+}
+}  // namespace
+}  // namespace gd
+
+extern "C" int gd_tap_gather3x3(const void* ytap, int32_t ld, const float* bias, float* out, int32_t n, int32_t cout,
+                                int32_t h, int32_t w, float out_scale, void* stream) {
+  GD_REQUIRE(ytap && out && n > 0 && h > 0 && w > 0, "gd_tap_gather3x3: bad arguments");
+  GD_REQUIRE(cout >= 1 && cout <= 7 && ld >= 64 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(ytap) & 15u) == 0,
+             "gd_tap_gather3x3: cout %d outside [1,7], or ytap rows (ld %d) not 16-byte aligned / shorter than 64", cout, ld);
+  const __half* y = reinterpret_cast<const __half*>(ytap);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const dim3 grid((w + kTgW - 1) / kTgW, (h + kTgH - 1) / kTgH, n);
+  switch (cout) {
+#define GD_TAP_CASE(K) \
+  case K: tap_gather3x3_kernel<K><<<grid, kTgW * kTgH, 0, st>>>(y, ld, bias, out, h, w, out_scale); break;
+    GD_TAP_CASE(1) GD_TAP_CASE(2) GD_TAP_CASE(3) GD_TAP_CASE(4) GD_TAP_CASE(5) GD_TAP_CASE(6) GD_TAP_CASE(7)
+#undef GD_TAP_CASE
+  }
+  GD_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
+
 extern "C" int gd_to_uint8_nhwc(const float* x, uint8_t* out, int32_t n, int32_t c, int32_t h, int32_t w, void* stream) {
   GD_REQUIRE(x && out && n > 0 && c > 0 && h > 0 && w > 0, "gd_to_uint8_nhwc: bad arguments");
   const size_t total = static_cast<size_t>(n) * c * h * w;

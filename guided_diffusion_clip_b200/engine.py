@@ -138,6 +138,17 @@ def pack_conv3x3_bwd(w: th.Tensor) -> th.Tensor:
     return _pad_rows(m)
 
 
+def pack_tap_expand(w: th.Tensor) -> th.Tensor:
+    """OIHW [Co,Ci,3,3] -> [64][Ci] fp16, row = (ky*3+kx)*Co + co (zero rows above 9*Co): the 3x3 conv as one 1x1 GEMM
+    whose 9*Co output columns are gathered by gd_tap_gather3x3 (narrow-output convs only, 9*Co <= 63)."""
+    co, ci = w.shape[:2]
+    m = w.float().permute(2, 3, 0, 1).reshape(9 * co, ci)
+    return th.cat([m, m.new_zeros(64 - 9 * co, ci)], 0).to(th.float16).contiguous()
+
+
+NARROW_COUT = 7  # 9 * cout <= 63: the tap-expanded GEMM still fits one 64-column tile
+
+
 def pack_conv_in(w: th.Tensor) -> th.Tensor:
     """First-layer weights [Co,Ci,3,3] (Ci*9 <= 64) -> [Co_pad][64] matching gd_im2col3x3_small_cin: k = (ky*3+kx)*Ci + ci."""
     co, ci = w.shape[:2]
@@ -244,6 +255,19 @@ class Emitter:
         if out_mode == L.OUT_NHWC_F16 and cout == out.c and cout % 64 == 0 and wpack.shape[0] == cout:
             # latest writer of this channel view: a later GroupNorm over it can ask this conv for fused statistics
             self._producers[(out.buf.data_ptr(), out.off, out.c)] = (d, n, h, w)
+
+    def conv3x3_narrow(self, a0: View, w_oihw: th.Tensor, bias: Optional[th.Tensor], out: th.Tensor, *,
+                       out_scale=1.0, geom: Optional[Tuple[int, int, int]] = None) -> None:
+        """3x3 conv to fp32 NCHW with cout <= NARROW_COUT as a tap-expanded 1x1 GEMM (64 columns, the fast fp16 NHWC
+        TMA-store epilogue) + tap gather: a tensor-core tile with 3-6 useful columns of 16 runs at 35-55 TFLOP/s."""
+        n, h, w = geom if geom is not None else (a0.n, a0.h, a0.w)
+        cout = int(w_oihw.shape[0])
+        ytap = new_act(n, h, w, 64, self.device)
+        self.keep.append(ytap.buf)
+        self.conv(a0, pack_tap_expand(w_oihw), None, 64, ytap, taps=1, geom=geom)
+        self.keep.append(bias)
+        self.prog.add("gd_tap_gather3x3", C.c_void_p(ytap.ptr), ytap.ld, _p(bias), _p(out), n, cout, h, w,
+                      C.c_float(float(out_scale)))
 
     def _producers_of(self, x: View):
         """The conv launch(es) that wrote view x: one conv, or two convs writing adjacent channel slices (skip concat)."""
@@ -515,8 +539,11 @@ class UNetPlan:
         g = em.scratch("gn_out", n, cur.h, cur.w, cur.c)
         em.gn_stats(cur, st)
         em.gn_apply(cur, st, em.f32("out.0.weight"), em.f32("out.0.bias"), g, silu=True)
-        em.conv(g, pack_conv3x3(em.P["out.2.weight"]), em.f32("out.2.bias"), model.out_channels, self.out,
-                out_mode=L.OUT_NCHW_F32)
+        if model.out_channels <= NARROW_COUT:
+            em.conv3x3_narrow(g, em.P["out.2.weight"], em.f32("out.2.bias"), self.out)
+        else:
+            em.conv(g, pack_conv3x3(em.P["out.2.weight"]), em.f32("out.2.bias"), model.out_channels, self.out,
+                    out_mode=L.OUT_NCHW_F32)
         self.prog = em.prog
 
     def load_inputs(self, x, timesteps, cond) -> None:
@@ -664,9 +691,13 @@ class ClassifierPlan:
                 g = g_in
             else:  # conv_in: dX in fp32 NCHW, loss scale undone, user scale applied at run time by self.scale
                 _, l, o = entry
-                self._dx_desc_index = len(bw.prog.calls)
-                bw.conv(g, pack_conv3x3_bwd(em.P[f"{l.key}.weight"]), None, l.cin, self.dx, out_mode=L.OUT_NCHW_F32,
-                        out_scale=1.0 / self.LOSS_SCALE, geom=(n, o.h, o.w))
+                wk = em.P[f"{l.key}.weight"]
+                if l.cin <= NARROW_COUT:  # dX = conv3x3 of dY with the flipped, transposed weights
+                    bw.conv3x3_narrow(g, wk.flip(2, 3).permute(1, 0, 2, 3), None, self.dx,
+                                      out_scale=1.0 / self.LOSS_SCALE, geom=(n, o.h, o.w))
+                else:
+                    bw.conv(g, pack_conv3x3_bwd(wk), None, l.cin, self.dx, out_mode=L.OUT_NCHW_F32,
+                            out_scale=1.0 / self.LOSS_SCALE, geom=(n, o.h, o.w))
         self.bwd = em.prog
 
     # -- execution --------------------------------------------------------------------------------

@@ -241,6 +241,16 @@ int gd_posterior_step(const gd_posterior_desc* desc, void* stream);
 /* ((x+1)*127.5).clamp(0,255).to(uint8) NCHW -> NHWC (scripts/classifier_sample.py:87-89; truncation). */
 int gd_to_uint8_nhwc(const float* x, uint8_t* out, int32_t n, int32_t c, int32_t h, int32_t w, void* stream);
 
+/* Second half of a 3x3 convolution with very few output channels (the UNet's 256->6 `out` head, unet.py:613-617, and
+ * the classifier's 128->3 data-gradient conv): the conv is evaluated as ONE 1x1 GEMM with 9*cout output columns,
+ * ytap[n][y][x][tap*cout+co] = sum_ci W[co][ci][ky][kx] * in[n][y][x][ci] (gd_conv_igemm, taps = 1, fp16 NHWC output with
+ * pixel stride ld), and this kernel gathers the taps into fp32 NCHW:
+ *   out[n][co][y][x] = out_scale * (bias[co] + sum_tap ytap[n][y+ky-1][x+kx-1][tap*cout+co]),  zero outside the image.
+ * A tensor-core tile with 6 useful columns of 16 runs at 3 % of peak; the 54-of-64-column GEMM an order of magnitude
+ * faster.  cout <= 7. */
+int gd_tap_gather3x3(const void* ytap, int32_t ld, const float* bias, float* out, int32_t n, int32_t cout, int32_t h,
+                     int32_t w, float out_scale, void* stream);
+
 /* Layout helpers used at the API boundary and by tests. */
 int gd_nchw_f32_to_nhwc_f16(const float* x, void* out, int32_t ld_out, int32_t n, int32_t c, int32_t h, int32_t w,
                             void* stream);

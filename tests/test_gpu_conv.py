@@ -6,7 +6,7 @@ import torch as th
 import torch.nn.functional as F
 
 from guided_diffusion_clip_b200 import _lib as L
-from guided_diffusion_clip_b200.engine import pack_1x1, pack_1x1_bwd, pack_conv3x3, pack_conv3x3_bwd
+from guided_diffusion_clip_b200.engine import pack_1x1, pack_1x1_bwd, pack_conv3x3, pack_conv3x3_bwd, pack_tap_expand
 from tests import gpu_helpers as H
 
 pytestmark = pytest.mark.gpu
@@ -121,6 +121,26 @@ def test_conv_nchw_fp32_small_cout(lib, cout):
     err = H.rel_err(out, ref)
     print(f"nchw fp32 cout={cout}: rel err {err:.3e}")
     assert err < 1e-3
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 32, 32, 128, 6), (3, 20, 24, 64, 3), (1, 8, 8, 192, 7), (2, 16, 8, 64, 1)])
+def test_conv_narrow_output_as_tap_expanded_gemm(lib, n, h, w, cin, cout):
+    """The 256->6 head / 128->3 dX convs as ONE 1x1 GEMM with 9*cout columns (engine.pack_tap_expand) + gd_tap_gather3x3,
+    against F.conv2d and against the plain 3x3 implicit GEMM; ragged image sizes exercise the zero border of the gather."""
+    import ctypes as C
+    x = _h(_rand((n, cin, h, w), 31))
+    wt = _h(_rand((cout, cin, 3, 3), 32, (cin * 9) ** -0.5))
+    b = _rand((cout,), 33, 0.1)
+    ref = F.conv2d(x, wt, b, padding=1) * 0.25
+    xb = H.nhwc_half(x)
+    ytap = H.conv_igemm(xb, cin, 0, pack_tap_expand(wt), None, 64, n, h, w, taps=1)  # fp16 NHWC, 64 columns
+    out = th.full((n, cout, h, w), float("nan"), device="cuda")
+    L.check(lib.gd_tap_gather3x3(H.vp(ytap), 64, H.vp(b), H.vp(out), n, cout, h, w, C.c_float(0.25), H.stream()))
+    plain = H.conv_igemm(xb, cin, 0, pack_conv3x3(wt), b, cout, n, h, w, out_mode=L.OUT_NCHW_F32, out_scale=0.25)
+    th.cuda.synchronize()
+    err, err2 = H.rel_err(out, ref), H.rel_err(out, plain)
+    print(f"narrow conv cout={cout} {h}x{w}: rel err vs torch {err:.3e}, vs plain 3x3 kernel {err2:.3e}")
+    assert err < 2e-3 and err2 < 2e-3  # the 9 tap partial sums are rounded to fp16 before the fp32 gather
 
 
 def test_conv_backward_data_packing(lib):
