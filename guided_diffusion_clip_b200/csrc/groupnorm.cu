@@ -326,6 +326,15 @@ __device__ __forceinline__ void load_dy(const __half* dy, int ld_dy, int n, int 
   }
 }
 
+// address of the dy row that pixel p of an h x w image pulls its gradient from (same resolution, or the parent pixel
+// of a 2x2 average pool at half resolution: every parent row is read by its 4 children, so it stays in L1 / L2)
+template <int kMode>
+__device__ __forceinline__ const __half* dy_row(const __half* dy_n, int ld_dy, int w, int p) {
+  if (kMode == GD_GN_SAME) return dy_n + static_cast<size_t>(p) * ld_dy;
+  const int iy = p / w, ix = p - iy * w;
+  return dy_n + (static_cast<size_t>(iy >> 1) * (w >> 1) + (ix >> 1)) * ld_dy;
+}
+
 template <bool kSilu>
 __device__ __forceinline__ float act_grad(float z) {
   if (!kSilu) return 1.0f;
@@ -390,21 +399,28 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_stats_kernel(const __half* __re
     }
   };
   int p = p0 + pl;
-  if (kMode == GD_GN_SAME) {
+  if (kMode == GD_GN_SAME || kMode == GD_GN_AVGPOOL2) {
     // 4 pixels per iteration: all eight 16-byte loads are issued before any arithmetic
-    const __half* dyn = dy + static_cast<size_t>(n) * hw * ld_dy + cch * 8;
+    const int hw_dy = kMode == GD_GN_SAME ? hw : (h >> 1) * (w >> 1);
+    const __half* dyn = dy + static_cast<size_t>(n) * hw_dy * ld_dy + cch * 8;
+    const float dsc = kMode == GD_GN_SAME ? 1.0f : 0.25f;
     for (; p + 3 * rep < p1; p += 4 * rep) {
       Half8 xv[4], dv[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         xv[u] = ld_half8_stream(xin + static_cast<size_t>(p + u * rep) * ld);
-        dv[u] = ld_half8_stream(dyn + static_cast<size_t>(p + u * rep) * ld_dy);
+        const __half* dp = dy_row<kMode>(dyn, ld_dy, w, p + u * rep);
+        dv[u] = kMode == GD_GN_SAME ? ld_half8_stream(dp) : ld_half8(dp);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         float xf[8], d[8];
         half8_to_float(xv[u], xf);
         half8_to_float(dv[u], d);
+        if (kMode != GD_GN_SAME) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d[j] *= dsc;
+        }
         accumulate(xf, d);
       }
     }
@@ -457,30 +473,43 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_apply_kernel(const __half* __re
     }
   };
   int p = p0 + pl;
-  if (kMode == GD_GN_SAME && (add == nullptr || add_mode == GD_GN_SAME)) {
+  if (kMode == GD_GN_SAME || kMode == GD_GN_AVGPOOL2) {
     // 4 pixels per iteration with every load (x, dy, add) issued up front
-    const __half* dyn = dy + static_cast<size_t>(n) * hw * ld_dy + cch * 8;
-    const __half* addn = add != nullptr ? add + static_cast<size_t>(n) * hw * ld_add + cch * 8 : nullptr;
+    const int hw_dy = kMode == GD_GN_SAME ? hw : (h >> 1) * (w >> 1);
+    const __half* dyn = dy + static_cast<size_t>(n) * hw_dy * ld_dy + cch * 8;
+    const float dsc = kMode == GD_GN_SAME ? 1.0f : 0.25f;
+    const bool add_same = add_mode == GD_GN_SAME;
+    const __half* addn = add != nullptr
+        ? add + static_cast<size_t>(n) * (add_same ? hw : (h >> 1) * (w >> 1)) * ld_add + cch * 8 : nullptr;
+    const float asc = add_same ? 1.0f : 0.25f;
     __half* dxn = dx + static_cast<size_t>(n) * hw * ld_dx + cch * 8;
     for (; p + 3 * rep < p1; p += 4 * rep) {
       Half8 xv[4], dv[4], av[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        xv[u] = ld_half8_stream(xin + static_cast<size_t>(p + u * rep) * ld);
-        dv[u] = ld_half8_stream(dyn + static_cast<size_t>(p + u * rep) * ld_dy);
-        if (addn != nullptr) av[u] = ld_half8_stream(addn + static_cast<size_t>(p + u * rep) * ld_add);
+        const int pp = p + u * rep;
+        xv[u] = ld_half8_stream(xin + static_cast<size_t>(pp) * ld);
+        const __half* dp = dy_row<kMode>(dyn, ld_dy, w, pp);
+        dv[u] = kMode == GD_GN_SAME ? ld_half8_stream(dp) : ld_half8(dp);
+        if (addn != nullptr)
+          av[u] = add_same ? ld_half8_stream(addn + static_cast<size_t>(pp) * ld_add)
+                           : ld_half8(dy_row<GD_GN_AVGPOOL2>(addn, ld_add, w, pp));
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         float xf[8], d[8], r[8];
         half8_to_float(xv[u], xf);
         half8_to_float(dv[u], d);
+        if (kMode != GD_GN_SAME) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d[j] *= dsc;
+        }
         grad_x(xf, d, r);
         if (addn != nullptr) {
           float t[8];
           half8_to_float(av[u], t);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) r[j] += t[j];
+          for (int j = 0; j < 8; ++j) r[j] = fmaf(asc, t[j], r[j]);
         }
         st_half8(dxn + static_cast<size_t>(p + u * rep) * ld_dx, float_to_half8(r));
       }
