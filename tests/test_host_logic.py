@@ -172,6 +172,9 @@ def test_abi_validates_arguments_without_gpu(lib):
     assert lib.gd_groupnorm_stats(ctypes.c_void_p(16), 48, 1, 4, 48, ctypes.c_float(1e-5), ctypes.c_void_p(16),
                                   ctypes.c_void_p(16), None) == -1
     assert b"multiple of 32" in lib.gd_last_error()
+    assert lib.gd_tap_gather3x3(ctypes.c_void_p(16), 64, None, ctypes.c_void_p(16), 1, 8, 4, 4, ctypes.c_float(1.0),
+                                None) == -1
+    assert b"outside [1,7]" in lib.gd_last_error()
     p = _lib.PosteriorDesc()
     assert lib.gd_posterior_step(p, None) == -1
     assert lib.gd_groupnorm_ws_floats(8, 1, 32) == 8 * 129 * 64
@@ -227,3 +230,38 @@ def test_upsampler_low_res_stream_is_rank_strided(tmp_path):
     assert set(next(gen).keys()) == {"low_res"}
     with pytest.raises(ValueError):
         next(dist_util.load_data_for_worker(path, 2, True, rank_=9, world=10))
+
+
+def test_weight_packing_algebra_on_cpu():
+    """The host-side weight packers restated as plain matrix products (no kernel involved): the tap-expanded packing
+    of the narrow-output convs (engine.pack_tap_expand + the gather gd_tap_gather3x3 performs) and the flipped /
+    transposed backward-data packing reproduce F.conv2d and its data gradient."""
+    import torch.nn.functional as F
+    from guided_diffusion_clip_b200.engine import pack_conv3x3, pack_conv3x3_bwd, pack_tap_expand
+    g = th.Generator().manual_seed(0)
+    n, ci, co, h, w = 2, 8, 3, 6, 5
+    x = th.randn(n, ci, h, w, generator=g).half().float()
+    wt = th.randn(co, ci, 3, 3, generator=g).half().float()
+    ref = F.conv2d(x, wt, padding=1)
+    # tap-expanded 1x1 GEMM: y[n,y,x,tap*co+c], then out[p] = sum_tap y[p + delta_tap][tap]
+    wp = pack_tap_expand(wt).float()
+    assert wp.shape == (64, ci) and float(wp[9 * co:].abs().max()) == 0.0
+    ytap = th.einsum("nchw,kc->nhwk", x, wp)
+    ypad = F.pad(ytap, (0, 0, 1, 1, 1, 1))
+    out = th.zeros(n, co, h, w)
+    for ky in range(3):
+        for kx in range(3):
+            t = ky * 3 + kx
+            out += ypad[:, ky:ky + h, kx:kx + w, t * co:(t + 1) * co].permute(0, 3, 1, 2)
+    assert th.allclose(out, ref, atol=1e-4)
+    # implicit-GEMM packing: k = (ky*3+kx)*Ci + ci over an im2col of the zero-padded input
+    cols = F.unfold(x, 3, padding=1).view(n, ci, 9, h * w).permute(0, 3, 2, 1).reshape(n, h * w, 9 * ci)
+    out2 = (cols @ pack_conv3x3(wt).float()[:co].t()).permute(0, 2, 1).reshape(n, co, h, w)
+    assert th.allclose(out2, ref, atol=1e-4)
+    # backward-data = forward conv of dy with the flipped, transposed weights
+    xg = x.clone().requires_grad_(True)
+    dy = th.randn(n, co, h, w, generator=g).half().float()
+    F.conv2d(xg, wt, padding=1).backward(dy)
+    dcols = F.unfold(dy, 3, padding=1).view(n, co, 9, h * w).permute(0, 3, 2, 1).reshape(n, h * w, 9 * co)
+    dx = (dcols @ pack_conv3x3_bwd(wt).float()[:ci].t()).permute(0, 2, 1).reshape(n, ci, h, w)
+    assert th.allclose(dx, xg.grad, atol=1e-4)
