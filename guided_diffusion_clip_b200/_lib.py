@@ -37,6 +37,13 @@ class ConvDesc(C.Structure):
     ]
 
 
+class ConvInDesc(C.Structure):
+    _fields_ = [
+        ("x", vp), ("wpack", vp), ("bias", vp), ("out", vp), ("stats_out", vp),
+        ("n", i32), ("cin", i32), ("h", i32), ("w", i32), ("cout", i32), ("ld_out", i32),
+    ]
+
+
 class PosteriorDesc(C.Structure):
     _fields_ = [
         ("x", vp), ("model_out", vp), ("grad", vp), ("noise", vp), ("sample", vp), ("pred_xstart", vp),
@@ -84,6 +91,7 @@ SIGNATURES = {
     "gd_logsoftmax_select_bwd": (C.c_int, [vp, vp, vp, i32, i32, f32, vp]),
     "gd_posterior_step": (C.c_int, [C.POINTER(PosteriorDesc), vp]),
     "gd_to_uint8_nhwc": (C.c_int, [vp, vp, i32, i32, i32, i32, vp]),
+    "gd_conv_in3x3": (C.c_int, [C.POINTER(ConvInDesc), vp]),
     "gd_tap_gather3x3": (C.c_int, [vp, i32, vp, vp, i32, i32, i32, i32, C.c_float, vp]),
     "gd_nchw_f32_to_nhwc_f16": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, vp]),
     "gd_nhwc_f16_to_nchw_f32": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, vp]),

@@ -369,11 +369,24 @@ class Emitter:
 
     # ---- blocks -------------------------------------------------------------------------------
     def conv_in(self, l: ConvInSpec, x_nchw: th.Tensor, out: View) -> None:
-        """First layer (unet.py:483): im2col to one 64-wide K block (cin*9 <= 64), then a K=64 GEMM on the tcgen05 kernel."""
-        cols = self.scratch("im2col", out.n, out.h, out.w, 64)
+        """First layer (unet.py:483).  Preferred: gd_conv_in3x3, one launch from the fp32 NCHW input with register
+        accumulators (the layer is bound by writing its output).  Shapes it does not cover (C_out not a multiple of 64,
+        fewer than 128 pixels per image): im2col to one 64-wide K block, then a K=64 GEMM on the tcgen05 kernel."""
         self.keep.append(x_nchw)
+        wp, bias = pack_conv_in(self.P[f"{l.key}.weight"]), self.f32(f"{l.key}.bias")
+        if (l.cout % 64 == 0 and (out.h * out.w) % 128 == 0 and out.ld % 8 == 0 and out.off % 8 == 0
+                and os.environ.get("GD_B200_NO_CONV_IN", "0") != "1"):
+            d = L.ConvInDesc()
+            d.x, d.wpack, d.bias, d.out, d.stats_out = x_nchw.data_ptr(), wp.data_ptr(), bias.data_ptr(), out.ptr, None
+            d.n, d.cin, d.h, d.w, d.cout, d.ld_out = out.n, l.cin, out.h, out.w, l.cout, out.ld
+            self.keep += [wp, bias, d]
+            self.prog.add("gd_conv_in3x3", C.byref(d))
+            if l.cout == out.c:
+                self._producers[(out.buf.data_ptr(), out.off, out.c)] = (d, out.n, out.h, out.w)
+            return
+        cols = self.scratch("im2col", out.n, out.h, out.w, 64)
         self.prog.add("gd_im2col3x3_small_cin", _p(x_nchw), C.c_void_p(cols.ptr), cols.ld, out.n, l.cin, out.h, out.w)
-        self.conv(cols, pack_conv_in(self.P[f"{l.key}.weight"]), self.f32(f"{l.key}.bias"), l.cout, out, taps=1)
+        self.conv(cols, wp, bias, l.cout, out, taps=1)
 
     def res_block(self, r: ResSpec, x: View, out: View, film_all: th.Tensor, tape: Optional[list] = None) -> None:
         """ResBlock._forward (unet.py:236-256) in 6 launches: GN stats, GN-apply(+SiLU, +pool/upsample), conv,

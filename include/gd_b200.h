@@ -92,6 +92,22 @@ int gd_groupnorm_finalize_partials(const float* p0, int32_t c0, int32_t ld0, con
 int gd_im2col3x3_small_cin(const float* x, void* out, int32_t ld_out, int32_t n, int32_t cin, int32_t h, int32_t w,
                            void* stream);
 
+/* The same first layer in ONE launch, straight from the fp32 NCHW network input (no im2col buffer): warp-level
+ * tensor-core MMAs with register accumulators -- at 27 MACs per output the layer is bound by writing its fp16 NHWC
+ * output, and on the tcgen05 path by reading accumulators out of TMEM.  wpack as for gd_im2col3x3_small_cin + gd_conv_igemm
+ * (fp16 [cout][64], k = (ky*3+kx)*cin + ci, zero padded).  Requires cout % 64 == 0 and h*w % 128 == 0.
+ * stats_out (optional): fused GroupNorm partials in gd_conv_igemm's format, one row per 128 pixels; rows beyond
+ * h*w/128 of an image's gd_conv_stats_rows block are left untouched (the caller zero-fills the buffer once). */
+typedef struct {
+  const float* x;      /* fp32 NCHW [n,cin,h,w] */
+  const void* wpack;   /* fp16 [cout][64] */
+  const float* bias;   /* fp32 [cout] */
+  void* out;           /* fp16 NHWC view, pixel stride ld_out */
+  float* stats_out;    /* fp32 [gd_conv_stats_rows(n,h,w)][cout/4][2] or NULL */
+  int32_t n, cin, h, w, cout, ld_out;
+} gd_conv_in_desc;
+int gd_conv_in3x3(const gd_conv_in_desc* desc, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * GroupNorm32 (+SiLU) (+FiLM scale/shift) (+avgpool2 / nearest-upsample2), nn.py:17-19,93-100 with
  * unet.py:184,200-208,248-252 and the h_upd of unet.py:191-195.  Two launches: statistics, then apply.

@@ -249,3 +249,46 @@ def test_conv_rejects_bad_arguments(lib):
     d = L.ConvDesc()
     rc = lib.gd_conv_igemm(d, None)
     assert rc != 0 and b"null" in lib.gd_last_error()
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,ld,off", [(2, 16, 16, 3, 64, 64, 0), (3, 32, 32, 3, 256, 512, 256),
+                                                   (2, 64, 64, 6, 192, 192, 0), (1, 16, 8, 3, 128, 136, 8),
+                                                   (2, 24, 16, 4, 64, 64, 0)])
+def test_conv_in3x3_direct_first_layer(lib, n, h, w, cin, cout, ld, off):
+    """gd_conv_in3x3 (first layer in one launch from the fp32 NCHW input) against F.conv2d, written into a channel
+    slice of a wider buffer; its fused GroupNorm partials, finalized by gd_groupnorm_finalize_partials, against the
+    statistics kernel on the stored tensor."""
+    import ctypes as C
+    from guided_diffusion_clip_b200.engine import pack_conv_in
+    x = _rand((n, cin, h, w), 41)
+    wt = _h(_rand((cout, cin, 3, 3), 42, (cin * 9) ** -0.5))
+    b = _rand((cout,), 43, 0.1)
+    ref = F.conv2d(_h(x), wt, b, padding=1)
+    wp = pack_conv_in(wt)
+    out = th.zeros((n, h, w, ld), dtype=th.float16, device="cuda")
+    rpi = C.c_int32(0)
+    rows = int(lib.gd_conv_stats_rows(n, h, w, C.byref(rpi)))
+    assert rows > 0
+    part = th.zeros((rows, cout // 4, 2), device="cuda")
+    d = L.ConvInDesc()
+    d.x, d.wpack, d.bias, d.out, d.stats_out = x.data_ptr(), wp.data_ptr(), b.data_ptr(), out.data_ptr() + 2 * off, part.data_ptr()
+    d.n, d.cin, d.h, d.w, d.cout, d.ld_out = n, cin, h, w, cout, ld
+    L.check(lib.gd_conv_in3x3(C.byref(d), H.stream()), "gd_conv_in3x3")
+    th.cuda.synchronize()
+    got = out[..., off:off + cout].permute(0, 3, 1, 2).float()
+    err = H.rel_err(got, ref)
+    print(f"conv_in3x3 cin={cin} cout={cout} {h}x{w}: rel err {err:.3e}")
+    assert err < 2e-3
+    if off:
+        assert float(out[..., :off].abs().max()) == 0.0
+    if off + cout < ld:
+        assert float(out[..., off + cout:].abs().max()) == 0.0
+    if (cout // 32) % 4:
+        return  # the finalize kernel sums whole 4-channel chunks per group: groups of 2 channels use gd_groupnorm_stats
+    st = th.empty((n, 32, 2), device="cuda")
+    L.check(lib.gd_groupnorm_finalize_partials(H.vp(part), cout, cout // 4, None, 0, 0, rpi.value, n, h * w,
+                                               C.c_float(1e-5), H.vp(st), H.stream()))
+    st_ref = H.gn_stats(out, cout, off)
+    th.cuda.synchronize()
+    assert float((st[..., 0] - st_ref[..., 0]).abs().max()) < 1e-4
+    assert H.rel_err(st[..., 1], st_ref[..., 1]) < 1e-4
