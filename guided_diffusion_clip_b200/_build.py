@@ -17,7 +17,7 @@ ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "libgd_b200.so")
 OBJ_DIR = os.path.join(HERE, "build")
 
-SOURCES = ["api.cu", "conv_igemm.cu", "conv_in.cu", "groupnorm.cu", "attention.cu", "attention_tc.cu", "elementwise.cu", "attnpool.cu", "bw_probe.cu", "clip_ops.cu"]
+SOURCES = ["api.cu", "conv_igemm.cu", "conv_in.cu", "groupnorm.cu", "attention.cu", "attention_tc.cu", "attention_hd.cu", "elementwise.cu", "attnpool.cu", "bw_probe.cu", "clip_ops.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

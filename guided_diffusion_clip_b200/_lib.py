@@ -92,6 +92,10 @@ SIGNATURES = {
     "gd_posterior_step": (C.c_int, [C.POINTER(PosteriorDesc), vp]),
     "gd_to_uint8_nhwc": (C.c_int, [vp, vp, i32, i32, i32, i32, vp]),
     "gd_conv_in3x3": (C.c_int, [C.POINTER(ConvInDesc), vp]),
+    "gd_im2col3x3_s2_nhwc": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, i32, vp]),
+    "gd_upsample2_nhwc": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, i32, vp]),
+    "gd_add_emb_nhwc": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, vp]),
+    "gd_attention_fwd_hd": (C.c_int, [vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, vp]),
     "gd_tap_gather3x3": (C.c_int, [vp, i32, vp, vp, i32, i32, i32, i32, C.c_float, vp]),
     "gd_nchw_f32_to_nhwc_f16": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, vp]),
     "gd_nhwc_f16_to_nchw_f32": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, vp]),

@@ -578,3 +578,123 @@ extern "C" int gd_logsoftmax_select_bwd(const float* logits, const int64_t* y, f
   count_launch(1);
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// conv_resample layers of models built with resblock_updown=False (the reference factory default,
+// script_util.py:60): Downsample = 3x3 stride-2 conv (unet.py:125-136), Upsample = nearest x2 then 3x3 conv
+// (unet.py:91-110); ResBlocks without FiLM add the embedding before the second GroupNorm (unet.py:253-255).
+// All three are single bandwidth-bound passes over fp16 NHWC with 16-byte vectors; the contractions run on
+// gd_conv_igemm (the strided conv as a taps = 1 GEMM over the gathered [.., 9*C] rows).
+// ---------------------------------------------------------------------------------------------
+namespace gd {
+namespace {
+
+__global__ void __launch_bounds__(256)
+im2col3x3_s2_kernel(const __half* __restrict__ x, int ld, __half* __restrict__ out, int ld_out, int n, int h, int w,
+                    int c8, int ho, int wo) {
+  const size_t total = static_cast<size_t>(n) * ho * wo * 9 * c8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int cc = static_cast<int>(i % c8);
+    size_t r = i / c8;
+    const int tap = static_cast<int>(r % 9);
+    r /= 9;
+    const int xo = static_cast<int>(r % wo);
+    r /= wo;
+    const int yo = static_cast<int>(r % ho);
+    const int img = static_cast<int>(r / ho);
+    const int yy = 2 * yo + tap / 3 - 1, xx = 2 * xo + tap % 3 - 1;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (yy >= 0 && yy < h && xx >= 0 && xx < w)
+      v = __ldg(reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(img) * h + yy) * w + xx) * ld) + cc);
+    *(reinterpret_cast<uint4*>(out + ((static_cast<size_t>(img) * ho + yo) * wo + xo) * ld_out + tap * c8 * 8) + cc) = v;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+upsample2_nhwc_kernel(const __half* __restrict__ x, int ld, __half* __restrict__ out, int ld_out, int n, int h, int w,
+                      int c8) {
+  const size_t total = static_cast<size_t>(n) * (2 * h) * (2 * w) * c8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int cc = static_cast<int>(i % c8);
+    size_t r = i / c8;
+    const int xo = static_cast<int>(r % (2 * w));
+    r /= 2 * w;
+    const int yo = static_cast<int>(r % (2 * h));
+    const int img = static_cast<int>(r / (2 * h));
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(img) * h + (yo >> 1)) * w + (xo >> 1)) * ld) + cc);
+    *(reinterpret_cast<uint4*>(out + ((static_cast<size_t>(img) * 2 * h + yo) * 2 * w + xo) * ld_out) + cc) = v;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+add_emb_nhwc_kernel(__half* __restrict__ x, int ld, const float* __restrict__ emb, int ld_emb, int n, int hw, int c8) {
+  const size_t total = static_cast<size_t>(n) * hw * c8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int cc = static_cast<int>(i % c8);
+    const size_t px = i / c8;
+    const int img = static_cast<int>(px / hw);
+    uint4* p = reinterpret_cast<uint4*>(x + px * ld) + cc;
+    uint4 v = *p;
+    const float4 e0 = __ldg(reinterpret_cast<const float4*>(emb + static_cast<size_t>(img) * ld_emb + cc * 8));
+    const float4 e1 = __ldg(reinterpret_cast<const float4*>(emb + static_cast<size_t>(img) * ld_emb + cc * 8) + 1);
+    __half2* hv = reinterpret_cast<__half2*>(&v);
+    float2 f;
+    f = __half22float2(hv[0]); hv[0] = __floats2half2_rn(f.x + e0.x, f.y + e0.y);
+    f = __half22float2(hv[1]); hv[1] = __floats2half2_rn(f.x + e0.z, f.y + e0.w);
+    f = __half22float2(hv[2]); hv[2] = __floats2half2_rn(f.x + e1.x, f.y + e1.y);
+    f = __half22float2(hv[3]); hv[3] = __floats2half2_rn(f.x + e1.z, f.y + e1.w);
+    *p = v;
+  }
+}
+
+int check_nhwc(const char* who, const void* x, int ld, const void* out, int ld_out, int n, int h, int w, int c, int c_out) {
+  GD_REQUIRE(x && out, "%s: null pointer", who);
+  GD_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, "%s: bad shape n=%d h=%d w=%d c=%d (c must be a multiple of 8)",
+             who, n, h, w, c);
+  GD_REQUIRE(ld >= c && ld % 8 == 0 && ld_out >= c_out && ld_out % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0 &&
+                 (reinterpret_cast<uintptr_t>(out) & 15u) == 0,
+             "%s: rows must be 16-byte aligned (ld %d, ld_out %d)", who, ld, ld_out);
+  return 0;
+}
+
+}  // namespace
+}  // namespace gd
+
+extern "C" int gd_im2col3x3_s2_nhwc(const void* x, int32_t ld, void* out, int32_t ld_out, int32_t n, int32_t h, int32_t w,
+                                    int32_t c, void* stream) {
+  if (int rc = check_nhwc("gd_im2col3x3_s2_nhwc", x, ld, out, ld_out, n, h, w, c, 9 * c)) return rc;
+  const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
+  const size_t total = static_cast<size_t>(n) * ho * wo * 9 * (c / 8);
+  im2col3x3_s2_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half*>(x), ld, reinterpret_cast<__half*>(out), ld_out, n, h, w, c / 8, ho, wo);
+  GD_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
+
+extern "C" int gd_upsample2_nhwc(const void* x, int32_t ld, void* out, int32_t ld_out, int32_t n, int32_t h, int32_t w,
+                                 int32_t c, void* stream) {
+  if (int rc = check_nhwc("gd_upsample2_nhwc", x, ld, out, ld_out, n, h, w, c, c)) return rc;
+  const size_t total = static_cast<size_t>(n) * 4 * h * w * (c / 8);
+  upsample2_nhwc_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half*>(x), ld, reinterpret_cast<__half*>(out), ld_out, n, h, w, c / 8);
+  GD_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
+
+extern "C" int gd_add_emb_nhwc(void* x, int32_t ld, const float* emb, int32_t ld_emb, int32_t n, int32_t hw, int32_t c,
+                               void* stream) {
+  if (int rc = check_nhwc("gd_add_emb_nhwc", x, ld, x, ld, n, hw, 1, c, c)) return rc;
+  GD_REQUIRE(emb != nullptr && ld_emb >= c && ld_emb % 4 == 0 && (reinterpret_cast<uintptr_t>(emb) & 15u) == 0,
+             "gd_add_emb_nhwc: embedding rows must be 16-byte aligned fp32 (ld_emb %d)", ld_emb);
+  const size_t total = static_cast<size_t>(n) * hw * (c / 8);
+  add_emb_nhwc_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<__half*>(x), ld, emb, ld_emb, n, hw, c / 8);
+  GD_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}

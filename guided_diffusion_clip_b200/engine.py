@@ -19,7 +19,7 @@ from typing import Dict, List, Optional, Tuple
 import torch as th
 
 from . import _lib as L
-from .unet import AttnSpec, ConvInSpec, ResSpec
+from .unet import AttnSpec, ConvInSpec, ResampleSpec, ResSpec
 
 GN_EPS = 1e-5
 
@@ -358,9 +358,7 @@ class Emitter:
         # emb = time_embed(...) + label ; every consumer applies SiLU first (unet.py:200) -> store SiLU(emb)
         self.linear(h1, self.f32("time_embed.2.weight"), self.f32("time_embed.2.bias"), emb_silu, m=n, k=e, n=e,
                     add=lab, silu_out=True)
-        blocks = spec.res_blocks()
-        if not self.model.use_scale_shift_norm:
-            raise NotImplementedError("use_scale_shift_norm=False has no CUDA path (every BASELINE config sets it)")
+        blocks = spec.res_blocks()  # rows of 2*C (scale, shift) with FiLM, of C (additive embedding) without
         w_all = th.cat([self.f32(f"{r.key}.emb_layers.1.weight") for r in blocks], 0).contiguous()
         b_all = th.cat([self.f32(f"{r.key}.emb_layers.1.bias") for r in blocks], 0).contiguous()
         film_all = th.empty((n, spec.film_total), dtype=th.float32, device=dev)
@@ -410,11 +408,20 @@ class Emitter:
         h1 = self.act(n, ho, wo, r.cout) if tape is not None else self.scratch("h1", n, ho, wo, r.cout)
         w1 = pack_conv3x3(self.P[f"{k}.in_layers.2.weight"])
         self.conv(a, w1, self.f32(f"{k}.in_layers.2.bias"), r.cout, h1)
+        film_ptr = film_all.data_ptr() + 4 * r.film_offset
+        film = self.model.use_scale_shift_norm
+        if not film:
+            # h = h + emb_out before the second GroupNorm (unet.py:253-255): one in-place pass; the statistics the
+            # conv fused into its epilogue describe the tensor before the add, so they are recomputed
+            if tape is not None:
+                raise NotImplementedError("data-gradient of ResBlocks without use_scale_shift_norm is not built")
+            self.prog.add("gd_add_emb_nhwc", C.c_void_p(h1.ptr), h1.ld, C.c_void_p(film_ptr), film_all.shape[1], n,
+                          ho * wo, r.cout)
+            self._producers.pop((h1.buf.data_ptr(), h1.off, h1.c), None)
         self.gn_stats(h1, st2)
         b = self.scratch("gn_out2", n, ho, wo, r.cout)
-        film_ptr = film_all.data_ptr() + 4 * r.film_offset
         self.gn_apply(h1, st2, self.f32(f"{k}.out_layers.0.weight"), self.f32(f"{k}.out_layers.0.bias"), b, silu=True,
-                      film=film_ptr, film_ld=film_all.shape[1])
+                      film=film_ptr if film else None, film_ld=film_all.shape[1] if film else 0)
         if r.has_skip_conv:
             assert r.mode == "none"
             w2 = pack_conv3x3(self.P[f"{k}.out_layers.3.weight"], self.P[f"{k}.skip_connection.weight"])
@@ -429,11 +436,31 @@ class Emitter:
         if tape is not None:
             tape.append(("res", r, x, st1, h1, st2, film_ptr, film_all.shape[1], out))
 
+    def resample(self, l: ResampleSpec, x: View, out: View) -> None:
+        """Downsample.op (3x3 stride-2 conv, unet.py:125-136) as a strided gather + taps=1 GEMM over K = 9*C;
+        Upsample (unet.py:100-110) as a nearest x2 copy + the regular 3x3 conv."""
+        n, c = x.n, l.ch
+        wp = pack_conv3x3(self.P[f"{l.key}.weight"])
+        bias = self.f32(f"{l.key}.bias")
+        if l.mode == "down":
+            ho, wo = (x.h - 1) // 2 + 1, (x.w - 1) // 2 + 1
+            cols = self.scratch("im2col_s2", n, ho, wo, 9 * c)
+            self.prog.add("gd_im2col3x3_s2_nhwc", C.c_void_p(x.ptr), x.ld, C.c_void_p(cols.ptr), cols.ld, n, x.h, x.w, c)
+            self.conv(cols, wp, bias, c, out, taps=1)
+        else:
+            up = self.scratch("up2", n, 2 * x.h, 2 * x.w, c)
+            self.prog.add("gd_upsample2_nhwc", C.c_void_p(x.ptr), x.ld, C.c_void_p(up.ptr), up.ld, n, x.h, x.w, c)
+            self.conv(up, wp, bias, c, out)
+
     def attn_block(self, a: AttnSpec, x: View, out: View, tape: Optional[list] = None) -> None:
         """AttentionBlock._forward (unet.py:299-305): GN, qkv 1x1, fused attention, proj 1x1 + residual."""
-        if a.ch != a.heads * 64:
-            raise NotImplementedError(
-                f"attention head dim {a.ch // a.heads} != 64: only num_head_channels=64 has a CUDA path")
+        hd = a.ch // a.heads
+        if a.ch != a.heads * hd or hd % 16 or hd > 256 or (hd > 128 and hd % 32):
+            raise NotImplementedError(f"attention head dim {a.ch}/{a.heads}: CUDA kernels exist for 16..128 in steps of "
+                                      "16 and 160 / 192 / 224 / 256")
+        if hd != 64 and tape is not None:
+            raise NotImplementedError(f"attention data-gradient exists for 64-wide heads only (got {hd}; the "
+                                      "classifier factory hard-codes 64, script_util.py:265)")
         n, h, w = x.n, x.h, x.w
         k = a.key
         st = self.stats_buf()
@@ -447,8 +474,12 @@ class Emitter:
         self.conv(g, pack_1x1(self.P[f"{k}.qkv.weight"]), self.f32(f"{k}.qkv.bias"), 3 * a.ch, qkv, taps=1)
         order = L.QKV_NEW if a.new_order else L.QKV_LEGACY
         self.keep.append(lse)
-        self.prog.add("gd_attention_fwd", C.c_void_p(qkv.ptr), qkv.ld, C.c_void_p(att.ptr), att.ld, _p(lse), n, h * w,
-                      a.heads, order)
+        if hd == 64:
+            self.prog.add("gd_attention_fwd", C.c_void_p(qkv.ptr), qkv.ld, C.c_void_p(att.ptr), att.ld, _p(lse), n, h * w,
+                          a.heads, order)
+        else:
+            self.prog.add("gd_attention_fwd_hd", C.c_void_p(qkv.ptr), qkv.ld, C.c_void_p(att.ptr), att.ld, _p(lse), n,
+                          h * w, a.heads, hd, order)
         self.conv(att, pack_1x1(self.P[f"{k}.proj_out.weight"]), self.f32(f"{k}.proj_out.bias"), a.ch, out, taps=1,
                   res=x, res_mode=L.RES_SAME)
         if tape is not None:
@@ -486,6 +517,8 @@ class UNetPlan:
                     ch = l.cout
                     if l.mode == "down":
                         hh, ww = hh // 2, ww // 2
+                elif isinstance(l, ResampleSpec):
+                    hh, ww = (hh - 1) // 2 + 1, (ww - 1) // 2 + 1
             hs_shapes.append((ch, hh, ww))
         # --- concat buffers: output block j consumes cat([h, hs.pop()]) ------------------------------
         n_out = len(spec.output_blocks)
@@ -502,6 +535,8 @@ class UNetPlan:
                     c2 = l.cout
                     if l.mode == "up":
                         h2, w2 = h2 * 2, w2 * 2
+                elif isinstance(l, ResampleSpec):
+                    h2, w2 = h2 * 2, w2 * 2
             hcur = (c2, h2, w2)
         final_view = em.act(n, hcur[1], hcur[2], hcur[0])
 
@@ -521,6 +556,10 @@ class UNetPlan:
                               (cur.h * 2, cur.w * 2) if l.mode == "up" else (cur.h, cur.w))
                     o = dst if last else em.scratch(f"blk{li % 2}", n, oh, ow, l.cout)
                     em.res_block(l, cur, o, film_all)
+                elif isinstance(l, ResampleSpec):
+                    oh, ow = ((cur.h - 1) // 2 + 1, (cur.w - 1) // 2 + 1) if l.mode == "down" else (cur.h * 2, cur.w * 2)
+                    o = dst if last else em.scratch(f"blk{li % 2}", n, oh, ow, l.ch)
+                    em.resample(l, cur, o)
                 else:
                     o = dst if last else em.scratch(f"blk{li % 2}", n, cur.h, cur.w, l.ch)
                     em.attn_block(l, cur, o)
@@ -623,6 +662,9 @@ class ClassifierPlan:
                         hh, ww = hh // 2, ww // 2
                     o = em.act(n, hh, ww, l.cout)
                     em.res_block(l, cur, o, film_all, tape)
+                elif isinstance(l, ResampleSpec):
+                    raise NotImplementedError("classifier_resblock_updown=False: the data-gradient of Downsample's "
+                                              "strided conv is not built (factory default is True, script_util.py:39)")
                 else:
                     o = em.act(n, hh, ww, l.ch)
                     em.attn_block(l, cur, o, tape)

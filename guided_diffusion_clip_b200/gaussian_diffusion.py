@@ -149,7 +149,7 @@ class GaussianDiffusion:
         raise NotImplementedError("ModelMeanType.PREVIOUS_X is not produced by any factory and has no CUDA path")
 
     def _launch_posterior(self, *, x, t, model_out, grad=None, noise=None, sample=None, pred_xstart=None, mean=None,
-                          var=None, logvar=None, clip_denoised=True, ddim=False, eta=0.0) -> None:
+                          var=None, logvar=None, clip_denoised=True, ddim=False, eta=0.0, mean_type=None) -> None:
         if x.device.type != "cuda":
             raise L.GdError("the fused posterior update only runs on CUDA; there is no CPU path")
         B, Cc = x.shape[:2]
@@ -166,7 +166,7 @@ class GaussianDiffusion:
         d.mean_out, d.var_out, d.logvar_out = ptr(mean), ptr(var), ptr(logvar)
         d.coef, d.t = self._coef_on(x.device).data_ptr(), t.data_ptr()
         d.n, d.c, d.hw = B, Cc, hw
-        d.var_type, d.mean_type = self._var_code(), self._mean_code()
+        d.var_type, d.mean_type = self._var_code(), (self._mean_code() if mean_type is None else mean_type)
         d.clip_denoised, d.ddim, d.eta = int(bool(clip_denoised)), int(bool(ddim)), float(eta)
         stream = C.c_void_p(th.cuda.current_stream().cuda_stream)
         L.check(L.load().gd_posterior_step(C.byref(d), stream), "gd_posterior_step")
@@ -214,16 +214,29 @@ class GaussianDiffusion:
 
     def p_mean_variance(self, model, x, t, clip_denoised=True, denoised_fn=None, model_kwargs=None):
         """dict(mean, variance, log_variance, pred_xstart) of p(x_{t-1} | x_t)  (gaussian_diffusion.py:232-326)."""
-        if denoised_fn is not None:
-            raise NotImplementedError("denoised_fn is a Python hook inside the fused update; not supported")
         x = x.float().contiguous()
         t = t.to(th.int64).contiguous()
         assert t.shape == (x.shape[0],)
         model_out = self._call_model(model, x, t, model_kwargs)
+        mean_type = None
+        if denoised_fn is not None:
+            model_out, mean_type = self._apply_denoised_fn(denoised_fn, x, t, model_out), L.MEAN_START_X
         mean, var, logvar, x0 = (th.empty_like(x) for _ in range(4))
         self._launch_posterior(x=x, t=t, model_out=model_out, pred_xstart=x0, mean=mean, var=var, logvar=logvar,
-                               clip_denoised=clip_denoised)
+                               clip_denoised=clip_denoised, mean_type=mean_type)
         return {"mean": mean, "variance": var, "log_variance": logvar, "pred_xstart": x0}
+
+    def _apply_denoised_fn(self, denoised_fn, x, t, model_out):
+        """process_xstart's Python hook (gaussian_diffusion.py:262-265: denoised_fn runs on the x_0 prediction BEFORE
+        the clamp).  The hook is arbitrary user code, so the fused update is split around it: one launch produces the
+        unclamped prediction, the hook runs, and the step is finished by the same kernel in START_X mode on
+        [denoised_fn(x_0), variance channels] — the reference derives everything after this point (posterior mean,
+        eps of condition_score / DDIM) from pred_xstart, never from the raw eps, so the results are identical."""
+        x0_raw = th.empty_like(x)
+        self._launch_posterior(x=x, t=t, model_out=model_out, pred_xstart=x0_raw, clip_denoised=False)
+        hooked = model_out.clone()
+        hooked[:, :x.shape[1]] = denoised_fn(x0_raw)
+        return hooked
 
     def condition_mean(self, cond_fn, p_mean_var, x, t, model_kwargs=None):
         """mean + variance * grad  (gaussian_diffusion.py:356-369); composable helper, the sampler fuses it."""
@@ -244,17 +257,18 @@ class GaussianDiffusion:
         """One reverse step = model call, optional cond_fn call, one fused kernel.  The noise is drawn by
         torch AFTER the model call and before cond_fn, in the reference's order (:430 / :585), so the RNG
         stream position per step is identical."""
-        if denoised_fn is not None:
-            raise NotImplementedError("denoised_fn is a Python hook inside the fused update; not supported")
         x = x.float().contiguous()
         t = t.to(th.int64).contiguous()
         # fast path: our own UNet (+ our own guidance object) -> the whole step is one CUDA-graph replay
         from .sampler import GraphedStepper
-        stepper = GraphedStepper.cached(self, model, cond_fn, tuple(x.shape), x.device, model_kwargs, clip_denoised,
-                                        ddim, eta)
+        stepper = None if denoised_fn is not None else GraphedStepper.cached(
+            self, model, cond_fn, tuple(x.shape), x.device, model_kwargs, clip_denoised, ddim, eta)
         if stepper is not None:
             return stepper.step(x, t, noise=noise, labels=(model_kwargs or {}).get("y"))
         model_out = self._call_model(model, x, t, model_kwargs)
+        mean_type = None
+        if denoised_fn is not None:
+            model_out, mean_type = self._apply_denoised_fn(denoised_fn, x, t, model_out), L.MEAN_START_X
         if noise is None:
             noise = th.randn_like(x)
         grad = None
@@ -262,7 +276,7 @@ class GaussianDiffusion:
             grad = self._wrap(cond_fn)(x, self._scale_timesteps(t), **model_kwargs).float().contiguous()
         sample, x0 = th.empty_like(x), th.empty_like(x)
         self._launch_posterior(x=x, t=t, model_out=model_out, grad=grad, noise=noise, sample=sample, pred_xstart=x0,
-                               clip_denoised=clip_denoised, ddim=ddim, eta=eta)
+                               clip_denoised=clip_denoised, ddim=ddim, eta=eta, mean_type=mean_type)
         return {"sample": sample, "pred_xstart": x0}
 
     def p_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None):

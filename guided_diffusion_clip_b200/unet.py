@@ -5,8 +5,10 @@ kernels (engine.py) through the C ABI.  torch.nn.Module is used only as the para
 `load_state_dict / state_dict / to / parameters / eval` behave exactly like the reference objects.
 
 Differences that are deliberate and documented in DESIGN.md:
-  * only dims=2, resblock_updown=True style resampling, use_scale_shift_norm=True and head dim 64 have
-    CUDA paths (every BASELINE config); anything else raises NotImplementedError at plan time.
+  * only dims=2 has a CUDA path.  The UNet forward covers both resampling styles (resblock_updown=True: pooled /
+    upsampled ResBlocks; False: Downsample / Upsample with conv_resample, unet.py:88-136), both ResBlock
+    conditioning styles (FiLM or additive embedding, unet.py:248-255) and head widths 16..256; the classifier
+    data-gradient is built for the factory's classifier family (resblock_updown, FiLM, 64-wide heads).
   * activations are always stored fp16 (fp32 accumulate); `use_fp16=False` models run the same kernels.
 """
 from __future__ import annotations
@@ -40,6 +42,14 @@ class ResSpec:
     @property
     def has_skip_conv(self) -> bool:
         return self.cin != self.cout
+
+
+@dataclass
+class ResampleSpec:
+    """Downsample.op (3x3 stride-2 conv, unet.py:125-136) or Upsample.conv after nearest x2 (unet.py:91-110)."""
+    key: str   # parameter prefix including ".op" / ".conv"
+    ch: int
+    mode: str  # "down" | "up"
 
 
 @dataclass
@@ -104,6 +114,11 @@ def _add_res(ps: _ParamSpec, key: str, cin: int, cout: int, emb_dim: int, scale_
         ps.add(f"{key}.skip_connection.bias", (cout,), "fan_in:%d" % cin, torso)
 
 
+def _add_resample(ps: _ParamSpec, key: str, ch: int):
+    ps.add(f"{key}.weight", (ch, ch, 3, 3), "fan_in", True)
+    ps.add(f"{key}.bias", (ch,), "fan_in:%d" % (ch * 9), True)
+
+
 def _add_attn(ps: _ParamSpec, key: str, ch: int, torso: bool):
     ps.add(f"{key}.norm.weight", (ch,), "ones")
     ps.add(f"{key}.norm.bias", (ch,), "zeros")
@@ -117,11 +132,13 @@ def build_torso(
     *, in_channels: int, model_channels: int, num_res_blocks: int, attention_resolutions, channel_mult,
     num_heads: int, num_head_channels: int, num_heads_upsample: int, use_scale_shift_norm: bool,
     resblock_updown: bool, use_new_attention_order: bool, decoder: bool, ps: _ParamSpec,
+    conv_resample: bool = True,
 ) -> TorsoSpec:
     """Walk the same construction order as unet.py:481-611 (UNet) / :739-823 (encoder)."""
-    if not resblock_updown and len(channel_mult) > 1:
+    if not resblock_updown and not conv_resample and len(channel_mult) > 1:
         raise NotImplementedError(
-            "only resblock_updown=True has a CUDA path (Downsample/Upsample with conv_resample are not built)")
+            "conv_resample=False (parameter-free AvgPool2d / nearest resampling layers between levels) has no CUDA "
+            "path; no factory of the reference passes it (script_util.py:130-167)")
     emb_dim = model_channels * 4
     spec = TorsoSpec(model_channels=model_channels, emb_dim=emb_dim, in_channels=in_channels)
     ch = int(channel_mult[0] * model_channels)
@@ -146,8 +163,12 @@ def build_torso(
             chans.append(ch)
         if level != len(channel_mult) - 1:
             idx = len(spec.input_blocks)
-            r = ResSpec(f"input_blocks.{idx}.0", ch, ch, "down")
-            _add_res(ps, r.key, ch, ch, emb_dim, use_scale_shift_norm, True)
+            if resblock_updown:
+                r = ResSpec(f"input_blocks.{idx}.0", ch, ch, "down")
+                _add_res(ps, r.key, ch, ch, emb_dim, use_scale_shift_norm, True)
+            else:
+                r = ResampleSpec(f"input_blocks.{idx}.0.op", ch, "down")
+                _add_resample(ps, r.key, ch)
             spec.input_blocks.append([r])
             chans.append(ch)
             ds *= 2
@@ -173,8 +194,12 @@ def build_torso(
                     _add_attn(ps, a.key, ch, True)
                     layers.append(a)
                 if level and i == num_res_blocks:
-                    r = ResSpec(f"output_blocks.{idx}.{len(layers)}", ch, ch, "up")
-                    _add_res(ps, r.key, ch, ch, emb_dim, use_scale_shift_norm, True)
+                    if resblock_updown:
+                        r = ResSpec(f"output_blocks.{idx}.{len(layers)}", ch, ch, "up")
+                        _add_res(ps, r.key, ch, ch, emb_dim, use_scale_shift_norm, True)
+                    else:
+                        r = ResampleSpec(f"output_blocks.{idx}.{len(layers)}.conv", ch, "up")
+                        _add_resample(ps, r.key, ch)
                     layers.append(r)
                     ds //= 2
                 spec.output_blocks.append(layers)
@@ -318,7 +343,7 @@ class UNetModel(_GdModule):
             attention_resolutions=self.attention_resolutions, channel_mult=self.channel_mult, num_heads=num_heads,
             num_head_channels=num_head_channels, num_heads_upsample=num_heads_upsample,
             use_scale_shift_norm=use_scale_shift_norm, resblock_updown=resblock_updown,
-            use_new_attention_order=use_new_attention_order, decoder=True, ps=ps)
+            use_new_attention_order=use_new_attention_order, decoder=True, ps=ps, conv_resample=conv_resample)
         ps.add("out.0.weight", (self.spec.out_ch_in,), "ones")
         ps.add("out.0.bias", (self.spec.out_ch_in,), "zeros")
         ps.add("out.2.weight", (out_channels, self.spec.out_ch_in, 3, 3), "zeros")  # zero_module, unet.py:616
@@ -438,7 +463,7 @@ class EncoderUNetModel(_GdModule):
             attention_resolutions=self.attention_resolutions, channel_mult=self.channel_mult, num_heads=num_heads,
             num_head_channels=num_head_channels, num_heads_upsample=num_heads_upsample,
             use_scale_shift_norm=use_scale_shift_norm, resblock_updown=resblock_updown,
-            use_new_attention_order=use_new_attention_order, decoder=False, ps=ps)
+            use_new_attention_order=use_new_attention_order, decoder=False, ps=ps, conv_resample=conv_resample)
         ch = self.spec.out_ch_in
         ds = 2 ** (len(self.channel_mult) - 1)
         self.pool_spatial = image_size // ds

@@ -108,6 +108,19 @@ typedef struct {
 } gd_conv_in_desc;
 int gd_conv_in3x3(const gd_conv_in_desc* desc, void* stream);
 
+/* conv_resample layers and FiLM-less ResBlocks of models built with the factory defaults resblock_updown=False /
+ * use_scale_shift_norm=False-style checkpoints (script_util.py:57-60).  fp16 NHWC views, c % 8 == 0.
+ *   gd_im2col3x3_s2_nhwc: Downsample.op = conv3x3 stride 2 pad 1 (unet.py:125-136) as a gather to
+ *     out[n][ho][wo][tap*c + ci] = x[n][2*yo+ky-1][2*xo+kx-1][ci] (0 outside), ho = (h-1)/2+1, followed by
+ *     gd_conv_igemm with taps = 1 over K = 9*c (same packed weight order as a 3x3 conv);
+ *   gd_upsample2_nhwc: F.interpolate(scale_factor=2, mode="nearest") of Upsample.forward (unet.py:100-110);
+ *   gd_add_emb_nhwc: h += emb_out[n][c] in place (unet.py:253-254), emb fp32 with row stride ld_emb. */
+int gd_im2col3x3_s2_nhwc(const void* x, int32_t ld, void* out, int32_t ld_out, int32_t n, int32_t h, int32_t w, int32_t c,
+                         void* stream);
+int gd_upsample2_nhwc(const void* x, int32_t ld, void* out, int32_t ld_out, int32_t n, int32_t h, int32_t w, int32_t c,
+                      void* stream);
+int gd_add_emb_nhwc(void* x, int32_t ld, const float* emb, int32_t ld_emb, int32_t n, int32_t hw, int32_t c, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * GroupNorm32 (+SiLU) (+FiLM scale/shift) (+avgpool2 / nearest-upsample2), nn.py:17-19,93-100 with
  * unet.py:184,200-208,248-252 and the h_upd of unet.py:191-195.  Two launches: statistics, then apply.
@@ -143,6 +156,13 @@ int gd_attention_fwd(const void* qkv, int32_t ld_qkv, void* out, int32_t ld_out,
 int gd_attention_bwd(const void* qkv, int32_t ld_qkv, const void* out, int32_t ld_out, const void* dout,
                      int32_t ld_dout, const float* lse, float* delta_ws, void* dqkv, int32_t ld_dqkv, int32_t n,
                      int32_t t, int32_t heads, int32_t order, void* stream);
+
+/* Forward for head widths other than 64 (16..128 in steps of 16, 160, 192, 224, 256): the reference's factory default
+ * num_heads=4 / num_head_channels=-1 (script_util.py:54-56) gives heads of ch/4 channels (unet.py:279-285).  Same
+ * contract as gd_attention_fwd with channel count heads*head_dim, scale head_dim^-1/2 on the scores; any t >= 1
+ * (ragged last tiles are masked).  Forward only. */
+int gd_attention_fwd_hd(const void* qkv, int32_t ld_qkv, void* out, int32_t ld_out, float* lse, int32_t n, int32_t t,
+                        int32_t heads, int32_t head_dim, int32_t order, void* stream);
 
 /* Same kernels for a sequence padded to t (multiple of 64) of which only the first t_valid tokens exist (ViT: 197 of
  * 256): keys >= t_valid get probability 0 in the forward and in both gradient kernels; padded query rows are computed

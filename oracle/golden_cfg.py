@@ -213,3 +213,60 @@ def clip_inputs():
     x = th.randn(2, 3, CLIP_INPUT, CLIP_INPUT, generator=g).clamp(-1, 1)
     txt = th.randn(2, CLIP_TINY["projection_dim"], generator=g)
     return x, txt / txt.norm(dim=-1, keepdim=True)
+
+
+# ---- model variants outside the BASELINE configs: the reference factory's own defaults (script_util.py:44-62:
+# num_heads=4 / num_head_channels=-1, resblock_updown=False -> Downsample / Upsample with conv_resample) and
+# improved-diffusion style blocks (use_scale_shift_norm=False); plus the denoised_fn hook of p_mean_variance -------
+VAR_SEED = 41
+VARIANT_KW = {
+    # additive embedding, conv resampling, heads of 48 (192/4) and 64 (256/4) channels, legacy qkv order
+    "plain": dict(image_size=IMAGE, num_channels=64, num_res_blocks=1, channel_mult="", learn_sigma=True,
+                  class_cond=True, use_checkpoint=False, attention_resolutions="16,8", num_heads=4,
+                  num_head_channels=-1, num_heads_upsample=-1, use_scale_shift_norm=False, dropout=0.0,
+                  resblock_updown=False, use_fp16=False, use_new_attention_order=False),
+    # model_and_diffusion_defaults() (script_util.py:44-62) with class_cond: 128 channels, 2 blocks per level,
+    # heads of 96 (384/4) and 128 (512/4) channels, FiLM, conv resampling
+    "defaults": dict(image_size=IMAGE, num_channels=128, num_res_blocks=2, channel_mult="", learn_sigma=False,
+                     class_cond=True, use_checkpoint=False, attention_resolutions="16,8", num_heads=4,
+                     num_head_channels=-1, num_heads_upsample=-1, use_scale_shift_norm=True, dropout=0.0,
+                     resblock_updown=False, use_fp16=False, use_new_attention_order=False),
+    # new qkv order with two wide heads upstream and one 256-wide head at the top (num_heads_upsample differs)
+    "wide_heads": dict(image_size=IMAGE, num_channels=64, num_res_blocks=1, channel_mult="", learn_sigma=True,
+                       class_cond=False, use_checkpoint=False, attention_resolutions="8", num_heads=1,
+                       num_head_channels=-1, num_heads_upsample=2, use_scale_shift_norm=True, dropout=0.0,
+                       resblock_updown=True, use_fp16=False, use_new_attention_order=True),
+}
+VARIANT_STRUCT = {
+    "plain": dict(num_res_blocks=1, channel_mult_len=4, num_heads=4, new_order=False),
+    "defaults": dict(num_res_blocks=2, channel_mult_len=4, num_heads=4, new_order=False),
+    "wide_heads": dict(num_res_blocks=1, channel_mult_len=4, num_heads=1, num_heads_upsample=2, new_order=True),
+}
+
+
+def ref_variant_kwargs(name: str):
+    """Constructor kwargs of the reference unet.UNetModel that script_util.create_model derives from VARIANT_KW[name]
+    (script_util.py:130-167; upstream nn.Embedding label semantics, as for ref_unet_kwargs)."""
+    kw = VARIANT_KW[name]
+    ds = tuple(IMAGE // int(r) for r in kw["attention_resolutions"].split(","))
+    return dict(image_size=IMAGE, in_channels=3, model_channels=kw["num_channels"],
+                out_channels=6 if kw["learn_sigma"] else 3, num_res_blocks=kw["num_res_blocks"],
+                attention_resolutions=ds, dropout=0.0, channel_mult=(1, 2, 3, 4),
+                num_classes=1000 if kw["class_cond"] else None, use_checkpoint=False, use_fp16=False,
+                num_heads=kw["num_heads"], num_head_channels=kw["num_head_channels"],
+                num_heads_upsample=kw["num_heads_upsample"], use_scale_shift_norm=kw["use_scale_shift_norm"],
+                resblock_updown=kw["resblock_updown"], use_new_attention_order=kw["use_new_attention_order"])
+
+
+def variant_inputs(name: str):
+    g = th.Generator().manual_seed(INPUT_SEED + 10 + sorted(VARIANT_KW).index(name))
+    x = th.randn(2, 3, IMAGE, IMAGE, generator=g)
+    return x, th.tensor([250, 7]), (th.tensor([17, 800]) if VARIANT_KW[name]["class_cond"] else None)
+
+
+def denoised_fn_example(x0: th.Tensor) -> th.Tensor:
+    """A non-trivial denoised_fn (gaussian_diffusion.py:262-265 applies it before the clamp)."""
+    return 0.8 * x0 + 0.1 * x0.flip(-1)
+
+
+DENOISED_CASES = ["ddpm_guided_mid", "ddim_guided_eta0", "ddim_xstart_t0"]

@@ -91,7 +91,8 @@ class Tables:
     def _f(self, arr, i) -> th.Tensor:
         return th.tensor(arr[i]).float()  # float64 -> float32, like `.float()` at gaussian_diffusion.py:914
 
-    def mean_variance(self, model_out: th.Tensor, x: th.Tensor, i: int, clip: bool = True) -> Dict[str, th.Tensor]:
+    def mean_variance(self, model_out: th.Tensor, x: th.Tensor, i: int, clip: bool = True,
+                      denoised_fn=None) -> Dict[str, th.Tensor]:
         C = x.shape[1]
         if self.learn_sigma:
             eps, v = model_out[:, :C], model_out[:, C:]
@@ -108,21 +109,24 @@ class Tables:
             var = self._f(va, i).expand(x.shape)
             logvar = self._f(lv, i).expand(x.shape)
         x0 = eps if self.predict_xstart else self._f(self.sqrt_recip, i) * x - self._f(self.sqrt_recipm1, i) * eps
+        if denoised_fn is not None:  # process_xstart, gaussian_diffusion.py:262-265
+            x0 = denoised_fn(x0)
         if clip:
             x0 = x0.clamp(-1, 1)
         mean = self._f(self.coef1, i) * x0 + self._f(self.coef2, i) * x
         return {"mean": mean, "variance": var, "log_variance": logvar, "pred_xstart": x0}
 
-    def p_sample(self, model_out, x, i, z, grad: Optional[th.Tensor] = None, clip: bool = True):
-        o = self.mean_variance(model_out, x, i, clip)
+    def p_sample(self, model_out, x, i, z, grad: Optional[th.Tensor] = None, clip: bool = True, denoised_fn=None):
+        o = self.mean_variance(model_out, x, i, clip, denoised_fn)
         mean = o["mean"]
         if grad is not None:
             mean = mean.float() + o["variance"] * grad.float()
         nz = 0.0 if i == 0 else 1.0
         return {"sample": mean + nz * th.exp(0.5 * o["log_variance"]) * z, "pred_xstart": o["pred_xstart"]}
 
-    def ddim_sample(self, model_out, x, i, z, grad: Optional[th.Tensor] = None, eta: float = 0.0, clip: bool = True):
-        o = self.mean_variance(model_out, x, i, clip)
+    def ddim_sample(self, model_out, x, i, z, grad: Optional[th.Tensor] = None, eta: float = 0.0, clip: bool = True,
+                    denoised_fn=None):
+        o = self.mean_variance(model_out, x, i, clip, denoised_fn)
         sr, srm1 = self._f(self.sqrt_recip, i), self._f(self.sqrt_recipm1, i)
         ab, abp = self._f(self.acp, i), self._f(self.acp_prev, i)
         x0 = o["pred_xstart"]

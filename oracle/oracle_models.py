@@ -53,9 +53,12 @@ def res_block(x, emb, sd, key: str, mode: str):
     h = _conv(h, sd, key + ".in_layers.2", 1)
     e = F.linear(F.silu(emb), sd[key + ".emb_layers.1.weight"].float(), sd[key + ".emb_layers.1.bias"].float())
     cout = h.shape[1]
-    assert e.shape[1] == 2 * cout, "oracle covers use_scale_shift_norm=True only"
-    scale, shift = e[:, :cout, None, None], e[:, cout:, None, None]
-    h = _gn(h, sd, key + ".out_layers.0") * (1 + scale) + shift
+    if e.shape[1] == 2 * cout:  # use_scale_shift_norm (unet.py:248-252)
+        scale, shift = e[:, :cout, None, None], e[:, cout:, None, None]
+        h = _gn(h, sd, key + ".out_layers.0") * (1 + scale) + shift
+    else:                       # additive embedding, then the plain out_layers (unet.py:253-255)
+        assert e.shape[1] == cout
+        h = _gn(h + e[:, :, None, None], sd, key + ".out_layers.0")
     h = _conv(F.silu(h), sd, key + ".out_layers.3", 1)
     if key + ".skip_connection.weight" in sd:
         x = _conv(x, sd, key + ".skip_connection", 0)
@@ -78,10 +81,11 @@ def qkv_attention(qkv: th.Tensor, heads: int, new_order: bool) -> th.Tensor:
 
 
 def attn_block(x, sd, key: str, head_dim: int, new_order: bool):
+    """head_dim > 0: num_head_channels; head_dim < 0: a fixed head count -head_dim (num_head_channels=-1, unet.py:279-285)."""
     n, c, hh, ww = x.shape
     g = _gn(x, sd, key + ".norm")
     qkv = _conv(g, sd, key + ".qkv", 0).reshape(n, 3 * c, hh * ww)
-    a = qkv_attention(qkv, c // head_dim, new_order).reshape(n, c, hh, ww)
+    a = qkv_attention(qkv, c // head_dim if head_dim > 0 else -head_dim, new_order).reshape(n, c, hh, ww)
     return x + _conv(a, sd, key + ".proj_out", 0)
 
 
@@ -96,6 +100,10 @@ def _run_layers(h, emb, sd, layer_keys: List[str], head_dim: int, new_order: boo
             h = attn_block(h, sd, lk, head_dim, new_order)
         elif lk + ".in_layers.0.weight" in sd:
             h = res_block(h, emb, sd, lk, modes.get(lk, "none"))
+        elif lk + ".op.weight" in sd:    # Downsample with conv_resample: 3x3 stride 2 (unet.py:125-136)
+            h = F.conv2d(h, sd[lk + ".op.weight"].float(), sd[lk + ".op.bias"].float(), stride=2, padding=1)
+        elif lk + ".conv.weight" in sd:  # Upsample: nearest x2, then 3x3 conv (unet.py:100-110)
+            h = _conv(F.interpolate(h, scale_factor=2, mode="nearest"), sd, lk + ".conv", 1)
         else:
             h = _conv(h, sd, lk, 1)
     return h
@@ -139,8 +147,13 @@ def _embed(sd, t, y, model_channels):
 
 
 def unet_forward(sd, x, t, y=None, *, num_res_blocks: int, channel_mult_len: int, head_dim: int = 64,
-                 new_order: bool = False, low_res: Optional[th.Tensor] = None) -> th.Tensor:
+                 new_order: bool = False, low_res: Optional[th.Tensor] = None, num_heads: int = 0,
+                 num_heads_upsample: int = 0) -> th.Tensor:
+    """num_heads > 0 selects num_head_channels=-1 semantics: a fixed head count (num_heads_upsample in the decoder)."""
     sd = {k: v.float() for k, v in sd.items()}
+    hd_up = head_dim
+    if num_heads > 0:
+        head_dim, hd_up = -num_heads, -(num_heads_upsample or num_heads)
     if low_res is not None:
         x = th.cat([x, F.interpolate(low_res, x.shape[2:], mode="bilinear")], dim=1)
     mc = sd["time_embed.0.weight"].shape[1]
@@ -154,7 +167,7 @@ def unet_forward(sd, x, t, y=None, *, num_res_blocks: int, channel_mult_len: int
     h = _run_layers(h, emb, sd, _block_layers(sd, "middle_block"), head_dim, new_order, modes)
     for j in range(_n_blocks(sd, "output_blocks")):
         h = th.cat([h, hs.pop()], dim=1)
-        h = _run_layers(h, emb, sd, _block_layers(sd, f"output_blocks.{j}"), head_dim, new_order, modes)
+        h = _run_layers(h, emb, sd, _block_layers(sd, f"output_blocks.{j}"), hd_up, new_order, modes)
     h = F.silu(_gn(h, sd, "out.0"))
     return _conv(h, sd, "out.2", 1)
 

@@ -133,7 +133,8 @@ def test_zero_modules_and_fp16_conversion():
 
 def test_unsupported_configurations_raise():
     with pytest.raises(NotImplementedError):
-        su.create_model(64, 64, 1, resblock_updown=False, num_head_channels=64)
+        from guided_diffusion_clip_b200.unet import UNetModel
+        UNetModel(64, 3, 64, 6, 1, (4,), conv_resample=False, num_head_channels=64)
     with pytest.raises(ValueError):
         su.create_model(96, 64, 1)
     with pytest.raises(NotImplementedError):
