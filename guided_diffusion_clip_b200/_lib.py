@@ -17,7 +17,8 @@ QKV_LEGACY, QKV_NEW = 0, 1
 VAR_LEARNED_RANGE, VAR_FIXED, VAR_LEARNED = 0, 1, 2
 MEAN_EPSILON, MEAN_START_X = 0, 1
 (COEF_SQRT_RECIP_ACP, COEF_SQRT_RECIPM1_ACP, COEF_POST_MEAN1, COEF_POST_MEAN2, COEF_LOG_BETA, COEF_POST_LOGVAR,
- COEF_FIXED_VAR, COEF_FIXED_LOGVAR, COEF_ACP, COEF_ACP_PREV, COEF_NONZERO) = range(11)
+ COEF_FIXED_VAR, COEF_FIXED_LOGVAR, COEF_ACP, COEF_ACP_PREV, COEF_NONZERO, COEF_ACP_NEXT) = range(12)
+DDIM_REVERSE = 2
 COEF_STRIDE = 12
 
 i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p

@@ -47,6 +47,7 @@ __global__ void posterior_kernel(const PostArgs p) {
     const float max_log = co[GD_COEF_LOG_BETA], min_log = co[GD_COEF_POST_LOGVAR];
     const float acp = co[GD_COEF_ACP], acp_prev = co[GD_COEF_ACP_PREV];
     const float nonzero = co[GD_COEF_NONZERO];
+    const float acp_next = co[GD_COEF_ACP_NEXT];
     const size_t mo = b * static_cast<size_t>(out_c) * p.hw + r;
     const float x = p.x[i];
     const float m_out = p.model_out[mo];
@@ -74,6 +75,12 @@ __global__ void posterior_kernel(const PostArgs p) {
     if (p.mean_out != nullptr) p.mean_out[i] = mean;
     if (p.var_out != nullptr) p.var_out[i] = var;
     if (p.logvar_out != nullptr) p.logvar_out[i] = logvar;
+    if (p.ddim == GD_DDIM_REVERSE) {  // ddim_reverse_sample (gaussian_diffusion.py:596-632): deterministic, x_t -> x_{t+1}
+      const float e = __fdiv_rn(sub(mul(sr, x), x0), srm1);
+      p.sample[i] = add(mul(x0, sqrtf(acp_next)), mul(sqrtf(sub(1.0f, acp_next)), e));
+      if (p.pred_xstart != nullptr) p.pred_xstart[i] = x0;
+      continue;
+    }
     if (p.noise == nullptr) {  // p_mean_variance only
       if (p.pred_xstart != nullptr) p.pred_xstart[i] = x0;
       continue;
@@ -381,6 +388,9 @@ extern "C" int gd_posterior_step(const gd_posterior_desc* d, void* stream) {
   GD_REQUIRE(d != nullptr, "gd_posterior_step: null descriptor");
   GD_REQUIRE(d->x && d->model_out && d->coef && d->t, "gd_posterior_step: null pointer");
   GD_REQUIRE(d->noise == nullptr || d->sample != nullptr, "gd_posterior_step: noise given but no sample output");
+  GD_REQUIRE(d->ddim >= 0 && d->ddim <= GD_DDIM_REVERSE, "gd_posterior_step: ddim must be 0, 1 or GD_DDIM_REVERSE");
+  GD_REQUIRE(d->ddim != GD_DDIM_REVERSE || (d->sample != nullptr && d->eta == 0.0f && d->grad == nullptr),
+             "gd_posterior_step: the reverse ODE step needs a sample output, eta == 0 and takes no guidance gradient");
   GD_REQUIRE(d->n > 0 && d->c > 0 && d->hw > 0, "gd_posterior_step: bad shape");
   GD_REQUIRE(d->var_type >= GD_VAR_LEARNED_RANGE && d->var_type <= GD_VAR_LEARNED, "gd_posterior_step: bad var_type");
   GD_REQUIRE(d->mean_type == GD_MEAN_EPSILON || d->mean_type == GD_MEAN_START_X,

@@ -127,6 +127,7 @@ class GaussianDiffusion:
         tab[:, L.COEF_ACP] = self.alphas_cumprod
         tab[:, L.COEF_ACP_PREV] = self.alphas_cumprod_prev
         tab[:, L.COEF_NONZERO] = (np.arange(T) != 0).astype(np.float64)
+        tab[:, L.COEF_ACP_NEXT] = self.alphas_cumprod_next
         return tab.astype(np.float32)
 
     def _coef_on(self, device) -> th.Tensor:
@@ -167,7 +168,7 @@ class GaussianDiffusion:
         d.coef, d.t = self._coef_on(x.device).data_ptr(), t.data_ptr()
         d.n, d.c, d.hw = B, Cc, hw
         d.var_type, d.mean_type = self._var_code(), (self._mean_code() if mean_type is None else mean_type)
-        d.clip_denoised, d.ddim, d.eta = int(bool(clip_denoised)), int(bool(ddim)), float(eta)
+        d.clip_denoised, d.ddim, d.eta = int(bool(clip_denoised)), int(ddim), float(eta)
         stream = C.c_void_p(th.cuda.current_stream().cuda_stream)
         L.check(L.load().gd_posterior_step(C.byref(d), stream), "gd_posterior_step")
 
@@ -180,6 +181,13 @@ class GaussianDiffusion:
         assert noise.shape == x_start.shape
         return (_extract_into_tensor(self.sqrt_alphas_cumprod, t, x_start.shape) * x_start
                 + _extract_into_tensor(self.sqrt_one_minus_alphas_cumprod, t, x_start.shape) * noise)
+
+    def q_mean_variance(self, x_start, t):
+        """q(x_t | x_0) moments (gaussian_diffusion.py:171-186); composable helper."""
+        mean = _extract_into_tensor(self.sqrt_alphas_cumprod, t, x_start.shape) * x_start
+        variance = _extract_into_tensor(1.0 - self.alphas_cumprod, t, x_start.shape)
+        log_variance = _extract_into_tensor(self.log_one_minus_alphas_cumprod, t, x_start.shape)
+        return mean, variance, log_variance
 
     def q_posterior_mean_variance(self, x_start, x_t, t):
         mean = (_extract_into_tensor(self.posterior_mean_coef1, t, x_t.shape) * x_start
@@ -287,6 +295,20 @@ class GaussianDiffusion:
                     eta=0.0):
         """DDIM step (gaussian_diffusion.py:546-594)."""
         return self._sample_step(model, x, t, clip_denoised, denoised_fn, cond_fn, model_kwargs, True, eta)
+
+    def ddim_reverse_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, model_kwargs=None, eta=0.0):
+        """x_{t+1} from x_t with the DDIM reverse ODE (gaussian_diffusion.py:596-632): model call + one launch."""
+        assert eta == 0.0, "Reverse ODE only for deterministic path"
+        x = x.float().contiguous()
+        t = t.to(th.int64).contiguous()
+        model_out = self._call_model(model, x, t, model_kwargs)
+        mean_type = None
+        if denoised_fn is not None:
+            model_out, mean_type = self._apply_denoised_fn(denoised_fn, x, t, model_out), L.MEAN_START_X
+        sample, x0 = th.empty_like(x), th.empty_like(x)
+        self._launch_posterior(x=x, t=t, model_out=model_out, sample=sample, pred_xstart=x0,
+                               clip_denoised=clip_denoised, ddim=L.DDIM_REVERSE, mean_type=mean_type)
+        return {"sample": sample, "pred_xstart": x0}
 
     # ------------------------------------------------------------------------------------------
     # loops

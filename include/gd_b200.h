@@ -251,6 +251,7 @@ enum {
   GD_COEF_ACP = 8,              /* alphas_cumprod                 :141 */
   GD_COEF_ACP_PREV = 9,         /* alphas_cumprod_prev            :142 */
   GD_COEF_NONZERO = 10,         /* 1.0 if t != 0 else 0.0         :431-433 */
+  GD_COEF_ACP_NEXT = 11,        /* alphas_cumprod_next            :143 (ddim_reverse_sample :596-632) */
   GD_COEF_STRIDE = 12
 };
 enum { GD_VAR_LEARNED_RANGE = 0, GD_VAR_FIXED = 1, GD_VAR_LEARNED = 2 };
@@ -269,9 +270,10 @@ typedef struct gd_posterior_desc {
   const int64_t* t;
   int32_t n, c, hw;
   int32_t var_type, mean_type, clip_denoised;
-  int32_t ddim;
+  int32_t ddim;           /* 0 ancestral p_sample, 1 ddim_sample, GD_DDIM_REVERSE ddim_reverse_sample (no noise / grad) */
   float eta;
 } gd_posterior_desc;
+enum { GD_DDIM_REVERSE = 2 };
 int gd_posterior_step(const gd_posterior_desc* desc, void* stream);
 
 /* ((x+1)*127.5).clamp(0,255).to(uint8) NCHW -> NHWC (scripts/classifier_sample.py:87-89; truncation). */

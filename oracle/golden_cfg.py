@@ -270,3 +270,7 @@ def denoised_fn_example(x0: th.Tensor) -> th.Tensor:
 
 
 DENOISED_CASES = ["ddpm_guided_mid", "ddim_guided_eta0", "ddim_xstart_t0"]
+
+# ddim_reverse_sample (gaussian_diffusion.py:596-632): (STEP_CASES entry whose diffusion / inputs are reused, step index)
+REVERSE_CASES = {"rev_eps_mid": ("ddim_guided_eta0", 30), "rev_eps_last": ("ddim_guided_eta0", 49),
+                 "rev_xstart_t0": ("ddim_xstart_t0", 0), "rev_learned": ("ddim_plain_eta1", 12)}

@@ -50,6 +50,12 @@ def main():
         out[f"denoised_{name}_sample"] = r["sample"].numpy()
         out[f"denoised_{name}_x0"] = r["pred_xstart"].numpy()
         out[f"denoised_{name}_mean"] = pmv["mean"].numpy()
+    for name, (step, i) in cfg.REVERSE_CASES.items():
+        d = rsu.create_gaussian_diffusion(**cfg.STEP_CASES[step]["diffusion"])
+        xs, mo, _, _ = cfg.step_inputs(step)
+        r = d.ddim_reverse_sample(lambda x_, t_, **k: mo, xs, th.tensor([i] * xs.shape[0]), model_kwargs={})
+        out[f"reverse_{name}_sample"] = r["sample"].numpy()
+        out[f"reverse_{name}_x0"] = r["pred_xstart"].numpy()
     path = os.path.join(ROOT, "tests", "golden", "variants_golden.npz")
     np.savez_compressed(path, **out)
     for k, v in out.items():

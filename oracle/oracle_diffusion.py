@@ -141,6 +141,18 @@ class Tables:
         return {"sample": mean_pred + nz * sigma * z, "pred_xstart": x0}
 
 
+def _ddim_reverse(self, model_out, x, i, clip: bool = True):
+    """ddim_reverse_sample, gaussian_diffusion.py:596-632 (eta = 0)."""
+    o = self.mean_variance(model_out, x, i, clip)
+    sr, srm1 = self._f(self.sqrt_recip, i), self._f(self.sqrt_recipm1, i)
+    eps = (sr * x - o["pred_xstart"]) / srm1
+    nxt = self._f(np.append(self.acp[1:], 0.0), i)
+    return {"sample": o["pred_xstart"] * th.sqrt(nxt) + th.sqrt(1 - nxt) * eps, "pred_xstart": o["pred_xstart"]}
+
+
+Tables.ddim_reverse_sample = _ddim_reverse
+
+
 def to_uint8_nhwc(sample: th.Tensor) -> th.Tensor:
     """scripts/classifier_sample.py:87-89."""
     return ((sample + 1) * 127.5).clamp(0, 255).to(th.uint8).permute(0, 2, 3, 1).contiguous()

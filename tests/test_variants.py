@@ -68,6 +68,16 @@ def test_denoised_fn_oracle_bit_exact(V, name):
     assert th.equal(tab.mean_variance(mo, xs, i, denoised_fn=fn)["mean"], th.from_numpy(V[f"denoised_{name}_mean"]))
 
 
+@pytest.mark.parametrize("name", sorted(cfg.REVERSE_CASES))
+def test_ddim_reverse_oracle_bit_exact(V, name):
+    step, i = cfg.REVERSE_CASES[name]
+    tab = _tables(cfg.STEP_CASES[step]["diffusion"])
+    xs, mo, _, _ = cfg.step_inputs(step)
+    r = tab.ddim_reverse_sample(mo, xs, i)
+    assert th.equal(r["sample"], th.from_numpy(V[f"reverse_{name}_sample"]))
+    assert th.equal(r["pred_xstart"], th.from_numpy(V[f"reverse_{name}_x0"]))
+
+
 def test_factory_defaults_build_a_model():
     """create_model_and_diffusion(**model_and_diffusion_defaults()) — the call every reference script makes — builds."""
     model, diffusion = su.create_model_and_diffusion(**su.model_and_diffusion_defaults())
@@ -210,3 +220,18 @@ def test_denoised_fn_matches_reference(lib, V, name):
     out = (d.ddim_sample if kw["ddim"] else d.p_sample)(model, xs, t, denoised_fn=cfg.denoised_fn_example, cond_fn=cond,
                                                        model_kwargs={})
     assert out["sample"].shape == xs.shape and bool(th.isfinite(out["sample"]).all())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(cfg.REVERSE_CASES))
+def test_ddim_reverse_sample_matches_reference(lib, V, name):
+    step, i = cfg.REVERSE_CASES[name]
+    d = su.create_gaussian_diffusion(**cfg.STEP_CASES[step]["diffusion"])
+    xs, mo, _, _ = (v.cuda() if isinstance(v, th.Tensor) else v for v in cfg.step_inputs(step))
+    r = d.ddim_reverse_sample(lambda x, ts, **k: mo, xs, th.tensor([i] * xs.shape[0], device="cuda"), model_kwargs={})
+    for key, got in (("sample", r["sample"]), ("x0", r["pred_xstart"])):
+        err = _rel(got, th.from_numpy(V[f"reverse_{name}_{key}"]).cuda())
+        print(f"ddim_reverse {name} {key}: rel err {err:.2e}")
+        assert err < 2e-6
+    with pytest.raises(AssertionError):
+        d.ddim_reverse_sample(lambda x, ts, **k: mo, xs, th.tensor([i] * xs.shape[0], device="cuda"), eta=0.5)
