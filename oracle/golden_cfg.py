@@ -274,3 +274,33 @@ DENOISED_CASES = ["ddpm_guided_mid", "ddim_guided_eta0", "ddim_xstart_t0"]
 # ddim_reverse_sample (gaussian_diffusion.py:596-632): (STEP_CASES entry whose diffusion / inputs are reused, step index)
 REVERSE_CASES = {"rev_eps_mid": ("ddim_guided_eta0", 30), "rev_eps_last": ("ddim_guided_eta0", 49),
                  "rev_xstart_t0": ("ddim_xstart_t0", 0), "rev_learned": ("ddim_plain_eta1", 12)}
+
+
+# ---- BASELINE configs[0] at FULL size: 64x64 class-conditional ADM (README.md:49 flags), unguided p_sample_loop,
+# timestep_respacing 25, batch 4 — the reference's own CPU-runnable case ------------------------------------------
+C1_SEED, C1_NOISE_SEED, C1_BATCH, C1_STEPS = 51, 52, 4, 25
+C1_KW = dict(image_size=64, num_channels=192, num_res_blocks=3, channel_mult="", learn_sigma=True, class_cond=True,
+             use_checkpoint=False, attention_resolutions="32,16,8", num_heads=4, num_head_channels=64,
+             num_heads_upsample=-1, use_scale_shift_norm=True, dropout=0.0, resblock_updown=True, use_fp16=False,
+             use_new_attention_order=True)
+C1_DIFFUSION = dict(steps=1000, learn_sigma=True, noise_schedule="cosine", timestep_respacing="25")
+C1_STRUCT = dict(num_res_blocks=3, channel_mult_len=4, head_dim=64, new_order=True)
+C1_CHECKPOINTS = (10, 25)  # number of reverse steps after which the sample is recorded
+
+
+def ref_c1_kwargs():
+    return dict(image_size=64, in_channels=3, model_channels=192, out_channels=6, num_res_blocks=3,
+                attention_resolutions=(2, 4, 8), dropout=0.0, channel_mult=(1, 2, 3, 4), num_classes=1000,
+                use_checkpoint=False, use_fp16=False, num_heads=4, num_head_channels=64, num_heads_upsample=-1,
+                use_scale_shift_norm=True, resblock_updown=True, use_new_attention_order=True)
+
+
+def c1_labels():
+    return th.tensor([1, 250, 500, 999])
+
+
+def c1_noise():
+    """The CPU-generator draws of the reference loop: randn(shape), then one randn_like per step."""
+    th.manual_seed(C1_NOISE_SEED)
+    shape = (C1_BATCH, 3, 64, 64)
+    return th.randn(*shape), [th.randn(*shape) for _ in range(C1_STEPS)]

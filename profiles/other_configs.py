@@ -1,4 +1,8 @@
-"""Step time of BASELINE configs[2..4] through the public sampling API (one process, one B200), CUDA-event timed:
+"""Step time of BASELINE configs[0] and configs[2..4] through the public sampling API (one process, one B200),
+CUDA-event timed:
+
+  cfg1  64x64 class-cond ADM (192 ch, 3 res blocks), unguided p_sample_loop, respacing 25, batch 4 (and 256): the
+        WHOLE loop through diffusion.p_sample_loop, wall clock, next to the reference's CPU time for the same job
 
   cfg3  256x256 unconditional ADM + CLIP ViT-B/16 image-encoder guidance, DDIM-50, batch 32
   cfg4  128->512 upsampler (SuperResModel, 192 ch), 250 steps, batch 8
@@ -35,6 +39,38 @@ def time_steps(fn, steps=6, warm=2):
     e1.record()
     th.cuda.synchronize()
     return e0.elapsed_time(e1) / steps
+
+
+def cfg1(batch=4):
+    import time
+    kw = su.model_and_diffusion_defaults()
+    kw.update(image_size=64, num_channels=192, num_res_blocks=3, attention_resolutions="32,16,8", num_head_channels=64,
+              class_cond=True, learn_sigma=True, noise_schedule="cosine", resblock_updown=True,
+              use_scale_shift_norm=True, use_new_attention_order=True, timestep_respacing="25")
+    model, diffusion = su.create_model_and_diffusion(**kw)
+    bench.randomize_(model, 3)
+    model.to(dev).eval()
+    g = th.Generator(device="cuda").manual_seed(4)
+    y = th.randint(0, 1000, (batch,), generator=g, device=dev)
+    mf = ModelFn(model, True)
+
+    def loop():
+        with th.no_grad():
+            return diffusion.p_sample_loop(mf, (batch, 3, 64, 64), model_kwargs={"y": y})
+
+    loop()  # plan build + graph capture
+    th.cuda.synchronize()
+    t0 = time.time()
+    reps = 3
+    for _ in range(reps):
+        out = loop()
+    th.cuda.synchronize()
+    s = (time.time() - t0) / reps
+    assert bool(th.isfinite(out).all())
+    return {"config": "cfg1 class-cond-64 (192ch x3), unguided p_sample_loop, 25 steps", "batch": batch,
+            "loop_seconds": round(s, 4), "ms_per_step": round(1e3 * s / 25, 3), "samples_per_s": round(batch / s, 2),
+            "step_tflops": round(219.36 * batch / (1e3 * s / 25), 1),
+            "reference_cpu_seconds_batch4": "59.8 s on 8 threads in the build container (oracle/make_golden_config1.py)"}
 
 
 def cfg3(batch=32):
@@ -117,7 +153,7 @@ def cfg5(batch=8):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["cfg3", "cfg4", "cfg5"]
+    which = sys.argv[1:] or ["cfg1", "cfg1:256", "cfg3", "cfg4", "cfg5"]
     for name in which:
         fn, _, b = name.partition(":")
         r = globals()[fn](int(b)) if b else globals()[fn]()
