@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "../../include/gd_b200.h"
 #include <stdarg.h>
+#include <stdlib.h>
 
 namespace gd {
 namespace {
@@ -16,12 +17,21 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches += n; }
+static int g_pdl = -1;
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("GD_B200_PDL");
+    g_pdl = (e != nullptr && e[0] == '1') ? 1 : 0;  // measured slower: off unless asked for
+  }
+  return g_pdl != 0;
+}
 void conv_debug_set(int key, int value);
 void attn_debug_set(int value);
 }  // namespace gd
 
 extern "C" void gd_debug_set(int key, int value) {
-  if (key == 5) gd::attn_debug_set(value);
+  if (key == 6) gd::g_pdl = value ? 1 : 0;
+  else if (key == 5) gd::attn_debug_set(value);
   else gd::conv_debug_set(key, value);
 }
 

@@ -97,6 +97,7 @@ __device__ __forceinline__ HeadPtrs head_ptrs(const __half* qkv_n, int head, int
 __global__ void __launch_bounds__(128)
 attn_fwd_kernel(const __half* __restrict__ qkv, int ld_qkv, __half* __restrict__ out, int ld_out,
                 float* __restrict__ lse, int t, int t_valid, int heads, int order) {
+  pdl_enter();
   __shared__ __align__(128) __half sQ[kBQ * kD];
   __shared__ __align__(128) __half sK[2][kBKV * kD];
   __shared__ __align__(128) __half sV[2][kBKV * kD];
@@ -263,6 +264,7 @@ attn_fwd_kernel(const __half* __restrict__ qkv, int ld_qkv, __half* __restrict__
 // ---------------------------------------------------------------------------------------------
 __global__ void attn_delta_kernel(const __half* __restrict__ out, int ld_out, const __half* __restrict__ dout,
                                   int ld_dout, float* __restrict__ delta, int t, int heads) {
+  pdl_enter();
   // one warp per (n, head, token): 64 channels -> 2 per lane
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -285,6 +287,7 @@ __global__ void __launch_bounds__(128)
 attn_bwd_dkv_kernel(const __half* __restrict__ qkv, int ld_qkv, const __half* __restrict__ dout, int ld_dout,
                     const float* __restrict__ lse, const float* __restrict__ delta, __half* __restrict__ dqkv,
                     int ld_dqkv, int t, int t_valid, int heads, int order) {
+  pdl_enter();
   // 32 KiB of tiles: buffer 1 of the Q/dO ring first stages this CTA's K and V (read once into registers).
   __shared__ __align__(128) __half sQ[2][kBQ * kD];
   __shared__ __align__(128) __half sdO[2][kBQ * kD];
@@ -432,6 +435,7 @@ __global__ void __launch_bounds__(128)
 attn_bwd_dq_kernel(const __half* __restrict__ qkv, int ld_qkv, const __half* __restrict__ dout, int ld_dout,
                    const float* __restrict__ lse, const float* __restrict__ delta, __half* __restrict__ dqkv,
                    int ld_dqkv, int t, int t_valid, int heads, int order) {
+  pdl_enter();
   __shared__ __align__(128) __half sQ[kBQ * kD];
   __shared__ __align__(128) __half sdO[kBQ * kD];
   __shared__ __align__(128) __half sK[2][kBKV * kD];
@@ -567,9 +571,9 @@ extern "C" int gd_attention_fwd_masked(const void* qkv, int32_t ld_qkv, void* ou
     return attn_fwd_tc_launch(qkv, ld_qkv, out, ld_out, lse, n, t, t_valid, heads, order,
                               reinterpret_cast<cudaStream_t>(stream));
   dim3 grid(t / kBQ, heads, n);  // 64-token sequences (8x8 resolution): warp-level mma.sync kernel
-  attn_fwd_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __half*>(qkv), ld_qkv, reinterpret_cast<__half*>(out), ld_out, lse, t, t_valid, heads, order);
-  GD_CHECK_CUDA(cudaGetLastError());
+  GD_CHECK_CUDA(launch_pdl(attn_fwd_kernel, grid, dim3(128), 0, reinterpret_cast<cudaStream_t>(stream),
+                           reinterpret_cast<const __half*>(qkv), ld_qkv, reinterpret_cast<__half*>(out), ld_out, lse, t,
+                           t_valid, heads, order));
   count_launch(1);
   return 0;
 }
@@ -590,18 +594,15 @@ extern "C" int gd_attention_bwd_masked(const void* qkv, int32_t ld_qkv, const vo
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int warps = heads * t;
   dim3 dgrid((warps * 32 + 255) / 256, n);
-  attn_delta_kernel<<<dgrid, 256, 0, st>>>(reinterpret_cast<const __half*>(out), ld_out,
-                                           reinterpret_cast<const __half*>(dout), ld_dout, delta_ws, t, heads);
-  GD_CHECK_CUDA(cudaGetLastError());
+  GD_CHECK_CUDA(launch_pdl(attn_delta_kernel, dgrid, dim3(256), 0, st, reinterpret_cast<const __half*>(out), ld_out,
+                           reinterpret_cast<const __half*>(dout), ld_dout, delta_ws, t, heads));
   dim3 grid(t / 64, heads, n);
-  attn_bwd_dkv_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const __half*>(qkv), ld_qkv,
-                                            reinterpret_cast<const __half*>(dout), ld_dout, lse, delta_ws,
-                                            reinterpret_cast<__half*>(dqkv), ld_dqkv, t, t_valid, heads, order);
-  GD_CHECK_CUDA(cudaGetLastError());
-  attn_bwd_dq_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const __half*>(qkv), ld_qkv,
-                                           reinterpret_cast<const __half*>(dout), ld_dout, lse, delta_ws,
-                                           reinterpret_cast<__half*>(dqkv), ld_dqkv, t, t_valid, heads, order);
-  GD_CHECK_CUDA(cudaGetLastError());
+  GD_CHECK_CUDA(launch_pdl(attn_bwd_dkv_kernel, grid, dim3(128), 0, st, reinterpret_cast<const __half*>(qkv), ld_qkv,
+                           reinterpret_cast<const __half*>(dout), ld_dout, lse, delta_ws, reinterpret_cast<__half*>(dqkv),
+                           ld_dqkv, t, t_valid, heads, order));
+  GD_CHECK_CUDA(launch_pdl(attn_bwd_dq_kernel, grid, dim3(128), 0, st, reinterpret_cast<const __half*>(qkv), ld_qkv,
+                           reinterpret_cast<const __half*>(dout), ld_dout, lse, delta_ws, reinterpret_cast<__half*>(dqkv),
+                           ld_dqkv, t, t_valid, heads, order));
   count_launch(3);
   return 0;
 }

@@ -154,6 +154,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __half* __restri
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_s = tmem_base;        // S: columns [0,128)
   const uint32_t tmem_o = tmem_base + 128;  // O accumulator: columns [128,192)
+  pdl_enter();  // barrier init and the TMEM allocation above overlap the predecessor kernel's tail
 
   if (warp >= 4) {
     // the non-softmax warpgroup needs few registers; the softmax warpgroup takes them (128 fp32 scores per thread)
@@ -410,9 +411,8 @@ int attn_fwd_tc_launch(const void* qkv, int ld_qkv, void* out, int ld_out, float
     configured = true;
   }
   dim3 grid(t / kBQ, heads, n);
-  attn_fwd_tc_kernel<<<grid, kTcThreads, kSmemBytes, stream>>>(map, reinterpret_cast<__half*>(out), ld_out, lse, t, t_valid,
-                                                               heads, order);
-  GD_CHECK_CUDA(cudaGetLastError());
+  GD_CHECK_CUDA(launch_pdl(attn_fwd_tc_kernel, grid, dim3(kTcThreads), kSmemBytes, stream, map,
+                           reinterpret_cast<__half*>(out), ld_out, lse, t, t_valid, heads, order));
   count_launch(1);
   return 0;
 }

@@ -33,7 +33,41 @@ void set_error(const char* fmt, ...);
 // ----------------------------------------------------------------------------------------------
 // device helpers
 // ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch: a kernel launched through launch_pdl() may be SCHEDULED while its predecessor in the
+// stream is still running (its CTAs become resident as SM resources free up) and must call pdl_wait() before its
+// first access to global memory; pdl_wait() returns once every prerequisite grid has completed and its writes are
+// visible.  pdl_trigger() lets the NEXT kernel in the stream be scheduled.  Every kernel calls wait first and then
+// trigger, so at most one successor is parked behind a running kernel.  The idea: hide the launch latency and the
+// CTA-scheduling ramp between the ~725 dependent launches of a sampling step (also inside a captured CUDA graph,
+// where the attribute becomes a programmatic edge).  MEASURED (profiles/pdl_ab_r01.log, same box, alternating runs):
+// the step gets SLOWER with the attribute on -- 166.6 -> 169.8 ms at batch 64, 22.0 -> 22.4 ms at batch 8 -- so it is
+// OFF by default; GD_B200_PDL=1 (or gd_debug_set(6, 1)) turns it on.  Without the attribute griddepcontrol.* are no-ops.
+bool pdl_enabled();
+
 #ifdef __CUDACC__
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+  pdl_wait();
+  pdl_trigger();
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -293,6 +293,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   if (kTwo) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  // everything above touched only shared memory, TMEM and the kernel parameters: it overlaps the predecessor's tail
+  pdl_enter();
 
   // K schedule shared by the producer and the MMA issuer.  Per 64-channel block of the main operand:
   //   halo mode (3x3, one image per tile): 3 activation groups (kx = 0..2), each ONE (BH+2) x BW halo tile that
@@ -921,19 +923,21 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = reinterpret_cast<cudaStream_t>(stream);
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     GD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true>, ma0, ma1, mb, mout, mres, p));
   } else {
     const int total_tiles = p.m_tiles * p.n_tiles;
     const int grid = total_tiles < g_num_sms ? total_tiles : g_num_sms;
-    conv_igemm_kernel<false><<<grid, kThreads, smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(ma0, ma1, mb, mout,
-                                                                                                    mres, p);
+    GD_CHECK_CUDA(launch_pdl(conv_igemm_kernel<false>, dim3(grid), dim3(kThreads), smem_bytes,
+                             reinterpret_cast<cudaStream_t>(stream), ma0, ma1, mb, mout, mres, p));
   }
   GD_CHECK_CUDA(cudaGetLastError());
   count_launch(1);

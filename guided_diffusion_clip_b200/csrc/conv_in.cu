@@ -49,6 +49,7 @@ conv_in3x3_kernel(const float* __restrict__ x, const __half* __restrict__ wpack,
   uint8_t* sStage = smem + cout * kRowB;                            // 4 warps x [32 pixels][64 channels] fp16
   float* sStat = reinterpret_cast<float*>(sStage + 4 * 4096);      // [4 warps][16 chunks][2]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  pdl_enter();
 
   for (int i = tid; i < cout * KS * 2; i += kCiThreads) {  // wpack rows are 64 halves (k zero padded)
     const int row = i / (KS * 2), ch = i - row * (KS * 2);
@@ -224,16 +225,16 @@ extern "C" int gd_conv_in3x3(const gd_conv_in_desc* d, void* stream) {
       GD_CHECK_CUDA(cudaFuncSetAttribute(conv_in3x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       configured = true;
     }
-    conv_in3x3_kernel<2><<<grid, kCiThreads, smem_bytes, st>>>(d->x, wp, d->bias, op, d->ld_out, d->stats_out, rpi, d->n,
-                                                               d->cin, d->h, d->w, d->cout);
+    GD_CHECK_CUDA(launch_pdl(conv_in3x3_kernel<2>, dim3(grid), dim3(kCiThreads), smem_bytes, st, d->x, wp, d->bias, op,
+                             d->ld_out, d->stats_out, rpi, d->n, d->cin, d->h, d->w, d->cout));
   } else {
     static bool configured = false;
     if (!configured) {
       GD_CHECK_CUDA(cudaFuncSetAttribute(conv_in3x3_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
       configured = true;
     }
-    conv_in3x3_kernel<4><<<grid, kCiThreads, smem_bytes, st>>>(d->x, wp, d->bias, op, d->ld_out, d->stats_out, rpi, d->n,
-                                                               d->cin, d->h, d->w, d->cout);
+    GD_CHECK_CUDA(launch_pdl(conv_in3x3_kernel<4>, dim3(grid), dim3(kCiThreads), smem_bytes, st, d->x, wp, d->bias, op,
+                             d->ld_out, d->stats_out, rpi, d->n, d->cin, d->h, d->w, d->cout));
   }
   GD_CHECK_CUDA(cudaGetLastError());
   count_launch(1);

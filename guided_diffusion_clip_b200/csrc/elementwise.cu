@@ -34,6 +34,7 @@ __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b);
 __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
 
 __global__ void posterior_kernel(const PostArgs p) {
+  pdl_enter();
   const size_t chw = static_cast<size_t>(p.c) * p.hw;
   const size_t total = static_cast<size_t>(p.n) * chw;
   const int out_c = (p.var_type == GD_VAR_FIXED) ? p.c : 2 * p.c;
@@ -129,6 +130,7 @@ template <bool kSiluIn>
 __global__ void linear_f32_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w,
                                   const float* __restrict__ b, const float* __restrict__ addp, int ld_add,
                                   float* __restrict__ y, int ldy, int m, int k, int n, int silu_out) {
+  pdl_enter();
   const int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (col >= n) return;
@@ -170,6 +172,7 @@ __global__ void __launch_bounds__(256)
 sgemm_nt_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w, const float* __restrict__ b,
                 const float* __restrict__ addp, int ld_add, float* __restrict__ y, int ldy, int m, int k, int n,
                 int silu_in, int silu_out) {
+  pdl_enter();
   __shared__ float sx[16][64 + 4];
   __shared__ float sw[16][64 + 4];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -402,8 +405,8 @@ extern "C" int gd_posterior_step(const gd_posterior_desc* d, void* stream) {
   p.n = d->n; p.c = d->c; p.hw = d->hw;
   p.var_type = d->var_type; p.mean_type = d->mean_type; p.clip = d->clip_denoised; p.ddim = d->ddim; p.eta = d->eta;
   const size_t total = static_cast<size_t>(d->n) * d->c * d->hw;
-  posterior_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
-  GD_CHECK_CUDA(cudaGetLastError());
+  GD_CHECK_CUDA(launch_pdl(posterior_kernel, dim3(grid_for(total, 256)), dim3(256), 0,
+                           reinterpret_cast<cudaStream_t>(stream), p));
   count_launch(1);
   return 0;
 }
@@ -425,18 +428,19 @@ extern "C" int gd_linear_f32(const float* x, int32_t ldx, const float* w, const 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (m > 16) {  // many rows: tiled GEMM (weights are re-used across rows through shared memory)
     dim3 grid2((n + 63) / 64, (m + 63) / 64);
-    sgemm_nt_kernel<<<grid2, 256, 0, st>>>(x, ldx, w, b, add, ld_add, y, ldy, m, k, n, silu_in, silu_out);
-    GD_CHECK_CUDA(cudaGetLastError());
+    GD_CHECK_CUDA(launch_pdl(sgemm_nt_kernel, grid2, dim3(256), 0, st, x, ldx, w, b, add, ld_add, y, ldy, m, k, n, silu_in,
+                             silu_out));
     count_launch(1);
     return 0;
   }
   const int warps = 8;
   const int grid = (n + warps - 1) / warps;
   if (silu_in)
-    linear_f32_kernel<true><<<grid, warps * 32, 0, st>>>(x, ldx, w, b, add, ld_add, y, ldy, m, k, n, silu_out);
+    GD_CHECK_CUDA(launch_pdl(linear_f32_kernel<true>, dim3(grid), dim3(warps * 32), 0, st, x, ldx, w, b, add, ld_add, y, ldy,
+                             m, k, n, silu_out));
   else
-    linear_f32_kernel<false><<<grid, warps * 32, 0, st>>>(x, ldx, w, b, add, ld_add, y, ldy, m, k, n, silu_out);
-  GD_CHECK_CUDA(cudaGetLastError());
+    GD_CHECK_CUDA(launch_pdl(linear_f32_kernel<false>, dim3(grid), dim3(warps * 32), 0, st, x, ldx, w, b, add, ld_add, y,
+                             ldy, m, k, n, silu_out));
   count_launch(1);
   return 0;
 }
@@ -478,6 +482,7 @@ template <int kCout>
 __global__ void __launch_bounds__(kTgW * kTgH)
 tap_gather3x3_kernel(const __half* __restrict__ ytap, int ld, const float* __restrict__ bias, float* __restrict__ out,
                      int h, int w, float out_scale) {
+  pdl_enter();
   __shared__ uint32_t tile[(kTgH + 2) * (kTgW + 2) * kTgRow];
   const int n = blockIdx.z, y0 = blockIdx.y * kTgH, x0 = blockIdx.x * kTgW;
   const size_t plane = static_cast<size_t>(h) * w;
@@ -526,7 +531,7 @@ extern "C" int gd_tap_gather3x3(const void* ytap, int32_t ld, const float* bias,
   const dim3 grid((w + kTgW - 1) / kTgW, (h + kTgH - 1) / kTgH, n);
   switch (cout) {
 #define GD_TAP_CASE(K) \
-  case K: tap_gather3x3_kernel<K><<<grid, kTgW * kTgH, 0, st>>>(y, ld, bias, out, h, w, out_scale); break;
+  case K: GD_CHECK_CUDA(launch_pdl(tap_gather3x3_kernel<K>, grid, dim3(kTgW * kTgH), 0, st, y, ld, bias, out, h, w, out_scale)); break;
     GD_TAP_CASE(1) GD_TAP_CASE(2) GD_TAP_CASE(3) GD_TAP_CASE(4) GD_TAP_CASE(5) GD_TAP_CASE(6) GD_TAP_CASE(7)
 #undef GD_TAP_CASE
   }

@@ -80,6 +80,7 @@ __device__ __forceinline__ void block_group_reduce(float* s_part, float* s_acc, 
 // ---------------------------------------------------------------------------------------------
 __global__ void gn_stats_kernel(const __half* __restrict__ x, int ld, int hw, int c, int c8, int rep, int px_per_chunk,
                                 float* __restrict__ partial) {
+  pdl_enter();
   __shared__ float s_acc[2 * kGroups];
   const int n = blockIdx.y, chunk = blockIdx.x;
   extern __shared__ float s_part[];
@@ -131,6 +132,7 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, int ld, int hw, in
 // mode 0: (mean, rstd); mode 1: (sum0/count, sum1/count)
 __global__ void gn_finalize_kernel(const float* __restrict__ partial, int chunks, float inv_count, float eps, int mode,
                                    float* __restrict__ out) {
+  pdl_enter();
   const int n = blockIdx.x, g = threadIdx.x;
   double a = 0.0, b = 0.0;
   for (int k = 0; k < chunks; ++k) {
@@ -197,6 +199,7 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, int ld, const floa
                                 const float* __restrict__ film, int film_ld, __half* __restrict__ out, int ld_out,
                                 __half* __restrict__ aux, int ld_aux, int h, int w, int c, int c8, int rep,
                                 int px_per_chunk) {
+  pdl_enter();
   const int n = blockIdx.y, chunk = blockIdx.x;
   const int cch = threadIdx.x % c8, pl = threadIdx.x / c8;
   float a[8], b[8];
@@ -375,6 +378,7 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_stats_kernel(const __half* __re
                                     const float* __restrict__ film, int film_ld, const __half* __restrict__ dy, int ld_dy,
                                     int h, int w, int c, int c8, int rep, int px_per_chunk,
                                     float* __restrict__ partial) {
+  pdl_enter();
   __shared__ float s_acc[2 * kGroups];
   const int n = blockIdx.y, chunk = blockIdx.x;
   extern __shared__ float s_part[];
@@ -448,6 +452,7 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_apply_kernel(const __half* __re
                                     const float* __restrict__ gsum, const __half* __restrict__ add, int ld_add,
                                     int add_mode, __half* __restrict__ dx, int ld_dx, int h, int w, int c, int c8,
                                     int rep, int px_per_chunk) {
+  pdl_enter();
   const int n = blockIdx.y, chunk = blockIdx.x;
   const int cch = threadIdx.x % c8, pl = threadIdx.x / c8;
   BwdAffine A;
@@ -548,6 +553,7 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_apply_kernel(const __half* __re
 __global__ void __launch_bounds__(128)
 gn_finalize_partials_kernel(const float* __restrict__ p0, int c0, int ld0, const float* __restrict__ p1, int c1,
                             int ld1, int rows_per_image, double inv_count, float eps, float* __restrict__ out) {
+  pdl_enter();
   __shared__ double sh[2][128];
   const int g = blockIdx.x, n = blockIdx.y, tid = threadIdx.x;
   const int cpg = (c0 + c1) / kGroups;
@@ -598,9 +604,9 @@ extern "C" int gd_groupnorm_finalize_partials(const float* p0, int32_t c0, int32
              "gd_groupnorm_finalize_partials: needs channels-per-group %% 4 == 0 (c0=%d c1=%d)", c0, c1);
   GD_REQUIRE(ld0 >= c0 / 4 && (p1 == nullptr || ld1 >= c1 / 4), "gd_groupnorm_finalize_partials: bad leading dimension");
   const double inv_count = 1.0 / (static_cast<double>(hw) * static_cast<double>(c / kGroups));
-  gn_finalize_partials_kernel<<<dim3(kGroups, n), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      p0, c0, ld0, p1, c1, ld1, rows_per_image, inv_count, eps, mean_rstd);
-  GD_CHECK_CUDA(cudaGetLastError());
+  GD_CHECK_CUDA(launch_pdl(gn_finalize_partials_kernel, dim3(kGroups, n), dim3(128), 0,
+                           reinterpret_cast<cudaStream_t>(stream), p0, c0, ld0, p1, c1, ld1, rows_per_image, inv_count, eps,
+                           mean_rstd));
   count_launch(1);
   return 0;
 }
@@ -625,27 +631,28 @@ extern "C" int gd_groupnorm_stats(const void* x, int32_t ld, int32_t n, int32_t 
   GD_REQUIRE(partial_ws != nullptr && mean_rstd != nullptr, "gd_groupnorm_stats: null workspace/output");
   const Geo g = make_geo(c, hw, n, kMaxChunks);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  gn_stats_kernel<<<dim3(g.chunks, n), g.threads, g.threads * 16 * sizeof(float), st>>>(reinterpret_cast<const __half*>(x), ld, hw, c, g.c8, g.rep,
-                                                          g.px_per_chunk, partial_ws);
-  GD_CHECK_CUDA(cudaGetLastError());
+  GD_CHECK_CUDA(launch_pdl(gn_stats_kernel, dim3(g.chunks, n), dim3(g.threads), g.threads * 16 * sizeof(float), st,
+                           reinterpret_cast<const __half*>(x), ld, hw, c, g.c8, g.rep, g.px_per_chunk, partial_ws));
   const float inv_count = 1.0f / (static_cast<float>(hw) * static_cast<float>(c / kGroups));
-  gn_finalize_kernel<<<n, kGroups, 0, st>>>(partial_ws, g.chunks, inv_count, eps, 0, mean_rstd);
-  GD_CHECK_CUDA(cudaGetLastError());
+  GD_CHECK_CUDA(launch_pdl(gn_finalize_kernel, dim3(n), dim3(kGroups), 0, st, partial_ws, g.chunks, inv_count, eps, 0,
+                           mean_rstd));
   count_launch(2);
   return 0;
 }
 
-#define GD_GN_DISPATCH(KERNEL, silu, mode, ...)                                   \
-  do {                                                                            \
-    if (silu) {                                                                   \
-      if (mode == GD_GN_SAME) KERNEL<true, GD_GN_SAME> __VA_ARGS__;               \
-      else if (mode == GD_GN_AVGPOOL2) KERNEL<true, GD_GN_AVGPOOL2> __VA_ARGS__;  \
-      else KERNEL<true, GD_GN_UPSAMPLE2> __VA_ARGS__;                             \
-    } else {                                                                      \
-      if (mode == GD_GN_SAME) KERNEL<false, GD_GN_SAME> __VA_ARGS__;              \
-      else if (mode == GD_GN_AVGPOOL2) KERNEL<false, GD_GN_AVGPOOL2> __VA_ARGS__; \
-      else KERNEL<false, GD_GN_UPSAMPLE2> __VA_ARGS__;                            \
-    }                                                                             \
+#define GD_GN_DISPATCH(KERNEL, silu, mode, ...)                                                                    \
+  do {                                                                                                             \
+    cudaError_t _le;                                                                                               \
+    if (silu) {                                                                                                    \
+      if (mode == GD_GN_SAME) _le = launch_pdl(KERNEL<true, GD_GN_SAME>, __VA_ARGS__);                             \
+      else if (mode == GD_GN_AVGPOOL2) _le = launch_pdl(KERNEL<true, GD_GN_AVGPOOL2>, __VA_ARGS__);                \
+      else _le = launch_pdl(KERNEL<true, GD_GN_UPSAMPLE2>, __VA_ARGS__);                                           \
+    } else {                                                                                                       \
+      if (mode == GD_GN_SAME) _le = launch_pdl(KERNEL<false, GD_GN_SAME>, __VA_ARGS__);                            \
+      else if (mode == GD_GN_AVGPOOL2) _le = launch_pdl(KERNEL<false, GD_GN_AVGPOOL2>, __VA_ARGS__);               \
+      else _le = launch_pdl(KERNEL<false, GD_GN_UPSAMPLE2>, __VA_ARGS__);                                          \
+    }                                                                                                              \
+    GD_CHECK_CUDA(_le);                                                                                            \
   } while (0)
 
 extern "C" int gd_groupnorm_apply(const void* x, int32_t ld, const float* mean_rstd, const float* gamma,
@@ -665,10 +672,9 @@ extern "C" int gd_groupnorm_apply(const void* x, int32_t ld, const float* mean_r
   const Geo g = make_geo(c, hw_iter, n, 4096);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   GD_GN_DISPATCH(gn_apply_kernel, silu, spatial_mode,
-                 <<<dim3(g.chunks, n), g.threads, 0, st>>>(reinterpret_cast<const __half*>(x), ld, mean_rstd, gamma,
-                                                          beta, film, film_ld, reinterpret_cast<__half*>(out), ld_out,
-                                                          reinterpret_cast<__half*>(aux_out), ld_aux, h, w, c, g.c8,
-                                                          g.rep, g.px_per_chunk));
+                 dim3(g.chunks, n), dim3(g.threads), 0, st, reinterpret_cast<const __half*>(x), ld, mean_rstd, gamma, beta,
+                 film, film_ld, reinterpret_cast<__half*>(out), ld_out, reinterpret_cast<__half*>(aux_out), ld_aux, h, w,
+                 c, g.c8, g.rep, g.px_per_chunk);
   GD_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
   return 0;
@@ -690,18 +696,17 @@ extern "C" int gd_groupnorm_bwd(const void* x, int32_t ld, const float* mean_rst
   // partial_ws layout: [n][kMaxChunks][32][2] partials, then [n][32][2] group means
   float* gsum = partial_ws + static_cast<size_t>(n) * kMaxChunks * kGroups * 2;
   GD_GN_DISPATCH(gn_bwd_stats_kernel, silu, spatial_mode,
-                 <<<dim3(g.chunks, n), g.threads, g.threads * 16 * sizeof(float), st>>>(reinterpret_cast<const __half*>(x), ld, mean_rstd, gamma,
-                                                          beta, film, film_ld, reinterpret_cast<const __half*>(dy),
-                                                          ld_dy, h, w, c, g.c8, g.rep, g.px_per_chunk, partial_ws));
+                 dim3(g.chunks, n), dim3(g.threads), g.threads * 16 * sizeof(float), st,
+                 reinterpret_cast<const __half*>(x), ld, mean_rstd, gamma, beta, film, film_ld,
+                 reinterpret_cast<const __half*>(dy), ld_dy, h, w, c, g.c8, g.rep, g.px_per_chunk, partial_ws);
   GD_CHECK_CUDA(cudaGetLastError());
   const float inv_count = 1.0f / (static_cast<float>(h * w) * static_cast<float>(c / kGroups));
-  gn_finalize_kernel<<<n, kGroups, 0, st>>>(partial_ws, g.chunks, inv_count, 0.f, 1, gsum);
-  GD_CHECK_CUDA(cudaGetLastError());
+  GD_CHECK_CUDA(launch_pdl(gn_finalize_kernel, dim3(n), dim3(kGroups), 0, st, partial_ws, g.chunks, inv_count, 0.f, 1,
+                           gsum));
   GD_GN_DISPATCH(gn_bwd_apply_kernel, silu, spatial_mode,
-                 <<<dim3(ga.chunks, n), ga.threads, 0, st>>>(
-                     reinterpret_cast<const __half*>(x), ld, mean_rstd, gamma, beta, film, film_ld,
-                     reinterpret_cast<const __half*>(dy), ld_dy, gsum, reinterpret_cast<const __half*>(add), ld_add,
-                     add_mode, reinterpret_cast<__half*>(dx), ld_dx, h, w, c, ga.c8, ga.rep, ga.px_per_chunk));
+                 dim3(ga.chunks, n), dim3(ga.threads), 0, st, reinterpret_cast<const __half*>(x), ld, mean_rstd, gamma, beta,
+                 film, film_ld, reinterpret_cast<const __half*>(dy), ld_dy, gsum, reinterpret_cast<const __half*>(add),
+                 ld_add, add_mode, reinterpret_cast<__half*>(dx), ld_dx, h, w, c, ga.c8, ga.rep, ga.px_per_chunk);
   GD_CHECK_CUDA(cudaGetLastError());
   count_launch(3);
   return 0;
