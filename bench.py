@@ -228,6 +228,65 @@ def top_conv_roofline(batch, image_size, burst_tflops, reps=12):
             "avg_launch_ms": avg, "flops_per_launch": flops}
 
 
+def hbm_kernels_roofline(diffusion, batch, image_size, hbm_gbs, reps=10):
+    """The two bandwidth-bound kernels of the step timed alone (CUDA events, current stream), rotating over 3 input
+    sets so that no launch finds its inputs in the 126 MB L2: the fused posterior update (21 channels x 4 B per
+    pixel = reads x, eps|v, grad, noise; writes sample, pred_xstart) and GroupNorm+SiLU+FiLM apply on the largest
+    activation (256 channels at full resolution: read fp16 once, write fp16 once)."""
+    import ctypes as C
+    from guided_diffusion_clip_b200 import _lib as L
+    lib = L.load()
+    dev = th.device("cuda", th.cuda.current_device())
+    shape = (batch, 3, image_size, image_size)
+    sets = [dict(x=th.randn(shape, device=dev), mo=th.randn((batch, 6) + shape[2:], device=dev),
+                 g=th.randn(shape, device=dev), z=th.randn(shape, device=dev)) for _ in range(3)]
+    sample, x0 = th.empty(shape, device=dev), th.empty(shape, device=dev)
+    t = th.full((batch,), diffusion.num_timesteps // 2, dtype=th.int64, device=dev)
+    out = []
+
+    def timed(fn):
+        evs = []
+        for i in range(reps + 3):
+            e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+            e0.record()
+            fn(i)
+            e1.record()
+            evs.append((e0, e1))
+        th.cuda.synchronize()
+        ms = [a.elapsed_time(b) for a, b in evs[3:]]
+        return sum(ms) / len(ms)
+
+    ms = timed(lambda i: diffusion._launch_posterior(x=sets[i % 3]["x"], t=t, model_out=sets[i % 3]["mo"],
+                                                     grad=sets[i % 3]["g"], noise=sets[i % 3]["z"], sample=sample,
+                                                     pred_xstart=x0))
+    nbytes = 21.0 * 4 * batch * image_size * image_size
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    out.append({"kernel": "posterior_kernel (guided p_sample update)", "bound": "hbm", "achieved": gbs, "peak": hbm_gbs,
+                "unit": "GB/s", "frac": gbs / hbm_gbs, "avg_launch_ms": ms, "algorithmic_bytes": nbytes})
+    del sets
+    c = 256
+    xs = [th.randn((batch, image_size, image_size, c), device=dev, dtype=th.float16) for _ in range(3)]
+    y = th.empty_like(xs[0])
+    st = th.zeros((batch, 32, 2), device=dev)
+    st[..., 1] = 1.0
+    gamma, beta = th.ones(c, device=dev), th.zeros(c, device=dev)
+    film = th.randn((batch, 2 * c), device=dev) * 0.1
+    stream = C.c_void_p(th.cuda.current_stream().cuda_stream)
+    vp = lambda v: C.c_void_p(v.data_ptr())  # noqa: E731
+
+    def gn(i):
+        L.check(lib.gd_groupnorm_apply(vp(xs[i % 3]), c, vp(st), vp(gamma), vp(beta), vp(film), 2 * c, vp(y), c, batch,
+                                       image_size, image_size, c, 1, L.GN_SAME, None, 0, stream), "gd_groupnorm_apply")
+
+    ms = timed(gn)
+    nbytes = 2.0 * 2 * batch * image_size * image_size * c
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    out.append({"kernel": "gn_apply_kernel (GroupNorm32+FiLM+SiLU, 256 ch @%dx%d)" % (image_size, image_size),
+                "bound": "hbm", "achieved": gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": gbs / hbm_gbs,
+                "avg_launch_ms": ms, "algorithmic_bytes": nbytes})
+    return out
+
+
 def run_gpu_arm(args):
     from guided_diffusion_clip_b200 import dist_util, script_util as su
     from guided_diffusion_clip_b200.sampler import ClassifierGuidance, GraphedStepper, ModelFn
@@ -343,13 +402,14 @@ def run_gpu_arm(args):
     step_tflops = GFLOP_PER_SAMPLE_STEP * 1e9 * B / (ms_per_step * 1e-3) / 1e12
     roof["step_tflops"] = step_tflops
     roof["step_frac_of_sustained"] = step_tflops / sustained
+    roof_hbm = hbm_kernels_roofline(diffusion, B, S, hbm)
     value = world * B / (STEPS_PER_SAMPLE * ms_per_step * 1e-3)
     line = {
         "metric": "guided_samples_per_sec_256", "value": value, "unit": "samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
         "config": workload_config(S, B, world), "finite": finite,
-        "roofline": roof, "clocks": clocks.summary(), "gpu_launches": launches_per_step * args.steps,
+        "roofline": roof, "roofline_hbm": roof_hbm, "clocks": clocks.summary(), "gpu_launches": launches_per_step * args.steps,
         "launches_per_step": launches_per_step, "gather_ms": gather_ms,
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": bytes_io + B * 8,
                 "d2h_bytes_per_step": bytes_io, "steps": n_e2e},

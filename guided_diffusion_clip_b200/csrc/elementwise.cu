@@ -33,68 +33,54 @@ __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b);
 __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
 
-__global__ void posterior_kernel(const PostArgs p) {
-  pdl_enter();
-  const size_t chw = static_cast<size_t>(p.c) * p.hw;
-  const size_t total = static_cast<size_t>(p.n) * chw;
-  const int out_c = (p.var_type == GD_VAR_FIXED) ? p.c : 2 * p.c;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const size_t b = i / chw, r = i - b * chw;
-    // per-sample timestep index into the coefficient table (_extract_into_tensor, gaussian_diffusion.py:904-917)
-    const float* co = p.coef + static_cast<size_t>(p.t[b]) * GD_COEF_STRIDE;
-    const float sr = co[GD_COEF_SQRT_RECIP_ACP], srm1 = co[GD_COEF_SQRT_RECIPM1_ACP];
-    const float c1 = co[GD_COEF_POST_MEAN1], c2 = co[GD_COEF_POST_MEAN2];
-    const float max_log = co[GD_COEF_LOG_BETA], min_log = co[GD_COEF_POST_LOGVAR];
-    const float acp = co[GD_COEF_ACP], acp_prev = co[GD_COEF_ACP_PREV];
-    const float nonzero = co[GD_COEF_NONZERO];
-    const float acp_next = co[GD_COEF_ACP_NEXT];
-    const size_t mo = b * static_cast<size_t>(out_c) * p.hw + r;
-    const float x = p.x[i];
-    const float m_out = p.model_out[mo];
-    float var, logvar;
-    if (p.var_type == GD_VAR_LEARNED_RANGE) {
-      const float v = p.model_out[mo + chw];
-      const float frac = mul(add(v, 1.0f), 0.5f);  // (v + 1) / 2
-      logvar = add(mul(frac, max_log), mul(sub(1.0f, frac), min_log));
-      var = expf(logvar);
-    } else if (p.var_type == GD_VAR_LEARNED) {
-      logvar = p.model_out[mo + chw];
-      var = expf(logvar);
-    } else {
-      var = co[GD_COEF_FIXED_VAR];
-      logvar = co[GD_COEF_FIXED_LOGVAR];
-    }
-    float x0;
-    if (p.mean_type == GD_MEAN_EPSILON) {
-      x0 = sub(mul(sr, x), mul(srm1, m_out));
-    } else {
-      x0 = m_out;
-    }
-    if (p.clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
-    float mean = add(mul(c1, x0), mul(c2, x));
-    if (p.mean_out != nullptr) p.mean_out[i] = mean;
-    if (p.var_out != nullptr) p.var_out[i] = var;
-    if (p.logvar_out != nullptr) p.logvar_out[i] = logvar;
-    if (p.ddim == GD_DDIM_REVERSE) {  // ddim_reverse_sample (gaussian_diffusion.py:596-632): deterministic, x_t -> x_{t+1}
-      const float e = __fdiv_rn(sub(mul(sr, x), x0), srm1);
-      p.sample[i] = add(mul(x0, sqrtf(acp_next)), mul(sqrtf(sub(1.0f, acp_next)), e));
-      if (p.pred_xstart != nullptr) p.pred_xstart[i] = x0;
-      continue;
-    }
-    if (p.noise == nullptr) {  // p_mean_variance only
-      if (p.pred_xstart != nullptr) p.pred_xstart[i] = x0;
-      continue;
-    }
-    float out;
+// One element of the update.  `b` = sample index (selects the coefficient row), `i` = flat index into x-shaped tensors,
+// `m_out` / `v_out` = the model's mean / variance channels at this element.  Returns through `r`.
+struct PostElem {
+  float mean, var, logvar, x0, out;
+};
+__device__ __forceinline__ void posterior_elem(const PostArgs& p, const float* __restrict__ co, float x, float m_out,
+                                               float v_out, float g, float z, PostElem& r) {
+  const float sr = co[GD_COEF_SQRT_RECIP_ACP], srm1 = co[GD_COEF_SQRT_RECIPM1_ACP];
+  const float c1 = co[GD_COEF_POST_MEAN1], c2 = co[GD_COEF_POST_MEAN2];
+  const float max_log = co[GD_COEF_LOG_BETA], min_log = co[GD_COEF_POST_LOGVAR];
+  const float acp = co[GD_COEF_ACP], acp_prev = co[GD_COEF_ACP_PREV];
+  const float nonzero = co[GD_COEF_NONZERO];
+  const float acp_next = co[GD_COEF_ACP_NEXT];
+  float var, logvar;
+  if (p.var_type == GD_VAR_LEARNED_RANGE) {
+    const float frac = mul(add(v_out, 1.0f), 0.5f);  // (v + 1) / 2
+    logvar = add(mul(frac, max_log), mul(sub(1.0f, frac), min_log));
+    var = expf(logvar);
+  } else if (p.var_type == GD_VAR_LEARNED) {
+    logvar = v_out;
+    var = expf(logvar);
+  } else {
+    var = co[GD_COEF_FIXED_VAR];
+    logvar = co[GD_COEF_FIXED_LOGVAR];
+  }
+  float x0;
+  if (p.mean_type == GD_MEAN_EPSILON) {
+    x0 = sub(mul(sr, x), mul(srm1, m_out));
+  } else {
+    x0 = m_out;
+  }
+  if (p.clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+  float mean = add(mul(c1, x0), mul(c2, x));
+  r.mean = mean;
+  r.var = var;
+  r.logvar = logvar;
+  r.out = 0.f;
+  if (p.ddim == GD_DDIM_REVERSE) {  // ddim_reverse_sample (gaussian_diffusion.py:596-632): deterministic, x_t -> x_{t+1}
+    const float e = __fdiv_rn(sub(mul(sr, x), x0), srm1);
+    r.out = add(mul(x0, sqrtf(acp_next)), mul(sqrtf(sub(1.0f, acp_next)), e));
+  } else if (p.noise != nullptr) {
     if (!p.ddim) {
-      if (p.grad != nullptr) mean = add(mean, mul(var, p.grad[i]));
-      const float z = p.noise[i];
-      out = add(mean, mul(mul(nonzero, expf(mul(0.5f, logvar))), z));
+      if (p.grad != nullptr) mean = add(mean, mul(var, g));
+      r.out = add(mean, mul(mul(nonzero, expf(mul(0.5f, logvar))), z));
     } else {
       if (p.grad != nullptr) {
         float e = __fdiv_rn(sub(mul(sr, x), x0), srm1);
-        e = sub(e, mul(sqrtf(sub(1.0f, acp)), p.grad[i]));
+        e = sub(e, mul(sqrtf(sub(1.0f, acp)), g));
         x0 = sub(mul(sr, x), mul(srm1, e));
       }
       const float e2 = __fdiv_rn(sub(mul(sr, x), x0), srm1);
@@ -102,11 +88,68 @@ __global__ void posterior_kernel(const PostArgs p) {
                               sqrtf(sub(1.0f, __fdiv_rn(acp, acp_prev))));
       const float mean_pred =
           add(mul(x0, sqrtf(acp_prev)), mul(sqrtf(sub(sub(1.0f, acp_prev), mul(sigma, sigma))), e2));
-      const float z = p.noise[i];
-      out = add(mean_pred, mul(mul(nonzero, sigma), z));
+      r.out = add(mean_pred, mul(mul(nonzero, sigma), z));
     }
-    p.sample[i] = out;
-    if (p.pred_xstart != nullptr) p.pred_xstart[i] = x0;
+  }
+  r.x0 = x0;
+}
+
+// kVec = 4: every tensor is read and written as float4 (host guarantees c*hw % 4 == 0 and 16-byte aligned pointers, so a
+// vector never straddles two samples or the eps / variance halves of the model output); kVec = 1: any shape.
+template <int kVec>
+__global__ void posterior_kernel(const PostArgs p) {
+  pdl_enter();
+  const size_t chw = static_cast<size_t>(p.c) * p.hw;
+  const size_t total = static_cast<size_t>(p.n) * chw / kVec;
+  const int out_c = (p.var_type == GD_VAR_FIXED) ? p.c : 2 * p.c;
+  const bool learned = p.var_type != GD_VAR_FIXED;
+  const bool writes_sample = p.ddim == GD_DDIM_REVERSE || p.noise != nullptr;
+  for (size_t iv = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; iv < total;
+       iv += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t i = iv * kVec;
+    const size_t b = i / chw, r = i - b * chw;
+    // per-sample timestep index into the coefficient table (_extract_into_tensor, gaussian_diffusion.py:904-917)
+    const float* co = p.coef + static_cast<size_t>(p.t[b]) * GD_COEF_STRIDE;
+    const size_t mo = b * static_cast<size_t>(out_c) * p.hw + r;
+    float x[kVec], m[kVec], v[kVec], g[kVec], z[kVec];
+    if (kVec == 4) {
+      *reinterpret_cast<float4*>(x) = __ldcs(reinterpret_cast<const float4*>(p.x + i));
+      *reinterpret_cast<float4*>(m) = __ldcs(reinterpret_cast<const float4*>(p.model_out + mo));
+      if (learned) *reinterpret_cast<float4*>(v) = __ldcs(reinterpret_cast<const float4*>(p.model_out + mo + chw));
+      if (p.grad != nullptr) *reinterpret_cast<float4*>(g) = __ldcs(reinterpret_cast<const float4*>(p.grad + i));
+      if (p.noise != nullptr) *reinterpret_cast<float4*>(z) = __ldcs(reinterpret_cast<const float4*>(p.noise + i));
+    } else {
+      x[0] = p.x[i];
+      m[0] = p.model_out[mo];
+      if (learned) v[0] = p.model_out[mo + chw];
+      if (p.grad != nullptr) g[0] = p.grad[i];
+      if (p.noise != nullptr) z[0] = p.noise[i];
+    }
+    float o_mean[kVec], o_var[kVec], o_logvar[kVec], o_x0[kVec], o_out[kVec];
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) {
+      PostElem e;
+      posterior_elem(p, co, x[j], m[j], learned ? v[j] : 0.f, p.grad != nullptr ? g[j] : 0.f,
+                     p.noise != nullptr ? z[j] : 0.f, e);
+      o_mean[j] = e.mean;
+      o_var[j] = e.var;
+      o_logvar[j] = e.logvar;
+      o_x0[j] = e.x0;
+      o_out[j] = e.out;
+    }
+    if (kVec == 4) {
+      if (p.mean_out != nullptr) *reinterpret_cast<float4*>(p.mean_out + i) = *reinterpret_cast<const float4*>(o_mean);
+      if (p.var_out != nullptr) *reinterpret_cast<float4*>(p.var_out + i) = *reinterpret_cast<const float4*>(o_var);
+      if (p.logvar_out != nullptr) *reinterpret_cast<float4*>(p.logvar_out + i) = *reinterpret_cast<const float4*>(o_logvar);
+      if (writes_sample) *reinterpret_cast<float4*>(p.sample + i) = *reinterpret_cast<const float4*>(o_out);
+      if (p.pred_xstart != nullptr) *reinterpret_cast<float4*>(p.pred_xstart + i) = *reinterpret_cast<const float4*>(o_x0);
+    } else {
+      if (p.mean_out != nullptr) p.mean_out[i] = o_mean[0];
+      if (p.var_out != nullptr) p.var_out[i] = o_var[0];
+      if (p.logvar_out != nullptr) p.logvar_out[i] = o_logvar[0];
+      if (writes_sample) p.sample[i] = o_out[0];
+      if (p.pred_xstart != nullptr) p.pred_xstart[i] = o_x0[0];
+    }
   }
 }
 
@@ -405,8 +448,20 @@ extern "C" int gd_posterior_step(const gd_posterior_desc* d, void* stream) {
   p.n = d->n; p.c = d->c; p.hw = d->hw;
   p.var_type = d->var_type; p.mean_type = d->mean_type; p.clip = d->clip_denoised; p.ddim = d->ddim; p.eta = d->eta;
   const size_t total = static_cast<size_t>(d->n) * d->c * d->hw;
-  GD_CHECK_CUDA(launch_pdl(posterior_kernel, dim3(grid_for(total, 256)), dim3(256), 0,
-                           reinterpret_cast<cudaStream_t>(stream), p));
+  uintptr_t align = 0;
+  for (const void* q : {static_cast<const void*>(d->x), static_cast<const void*>(d->model_out),
+                        static_cast<const void*>(d->grad), static_cast<const void*>(d->noise),
+                        static_cast<const void*>(d->sample), static_cast<const void*>(d->pred_xstart),
+                        static_cast<const void*>(d->mean_out), static_cast<const void*>(d->var_out),
+                        static_cast<const void*>(d->logvar_out)})
+    align |= reinterpret_cast<uintptr_t>(q);
+  const bool vec4 = (static_cast<size_t>(d->c) * d->hw) % 4 == 0 && (align & 15u) == 0;
+  if (vec4)
+    GD_CHECK_CUDA(launch_pdl(posterior_kernel<4>, dim3(grid_for(total / 4, 256, 148 * 8)), dim3(256), 0,
+                             reinterpret_cast<cudaStream_t>(stream), p));
+  else
+    GD_CHECK_CUDA(launch_pdl(posterior_kernel<1>, dim3(grid_for(total, 256)), dim3(256), 0,
+                             reinterpret_cast<cudaStream_t>(stream), p));
   count_launch(1);
   return 0;
 }
