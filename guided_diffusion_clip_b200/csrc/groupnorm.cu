@@ -548,40 +548,55 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_apply_kernel(const __half* __re
 // mean / rstd from the partials a producing conv's epilogue emitted (gd_conv_desc.stats_out): per 32-pixel row
 // block and 4-channel chunk (sum, sum of squares).  The normalised tensor may be the concatenation of two conv
 // outputs (c0 channels from p0, then c1 from p1); a group may straddle the boundary.
-// One CTA per (group, image); fixed-order tree reduction in fp64 -> bitwise reproducible.
+// One warp per (group, image); fixed-order reduction in fp64 -> bitwise reproducible.
 // ---------------------------------------------------------------------------------------------
+// kW warps share one (group, image): kW = 1 for layers with few partial rows (one warp each, four per CTA, no block
+// barrier), kW = 4 for the full-resolution layers (512 / 128 rows per image) so that every lane still has only a
+// handful of independent loads in flight.
+template <int kW>
 __global__ void __launch_bounds__(128)
 gn_finalize_partials_kernel(const float* __restrict__ p0, int c0, int ld0, const float* __restrict__ p1, int c1,
-                            int ld1, int rows_per_image, double inv_count, float eps, float* __restrict__ out) {
+                            int ld1, int rows_per_image, int n_img, double inv_count, float eps, float* __restrict__ out) {
   pdl_enter();
-  __shared__ double sh[2][128];
-  const int g = blockIdx.x, n = blockIdx.y, tid = threadIdx.x;
+  __shared__ double sh[2][4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int item = kW == 1 ? blockIdx.x * 4 + warp : blockIdx.x;
+  const bool active = item < kGroups * n_img;
+  const int g = item % kGroups, n = item / kGroups;
   const int cpg = (c0 + c1) / kGroups;
   const int ch_lo = g * cpg, ch_hi = ch_lo + cpg;
   double s = 0.0, ss = 0.0;
-#pragma unroll 4  // independent loads of 4 rows in flight (the kernel is pure latency)
-  for (int r = tid; r < rows_per_image; r += 128) {
-    const size_t row = static_cast<size_t>(n) * rows_per_image + r;
-    for (int ch = ch_lo; ch < ch_hi; ch += 4) {
-      const float* src = ch < c0 ? p0 + (row * ld0 + (ch >> 2)) * 2 : p1 + (row * ld1 + ((ch - c0) >> 2)) * 2;
-      const float2 v = *reinterpret_cast<const float2*>(src);
-      s += v.x;
-      ss += v.y;
+  if (active) {
+#pragma unroll 4
+    for (int r = (kW == 1 ? lane : threadIdx.x); r < rows_per_image; r += 32 * kW) {
+      const size_t row = static_cast<size_t>(n) * rows_per_image + r;
+      for (int ch = ch_lo; ch < ch_hi; ch += 4) {
+        const float* src = ch < c0 ? p0 + (row * ld0 + (ch >> 2)) * 2 : p1 + (row * ld1 + ((ch - c0) >> 2)) * 2;
+        const float2 v = __ldcg(reinterpret_cast<const float2*>(src));
+        s += v.x;
+        ss += v.y;
+      }
     }
   }
-  sh[0][tid] = s;
-  sh[1][tid] = ss;
-  __syncthreads();
-  for (int o = 64; o > 0; o >>= 1) {
-    if (tid < o) {
-      sh[0][tid] += sh[0][tid + o];
-      sh[1][tid] += sh[1][tid + o];
+  // fixed-order fp64 reduction -> bitwise reproducible
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  if (kW == 4) {
+    if (lane == 0) {
+      sh[0][warp] = s;
+      sh[1][warp] = ss;
     }
     __syncthreads();
+    s = (sh[0][0] + sh[0][1]) + (sh[0][2] + sh[0][3]);
+    ss = (sh[1][0] + sh[1][1]) + (sh[1][2] + sh[1][3]);
+    if (warp != 0) return;
   }
-  if (tid == 0) {
-    const double mean = sh[0][0] * inv_count;
-    double var = sh[1][0] * inv_count - mean * mean;
+  if (active && lane == 0) {
+    const double mean = s * inv_count;
+    double var = ss * inv_count - mean * mean;
     if (var < 0.0) var = 0.0;
     float* o = out + (static_cast<size_t>(n) * kGroups + g) * 2;
     o[0] = static_cast<float>(mean);
@@ -604,9 +619,14 @@ extern "C" int gd_groupnorm_finalize_partials(const float* p0, int32_t c0, int32
              "gd_groupnorm_finalize_partials: needs channels-per-group %% 4 == 0 (c0=%d c1=%d)", c0, c1);
   GD_REQUIRE(ld0 >= c0 / 4 && (p1 == nullptr || ld1 >= c1 / 4), "gd_groupnorm_finalize_partials: bad leading dimension");
   const double inv_count = 1.0 / (static_cast<double>(hw) * static_cast<double>(c / kGroups));
-  GD_CHECK_CUDA(launch_pdl(gn_finalize_partials_kernel, dim3(kGroups, n), dim3(128), 0,
-                           reinterpret_cast<cudaStream_t>(stream), p0, c0, ld0, p1, c1, ld1, rows_per_image, inv_count, eps,
-                           mean_rstd));
+  if (rows_per_image >= 128)
+    GD_CHECK_CUDA(launch_pdl(gn_finalize_partials_kernel<4>, dim3(kGroups * n), dim3(128), 0,
+                             reinterpret_cast<cudaStream_t>(stream), p0, c0, ld0, p1, c1, ld1, rows_per_image, n,
+                             inv_count, eps, mean_rstd));
+  else
+    GD_CHECK_CUDA(launch_pdl(gn_finalize_partials_kernel<1>, dim3((kGroups * n + 3) / 4), dim3(128), 0,
+                             reinterpret_cast<cudaStream_t>(stream), p0, c0, ld0, p1, c1, ld1, rows_per_image, n,
+                             inv_count, eps, mean_rstd));
   count_launch(1);
   return 0;
 }
