@@ -95,6 +95,7 @@ SIGNATURES = {
     "gd_conv_in3x3": (C.c_int, [C.POINTER(ConvInDesc), vp]),
     "gd_im2col3x3_s2_nhwc": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, i32, vp]),
     "gd_upsample2_nhwc": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, i32, vp]),
+    "gd_col2im3x3_s2_nhwc": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, i32, vp]),
     "gd_add_emb_nhwc": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, vp]),
     "gd_attention_fwd_hd": (C.c_int, [vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, vp]),
     "gd_tap_gather3x3": (C.c_int, [vp, i32, vp, vp, i32, i32, i32, i32, C.c_float, vp]),

@@ -720,6 +720,51 @@ add_emb_nhwc_kernel(__half* __restrict__ x, int ld, const float* __restrict__ em
   }
 }
 
+// transpose of im2col3x3_s2_kernel: dx[n][y][x][c] = sum over the (ky, kx) with y = 2*yo + ky - 1, x = 2*xo + kx - 1 of
+// dcols[n][yo][xo][(ky*3+kx)*C + c]  (1, 2 or 4 terms per pixel); fp32 sums, fp16 result
+__global__ void __launch_bounds__(256)
+col2im3x3_s2_kernel(const __half* __restrict__ dcols, int ld, __half* __restrict__ dx, int ld_dx, int n, int h, int w,
+                    int c8, int ho, int wo) {
+  const size_t total = static_cast<size_t>(n) * h * w * c8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int cc = static_cast<int>(i % c8);
+    size_t r = i / c8;
+    const int x = static_cast<int>(r % w);
+    r /= w;
+    const int y = static_cast<int>(r % h);
+    const int img = static_cast<int>(r / h);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int ty = y + 1 - ky;
+      if (ty < 0 || (ty & 1) != 0 || (ty >> 1) >= ho) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int tx = x + 1 - kx;
+        if (tx < 0 || (tx & 1) != 0 || (tx >> 1) >= wo) continue;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(
+                                  dcols + ((static_cast<size_t>(img) * ho + (ty >> 1)) * wo + (tx >> 1)) * ld +
+                                  (ky * 3 + kx) * c8 * 8) + cc);
+        const __half2* hv = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(hv[j]);
+          acc[2 * j] += f.x;
+          acc[2 * j + 1] += f.y;
+        }
+      }
+    }
+    uint4 o;
+    __half2* ho2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ho2[j] = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
+    *(reinterpret_cast<uint4*>(dx + ((static_cast<size_t>(img) * h + y) * w + x) * ld_dx) + cc) = o;
+  }
+}
+
 int check_nhwc(const char* who, const void* x, int ld, const void* out, int ld_out, int n, int h, int w, int c, int c_out) {
   GD_REQUIRE(x && out, "%s: null pointer", who);
   GD_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, "%s: bad shape n=%d h=%d w=%d c=%d (c must be a multiple of 8)",
@@ -764,6 +809,18 @@ extern "C" int gd_add_emb_nhwc(void* x, int32_t ld, const float* emb, int32_t ld
   const size_t total = static_cast<size_t>(n) * hw * (c / 8);
   add_emb_nhwc_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<__half*>(x), ld, emb, ld_emb, n, hw, c / 8);
+  GD_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
+
+extern "C" int gd_col2im3x3_s2_nhwc(const void* dcols, int32_t ld, void* dx, int32_t ld_dx, int32_t n, int32_t h, int32_t w,
+                                    int32_t c, void* stream) {
+  if (int rc = check_nhwc("gd_col2im3x3_s2_nhwc", dx, ld_dx, dcols, ld, n, h, w, c, 9 * c)) return rc;
+  const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
+  const size_t total = static_cast<size_t>(n) * h * w * (c / 8);
+  col2im3x3_s2_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half*>(dcols), ld, reinterpret_cast<__half*>(dx), ld_dx, n, h, w, c / 8, ho, wo);
   GD_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
   return 0;

@@ -413,8 +413,6 @@ class Emitter:
         if not film:
             # h = h + emb_out before the second GroupNorm (unet.py:253-255): one in-place pass; the statistics the
             # conv fused into its epilogue describe the tensor before the add, so they are recomputed
-            if tape is not None:
-                raise NotImplementedError("data-gradient of ResBlocks without use_scale_shift_norm is not built")
             self.prog.add("gd_add_emb_nhwc", C.c_void_p(h1.ptr), h1.ld, C.c_void_p(film_ptr), film_all.shape[1], n,
                           ho * wo, r.cout)
             self._producers.pop((h1.buf.data_ptr(), h1.off, h1.c), None)
@@ -434,7 +432,8 @@ class Emitter:
             else:
                 self.conv(b, w2, self.f32(f"{k}.out_layers.3.bias"), r.cout, out, res=x, res_mode=rmode)
         if tape is not None:
-            tape.append(("res", r, x, st1, h1, st2, film_ptr, film_all.shape[1], out))
+            # without FiLM the saved h1 already holds h + emb_out (what the second GroupNorm saw): d(h + e)/dh = 1
+            tape.append(("res", r, x, st1, h1, st2, film_ptr if film else None, film_all.shape[1] if film else 0, out))
 
     def resample(self, l: ResampleSpec, x: View, out: View) -> None:
         """Downsample.op (3x3 stride-2 conv, unet.py:125-136) as a strided gather + taps=1 GEMM over K = 9*C;
@@ -662,9 +661,12 @@ class ClassifierPlan:
                         hh, ww = hh // 2, ww // 2
                     o = em.act(n, hh, ww, l.cout)
                     em.res_block(l, cur, o, film_all, tape)
-                elif isinstance(l, ResampleSpec):
-                    raise NotImplementedError("classifier_resblock_updown=False: the data-gradient of Downsample's "
-                                              "strided conv is not built (factory default is True, script_util.py:39)")
+                elif isinstance(l, ResampleSpec):  # classifier_resblock_updown=False: Downsample.op, 3x3 stride 2
+                    assert l.mode == "down"
+                    hh, ww = (hh - 1) // 2 + 1, (ww - 1) // 2 + 1
+                    o = em.act(n, hh, ww, l.ch)
+                    em.resample(l, cur, o)
+                    tape.append(("down", l, cur, o))
                 else:
                     o = em.act(n, hh, ww, l.ch)
                     em.attn_block(l, cur, o, tape)
@@ -743,6 +745,16 @@ class ClassifierPlan:
                 g_in = bw.scratch("gB" if flip else "gA", n, x.h, x.w, a.ch)
                 bw.gn_bwd(x, st_a, em.f32(f"{k}.norm.weight"), em.f32(f"{k}.norm.bias"), d_a, g_in, silu=False, add=g,
                           add_mode=L.GN_SAME)
+                g = g_in
+            elif kind == "down":  # dX of the strided conv: dcols = dY x W (GEMM), then the transpose of the gather
+                _, l, x, o = entry
+                wt = pack_conv3x3(em.P[f"{l.key}.weight"])[:l.ch].t().contiguous()  # [9*C_in][C_out]
+                dcols = bw.scratch("dcols", n, o.h, o.w, 9 * l.ch)
+                bw.conv(g, wt, None, 9 * l.ch, dcols, taps=1)
+                flip ^= 1
+                g_in = bw.scratch("gB" if flip else "gA", n, x.h, x.w, l.ch)
+                bw.prog.add("gd_col2im3x3_s2_nhwc", C.c_void_p(dcols.ptr), dcols.ld, C.c_void_p(g_in.ptr), g_in.ld, n, x.h,
+                            x.w, l.ch)
                 g = g_in
             else:  # conv_in: dX in fp32 NCHW, loss scale undone, user scale applied at run time by self.scale
                 _, l, o = entry

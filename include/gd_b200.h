@@ -112,7 +112,8 @@ int gd_conv_in3x3(const gd_conv_in_desc* desc, void* stream);
  * use_scale_shift_norm=False-style checkpoints (script_util.py:57-60).  fp16 NHWC views, c % 8 == 0.
  *   gd_im2col3x3_s2_nhwc: Downsample.op = conv3x3 stride 2 pad 1 (unet.py:125-136) as a gather to
  *     out[n][ho][wo][tap*c + ci] = x[n][2*yo+ky-1][2*xo+kx-1][ci] (0 outside), ho = (h-1)/2+1, followed by
- *     gd_conv_igemm with taps = 1 over K = 9*c (same packed weight order as a 3x3 conv);
+ *     gd_conv_igemm with taps = 1 over K = 9*c (same packed weight order as a 3x3 conv); gd_col2im3x3_s2_nhwc is its
+ *     transpose for the classifier's data-gradient;
  *   gd_upsample2_nhwc: F.interpolate(scale_factor=2, mode="nearest") of Upsample.forward (unet.py:100-110);
  *   gd_add_emb_nhwc: h += emb_out[n][c] in place (unet.py:253-254), emb fp32 with row stride ld_emb. */
 int gd_im2col3x3_s2_nhwc(const void* x, int32_t ld, void* out, int32_t ld_out, int32_t n, int32_t h, int32_t w, int32_t c,
@@ -120,6 +121,11 @@ int gd_im2col3x3_s2_nhwc(const void* x, int32_t ld, void* out, int32_t ld_out, i
 int gd_upsample2_nhwc(const void* x, int32_t ld, void* out, int32_t ld_out, int32_t n, int32_t h, int32_t w, int32_t c,
                       void* stream);
 int gd_add_emb_nhwc(void* x, int32_t ld, const float* emb, int32_t ld_emb, int32_t n, int32_t hw, int32_t c, void* stream);
+/* Data-gradient of Downsample.op: the transpose of gd_im2col3x3_s2_nhwc.  dcols = dY x W (gd_conv_igemm, taps = 1, packed
+ * weights transposed to [9*c][c_out]) as fp16 [n][ho][wo][9*c]; dx[n][y][x][ci] sums the 1, 2 or 4 tap columns that read
+ * input pixel (y, x) in the forward pass. */
+int gd_col2im3x3_s2_nhwc(const void* dcols, int32_t ld, void* dx, int32_t ld_dx, int32_t n, int32_t h, int32_t w, int32_t c,
+                         void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * GroupNorm32 (+SiLU) (+FiLM scale/shift) (+avgpool2 / nearest-upsample2), nn.py:17-19,93-100 with

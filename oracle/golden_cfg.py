@@ -304,3 +304,9 @@ def c1_noise():
     th.manual_seed(C1_NOISE_SEED)
     shape = (C1_BATCH, 3, 64, 64)
     return th.randn(*shape), [th.randn(*shape) for _ in range(C1_STEPS)]
+
+# classifier without use_scale_shift_norm (classifier_defaults() flag; additive embedding in every ResBlock)
+CLF_PLAIN_SEED = 45
+CLF_PLAIN_KW = dict(CLASSIFIER_KW, classifier_use_scale_shift_norm=False)
+CLF_CONVDOWN_SEED = 46
+CLF_CONVDOWN_KW = dict(CLASSIFIER_KW, classifier_resblock_updown=False)  # Downsample.op = 3x3 stride-2 conv

@@ -56,6 +56,19 @@ def main():
         r = d.ddim_reverse_sample(lambda x_, t_, **k: mo, xs, th.tensor([i] * xs.shape[0]), model_kwargs={})
         out[f"reverse_{name}_sample"] = r["sample"].numpy()
         out[f"reverse_{name}_x0"] = r["pred_xstart"].numpy()
+    # classifier variant: logits and the guidance gradient of scripts/classifier_sample.py:54-61
+    import torch.nn.functional as F
+    for tag, kw, seed in (("plain", cfg.CLF_PLAIN_KW, cfg.CLF_PLAIN_SEED),
+                          ("convdown", cfg.CLF_CONVDOWN_KW, cfg.CLF_CONVDOWN_SEED)):
+        clf = rsu.create_classifier(**kw)
+        clf.load_state_dict(make_state_dict({k: tuple(v.shape) for k, v in clf.state_dict().items()}, seed), strict=True)
+        clf.eval()
+        x, t, y = cfg.model_inputs()
+        out[f"clf_{tag}_logits"] = clf(x, t).numpy()
+        with th.enable_grad():
+            x_in = x.detach().requires_grad_(True)
+            sel = F.log_softmax(clf(x_in, t), dim=-1)[range(len(x)), y.view(-1)]
+            out[f"clf_{tag}_grad"] = th.autograd.grad(sel.sum(), x_in)[0].numpy()
     path = os.path.join(ROOT, "tests", "golden", "variants_golden.npz")
     np.savez_compressed(path, **out)
     for k, v in out.items():

@@ -78,6 +78,23 @@ def test_ddim_reverse_oracle_bit_exact(V, name):
     assert th.equal(r["pred_xstart"], th.from_numpy(V[f"reverse_{name}_x0"]))
 
 
+CLF_VARIANTS = {"plain": (cfg.CLF_PLAIN_KW, cfg.CLF_PLAIN_SEED), "convdown": (cfg.CLF_CONVDOWN_KW, cfg.CLF_CONVDOWN_SEED)}
+
+
+@pytest.mark.parametrize("tag", sorted(CLF_VARIANTS))
+def test_classifier_variant_oracle_matches_reference(V, tag):
+    kw, seed = CLF_VARIANTS[tag]
+    m = su.create_classifier(**kw)
+    sd = om.make_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed)
+    x, t, y = cfg.model_inputs()
+    with th.no_grad():
+        logits = om.classifier_forward(sd, x, t, **cfg.CLF_STRUCT)
+    grad = om.classifier_guidance(sd, x, t, y, 1.0, **cfg.CLF_STRUCT)
+    assert float((logits - th.from_numpy(V[f"clf_{tag}_logits"])).abs().max()) < 2e-4
+    ref = th.from_numpy(V[f"clf_{tag}_grad"])
+    assert float((grad - ref).abs().max() / ref.abs().max()) < 2e-4
+
+
 def test_factory_defaults_build_a_model():
     """create_model_and_diffusion(**model_and_diffusion_defaults()) — the call every reference script makes — builds."""
     model, diffusion = su.create_model_and_diffusion(**su.model_and_diffusion_defaults())
@@ -274,3 +291,44 @@ def test_posterior_scalar_and_vector_paths_agree_with_oracle(lib, name, hw):
     s1, p1 = run(1)
     assert th.equal(s0, s1) and th.equal(p0, p1)
     assert _rel(s0, ref["sample"]) < 2e-6 and _rel(p0, ref["pred_xstart"]) < 2e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", sorted(CLF_VARIANTS))
+def test_classifier_variant_logits_and_gradient_match_reference(lib, V, tag):
+    """classifier_use_scale_shift_norm=False / classifier_resblock_updown=False: forward and data-gradient (the
+    reference's own closure through autograd, and the ClassifierGuidance fast path) against the real reference."""
+    from guided_diffusion_clip_b200.sampler import ClassifierGuidance
+    kw, seed = CLF_VARIANTS[tag]
+    m = su.create_classifier(**kw)
+    sd = om.make_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    x, t, y = (v.cuda() for v in cfg.model_inputs())
+    with th.no_grad():
+        logits = m(x, t)
+    ref_l = th.from_numpy(V[f"clf_{tag}_logits"]).cuda()
+    ref_g = th.from_numpy(V[f"clf_{tag}_grad"]).cuda()
+    print(f"{tag} classifier logits rel err {_rel(logits, ref_l):.3e}")
+    assert _rel(logits, ref_l) < TOL
+    with th.enable_grad():
+        x_in = x.detach().requires_grad_(True)
+        sel = F.log_softmax(m(x_in, t), dim=-1)[range(len(x)), y.view(-1)]
+        g1 = th.autograd.grad(sel.sum(), x_in)[0]
+    g2 = ClassifierGuidance(m, 1.0)(x, t, y=y)
+    print(f"{tag} classifier gradient rel err {_rel(g1, ref_g):.3e} (closure), {_rel(g2, ref_g):.3e} (guidance object)")
+    assert _rel(g1, ref_g) < TOL and _rel(g2, ref_g) < TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,h,w,c", [(2, 16, 16, 64), (1, 9, 13, 128), (3, 8, 8, 192)])
+def test_col2im_is_the_transpose_of_the_strided_gather(lib, n, h, w, c):
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    dcols = (_rand((n, ho, wo, 9 * c), 81) * 0.5).half()
+    dx = th.full((n, h, w, c + 8), 3.0, dtype=th.float16, device="cuda")
+    L.check(lib.gd_col2im3x3_s2_nhwc(dcols.data_ptr(), 9 * c, dx.data_ptr() + 16, c + 8, n, h, w, c, _stream()))
+    th.cuda.synchronize()
+    cols = dcols.float().reshape(n, ho * wo, 9, c).permute(0, 3, 2, 1).reshape(n, c * 9, ho * wo)  # F.fold layout
+    ref = F.fold(cols, (h, w), 3, padding=1, stride=2)
+    assert _rel(dx[..., 8:].permute(0, 3, 1, 2), ref) < 2e-3
+    assert float((dx[..., :8] - 3.0).abs().max()) == 0.0
