@@ -792,6 +792,10 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
     GD_REQUIRE(d->out_mode == GD_OUT_NHWC_F16 && d->cout % 64 == 0 && d->n_pad == d->cout && bw * bh >= 32 &&
                    (d->bn == 0 || d->bn % 64 == 0),
                "gd_conv_igemm: fused GroupNorm statistics need fp16 NHWC output, cout %% 64 == 0 and >= 32 pixels/image");
+  if (want_stats)
+    GD_REQUIRE(bi == 1 || ((d->w + bw - 1) / bw) * ((d->h + bh - 1) / bh) == 1,
+               "gd_conv_igemm: fused GroupNorm statistics are not defined for %dx%d images (several images per tile and "
+               "several tiles per image); gd_conv_stats_rows returns 0 for this geometry", d->h, d->w);
 
   if (g_num_sms == 0) {
     int dev = 0;
@@ -951,6 +955,14 @@ extern "C" int64_t gd_conv_stats_rows(int32_t n, int32_t h, int32_t w, int32_t* 
     return 0;
   }
   const int tiles_per_group = ((w + bw - 1) / bw) * ((h + bh - 1) / bh);
+  // Several images per tile AND several tiles per image (small images that are not a power of two, e.g. 12x12: two
+  // images per 8x8 tile, four tiles per image): the per-quarter rows of one image would interleave with its tile
+  // mate's, but gd_groupnorm_finalize_partials reads a contiguous block of rows per image -> no fused statistics
+  // for that geometry (the caller falls back to gd_groupnorm_stats).
+  if (bi > 1 && tiles_per_group > 1) {
+    if (rows_per_image) *rows_per_image = 0;
+    return 0;
+  }
   const int groups = (n + bi - 1) / bi;
   // a tile that lies inside one image (bi == 1) emits ONE partial row, otherwise one per 32-pixel quarter
   const int per_tile = bi == 1 ? 1 : 4;

@@ -473,7 +473,7 @@ class Emitter:
         self.conv(g, pack_1x1(self.P[f"{k}.qkv.weight"]), self.f32(f"{k}.qkv.bias"), 3 * a.ch, qkv, taps=1)
         order = L.QKV_NEW if a.new_order else L.QKV_LEGACY
         self.keep.append(lse)
-        if hd == 64:
+        if hd == 64 and ((h * w) % 64 == 0 or keep):  # (token counts off the 64 grid: the any-length kernel, forward only)
             self.prog.add("gd_attention_fwd", C.c_void_p(qkv.ptr), qkv.ld, C.c_void_p(att.ptr), att.ld, _p(lse), n, h * w,
                           a.heads, order)
         else:

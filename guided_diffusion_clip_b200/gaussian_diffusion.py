@@ -272,7 +272,7 @@ class GaussianDiffusion:
         stepper = None if denoised_fn is not None else GraphedStepper.cached(
             self, model, cond_fn, tuple(x.shape), x.device, model_kwargs, clip_denoised, ddim, eta)
         if stepper is not None:
-            return stepper.step(x, t, noise=noise, labels=(model_kwargs or {}).get("y"))
+            return stepper.step(x, t, noise=noise, labels=(model_kwargs or {}).get("y"), model_kwargs=model_kwargs)
         model_out = self._call_model(model, x, t, model_kwargs)
         mean_type = None
         if denoised_fn is not None:

@@ -52,22 +52,28 @@ class GraphedStepper:
 
     @staticmethod
     def cached(diffusion, model, cond_fn, shape, device, model_kwargs, clip_denoised, ddim, eta):
-        """Stepper for this (diffusion, model, guidance, shape) or None when the fast path does not apply.
-        Cached on the diffusion object; invalidated when either model's parameters change."""
+        """Stepper for this (diffusion, model, guidance, shape) or None when no fast path applies.  Cached on the
+        diffusion object; invalidated when any involved model's parameters change.  Two kinds: the specialised
+        GraphedStepper (class-conditional / unconditional UNetModel + ClassifierGuidance: classifier forked onto a
+        second stream) and GenericGraphedStepper (every other combination of OUR model classes and guidance objects,
+        e.g. SuperResModel + low_res, the fork's clip_feat models, CLIPGuidance)."""
         if os.environ.get("GD_B200_NO_GRAPH", "0") == "1" or th.device(device).type != "cuda":
             return None
         m = model.model if isinstance(model, ModelFn) else model
-        if type(m) is not UNetModel:
+        if not isinstance(m, UNetModel):
             return None
-        if cond_fn is not None and not isinstance(cond_fn, ClassifierGuidance):
+        sig = GenericGraphedStepper.signature(m, model, cond_fn, model_kwargs, device)
+        if sig is None:
             return None
-        key = (id(m), m._param_version, getattr(model, "class_cond", True),
-               (id(cond_fn.classifier), cond_fn.classifier._param_version, cond_fn.classifier_scale) if cond_fn else None,
-               tuple(shape), str(device), bool(clip_denoised), bool(ddim), float(eta))
+        key = (sig, tuple(shape), str(device), bool(clip_denoised), bool(ddim), float(eta))
         cache = diffusion.__dict__.setdefault("_steppers", {})
         if key not in cache:
-            cache[key] = GraphedStepper.maybe_create(diffusion, model, cond_fn, shape, device, model_kwargs,
-                                                     clip_denoised, ddim, eta)
+            st = GraphedStepper.maybe_create(diffusion, model, cond_fn, shape, device, model_kwargs, clip_denoised,
+                                             ddim, eta)
+            if st is None:
+                st = GenericGraphedStepper(diffusion, model, cond_fn, tuple(shape), device, model_kwargs,
+                                           clip_denoised, ddim, eta)
+            cache[key] = st
         return cache[key]
 
     @staticmethod
@@ -201,7 +207,7 @@ class GraphedStepper:
         return n
 
     def step(self, img: th.Tensor, t: th.Tensor, noise: Optional[th.Tensor] = None,
-             labels: Optional[th.Tensor] = None):
+             labels: Optional[th.Tensor] = None, model_kwargs=None):
         if labels is not None and self.y is not None:
             self.y.copy_(labels)
             if self.uses_y:
@@ -210,6 +216,94 @@ class GraphedStepper:
         for sl, unet, _, _, _ in self.parts:
             unet.x_in.copy_(img[sl])
         self.t_idx.copy_(t)
+        if noise is None:
+            self.noise.normal_()
+        else:
+            self.noise.copy_(noise)
+        self.graph.replay()
+        return {"sample": self.sample.clone(), "pred_xstart": self.x0.clone()}
+
+
+class GenericGraphedStepper:
+    """One sampling step of ANY of our own model classes (UNetModel, SuperResModel, the fork's UNetModel_clip_feat /
+    SRImageModel_Feat, optionally behind ModelFn) with no guidance, ClassifierGuidance or CLIPGuidance, as a single
+    CUDA-graph replay.  The generic per-step code of GaussianDiffusion._sample_step — model call through the respacing
+    wrapper, cond_fn call, fused update — is captured once over static copies of x, t, the noise and every tensor in
+    model_kwargs; per step the host copies the inputs into those buffers, draws the noise and replays.  The noise is
+    drawn with the same generator call count as the eager path (one normal_ of x's shape per step), so eager and
+    graphed loops produce identical bits."""
+
+    @staticmethod
+    def signature(m, model, cond_fn, model_kwargs, device):
+        """Hashable description of everything the captured graph depends on, or None if something is not ours."""
+        from .clip import CLIPGuidance
+        dev = th.device(device)
+        if cond_fn is None:
+            csig = None
+        elif isinstance(cond_fn, ClassifierGuidance):
+            csig = ("clf", id(cond_fn.classifier), cond_fn.classifier._param_version, cond_fn.classifier_scale)
+        elif isinstance(cond_fn, CLIPGuidance):
+            if not (isinstance(cond_fn.text, th.Tensor) and cond_fn.text.device.type == "cuda"):
+                return None
+            csig = ("clip", id(cond_fn.encoder), getattr(cond_fn.encoder, "_param_version", 0), id(cond_fn.text),
+                    cond_fn.scale)
+        else:
+            return None
+        ksig = []
+        for k in sorted(model_kwargs or {}):
+            v = model_kwargs[k]
+            if isinstance(v, th.Tensor):
+                if v.device.type != dev.type:
+                    return None
+                ksig.append((k, tuple(v.shape), str(v.dtype)))
+            elif v is None or isinstance(v, (bool, int, float, str)):
+                ksig.append((k, v))
+            else:
+                return None
+        return (id(m), m._param_version, type(model).__name__, getattr(model, "class_cond", None), csig, tuple(ksig))
+
+    def __init__(self, diffusion, model, cond_fn, shape, device, model_kwargs, clip_denoised, ddim, eta):
+        from .engine import norm_device
+        dev = th.device(norm_device(device))
+        self.diffusion, self.model, self.cond_fn = diffusion, model, cond_fn
+        self.clip, self.ddim, self.eta = clip_denoised, ddim, eta
+        self.x = th.zeros(shape, dtype=th.float32, device=dev)
+        self.t = th.zeros((shape[0],), dtype=th.int64, device=dev)
+        self.noise = th.zeros(shape, dtype=th.float32, device=dev)
+        self.sample = th.empty(shape, dtype=th.float32, device=dev)
+        self.x0 = th.empty(shape, dtype=th.float32, device=dev)
+        self.kw = {k: (v.detach().clone() if isinstance(v, th.Tensor) else v) for k, v in (model_kwargs or {}).items()}
+        self.launches_per_step = 0
+        # eager warm-up on a side stream: builds every plan (host-side weight packing, allocations) outside the capture
+        side = th.cuda.Stream(device=dev)
+        side.wait_stream(th.cuda.current_stream())
+        with th.cuda.stream(side):
+            lib = L.load()
+            lib.gd_launch_count_reset()
+            self._body()
+            self.launches_per_step = int(lib.gd_launch_count())
+        th.cuda.current_stream().wait_stream(side)
+        th.cuda.synchronize()
+        self.graph = th.cuda.CUDAGraph()
+        with th.cuda.graph(self.graph):
+            self._body()
+
+    def _body(self) -> None:
+        d = self.diffusion
+        with th.no_grad():
+            model_out = d._call_model(self.model, self.x, self.t, self.kw)
+            grad = None
+            if self.cond_fn is not None:
+                grad = d._wrap(self.cond_fn)(self.x, d._scale_timesteps(self.t), **self.kw).float().contiguous()
+            d._launch_posterior(x=self.x, t=self.t, model_out=model_out, grad=grad, noise=self.noise, sample=self.sample,
+                                pred_xstart=self.x0, clip_denoised=self.clip, ddim=self.ddim, eta=self.eta)
+
+    def step(self, img: th.Tensor, t: th.Tensor, noise: Optional[th.Tensor] = None, labels=None, model_kwargs=None):
+        self.x.copy_(img)
+        self.t.copy_(t)
+        for k, v in (model_kwargs or {}).items():
+            if isinstance(v, th.Tensor):
+                self.kw[k].copy_(v)
         if noise is None:
             self.noise.normal_()
         else:

@@ -266,3 +266,17 @@ def test_weight_packing_algebra_on_cpu():
     dcols = F.unfold(dy, 3, padding=1).view(n, co, 9, h * w).permute(0, 3, 2, 1).reshape(n, h * w, 9 * co)
     dx = (dcols @ pack_conv3x3_bwd(wt).float()[:ci].t()).permute(0, 2, 1).reshape(n, ci, h, w)
     assert th.allclose(dx, xg.grad, atol=1e-4)
+
+
+def test_fused_statistics_geometry_excludes_interleaved_images(lib):
+    """gd_conv_stats_rows: one partial row per 128-pixel tile (images >= 128 pixels per tile), four per tile when a tile
+    holds several WHOLE images (8x8), and none when several images share a tile AND an image spans several tiles
+    (12x12, 10x10: the rows of one image would interleave with its tile mate's) — found by the 48x48 model test."""
+    import ctypes
+    rpi = ctypes.c_int32(-1)
+    assert lib.gd_conv_stats_rows(4, 256, 256, ctypes.byref(rpi)) == 4 * 512 and rpi.value == 512
+    assert lib.gd_conv_stats_rows(4, 8, 8, ctypes.byref(rpi)) == 8 and rpi.value == 2
+    assert lib.gd_conv_stats_rows(3, 8, 8, ctypes.byref(rpi)) == 8 and rpi.value == 2   # last pair half empty
+    for hw in (12, 10, 6):
+        assert lib.gd_conv_stats_rows(4, hw, hw, ctypes.byref(rpi)) == 0 and rpi.value == 0
+    assert lib.gd_conv_stats_rows(4, 24, 24, ctypes.byref(rpi)) == 24 and rpi.value == 6

@@ -332,3 +332,23 @@ def test_col2im_is_the_transpose_of_the_strided_gather(lib, n, h, w, c):
     ref = F.fold(cols, (h, w), 3, padding=1, stride=2)
     assert _rel(dx[..., 8:].permute(0, 3, 1, 2), ref) < 2e-3
     assert float((dx[..., :8] - 3.0).abs().max()) == 0.0
+
+
+@pytest.mark.gpu
+def test_unet_on_an_image_size_off_the_64_token_grid(lib):
+    """48x48 input: attention over 12x12 = 144 tokens (64-wide heads go through the any-length kernel),
+    ragged conv tiles everywhere; against the oracle on the same weights."""
+    kw = dict(cfg.UNET_KW, image_size=48, attention_resolutions="12", channel_mult="1,2,4")
+    m = su.create_model(**kw)
+    sd = om.make_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, 77)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    g = th.Generator().manual_seed(78)
+    x = th.randn(3, 3, 48, 48, generator=g)
+    t, y = th.tensor([5, 500, 999]), th.tensor([0, 10, 999])
+    with th.no_grad():
+        ref = om.unet_forward(sd, x, t, y, num_res_blocks=1, channel_mult_len=3, head_dim=64, new_order=True)
+        out = m(x.cuda(), t.cuda(), y.cuda())
+    err = _rel(out, ref.cuda())
+    print(f"48x48 UNet vs oracle: rel err {err:.3e}")
+    assert err < TOL
