@@ -79,3 +79,32 @@ def test_superres_geometry_sweep(lib, hw, low_hw, batch):
     err = float((out - ref).abs().max() / ref.abs().max())
     print(f"super-res {low_hw} -> {hw}: rel err {err:.3e}")
     assert err < TOL
+
+
+@pytest.mark.parametrize("size,batch,over,levels", [
+    (64, 5, {}, 4), (64, 1, dict(classifier_depth=2), 4), (128, 3, {}, 5),
+    (128, 2, dict(classifier_attention_resolutions="32,16,8", classifier_width=128), 5)])
+def test_classifier_guidance_geometry_sweep(lib, size, batch, over, levels):
+    """Classifier logits and guidance gradient at odd batch sizes, depth 2 and the 5-level 128x128 structure
+    (script_util.py:244-255 channel_mult table) against the oracle."""
+    from guided_diffusion_clip_b200.sampler import ClassifierGuidance
+    kw = dict(cfg.CLASSIFIER_KW, image_size=size)
+    kw.update(over)
+    m = su.create_classifier(**kw)
+    sd = om.make_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, 700 + size + batch)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    g = th.Generator().manual_seed(800 + batch)
+    x = th.randn((batch, 3, size, size), generator=g)
+    t = th.randint(0, 1000, (batch,), generator=g)
+    y = th.randint(0, 1000, (batch,), generator=g)
+    okw = dict(num_res_blocks=kw["classifier_depth"], channel_mult_len=levels, head_dim=64)
+    with th.no_grad():
+        ref_l = om.classifier_forward(sd, x, t, **okw)
+        logits = m(x.cuda(), t.cuda()).cpu()
+    ref_g = om.classifier_guidance(sd, x, t, y, 2.5, **okw)
+    grad = ClassifierGuidance(m, 2.5)(x.cuda(), t.cuda(), y=y.cuda()).cpu()
+    el = float((logits - ref_l).abs().max() / ref_l.abs().max())
+    eg = float((grad - ref_g).abs().max() / ref_g.abs().max())
+    print(f"classifier {size}x{size} batch {batch} {over}: logits rel err {el:.3e}, gradient rel err {eg:.3e}")
+    assert el < TOL and eg < TOL
