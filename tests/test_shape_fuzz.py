@@ -108,3 +108,26 @@ def test_classifier_guidance_geometry_sweep(lib, size, batch, over, levels):
     eg = float((grad - ref_g).abs().max() / ref_g.abs().max())
     print(f"classifier {size}x{size} batch {batch} {over}: logits rel err {el:.3e}, gradient rel err {eg:.3e}")
     assert el < TOL and eg < TOL
+
+
+@pytest.mark.parametrize("hw,batch", [((64, 64), 3), ((96, 128), 1), ((200, 200), 2), ((50, 70), 5)])
+def test_clip_guidance_geometry_sweep(lib, hw, batch):
+    """CLIP guidance gradient for sampler resolutions equal to, above and below the encoder's input size, non-square
+    and at odd batch sizes (bilinear resize + its transpose, padded-token attention) against the CLIP oracle."""
+    from guided_diffusion_clip_b200 import clip as gclip
+    from oracle import oracle_clip as oc
+    enc = gclip.CLIPVisionEncoder(**cfg.CLIP_TINY)
+    sd = cfg.clip_state_dict({k: tuple(v.shape) for k, v in enc.state_dict().items()})
+    enc.load_state_dict(sd, strict=True)
+    enc = enc.cuda().eval()
+    g = th.Generator().manual_seed(900 + hw[0])
+    x = th.randn((batch, 3) + hw, generator=g).clamp(-1, 1)
+    txt = th.randn(batch, cfg.CLIP_TINY["projection_dim"], generator=g)
+    txt = txt / txt.norm(dim=-1, keepdim=True)
+    ckw = dict(heads=cfg.CLIP_TINY["num_attention_heads"], layers=cfg.CLIP_TINY["num_hidden_layers"],
+               patch=cfg.CLIP_TINY["patch_size"], image_size=cfg.CLIP_TINY["image_size"])
+    ref = oc.guidance(sd, x, txt, cfg.CLIP_SCALE, **ckw)
+    got = gclip.CLIPGuidance(enc, txt.cuda(), cfg.CLIP_SCALE)(x.cuda(), None).cpu()
+    err = float((got - ref).abs().max() / ref.abs().max())
+    print(f"CLIP guidance {hw} batch {batch}: rel err {err:.3e}")
+    assert err < TOL
