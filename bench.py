@@ -179,7 +179,7 @@ def run_reference_arm(args):
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -422,10 +422,34 @@ def run_gpu_arm(args):
             "value": 1.0 / (STEPS_PER_SAMPLE * s), "unit": "samples/s", "cores": cores, "kind": "port",
             "sample": f"{args.cpu_steps} guided step(s) at batch 1 after 1 warm-up, {S}x{S}, fp32, {cores} threads; "
                       f"extrapolated x{STEPS_PER_SAMPLE} steps ({s:.2f} s/step)"}
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL writes "NCCL version ..." to stdout
+    when the box sets NCCL_DEBUG=VERSION): send file descriptor 1 to stderr for the whole run and keep a private
+    duplicate of the real stdout for the result line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
