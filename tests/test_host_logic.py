@@ -280,3 +280,23 @@ def test_fused_statistics_geometry_excludes_interleaved_images(lib):
     for hw in (12, 10, 6):
         assert lib.gd_conv_stats_rows(4, hw, hw, ctypes.byref(rpi)) == 0 and rpi.value == 0
     assert lib.gd_conv_stats_rows(4, 24, 24, ctypes.byref(rpi)) == 24 and rpi.value == 6
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """The driver parses bench.py's stdout: ONE JSON line, whatever libraries print (they are sent to stderr).  The
+    reference arm runs on the host cores, so this is testable without a GPU (64x64 keeps it to seconds)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0", "--image-size", "64", "--gpus", "1"], capture_output=True, text=True,
+                       timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "samples/s" and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["value"] > 0 and d["n_gpus"] == 1 and d["steps"] == 1
