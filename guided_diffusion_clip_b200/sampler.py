@@ -68,6 +68,10 @@ class GraphedStepper:
         key = (sig, tuple(shape), str(device), bool(clip_denoised), bool(ddim), float(eta))
         cache = diffusion.__dict__.setdefault("_steppers", {})
         if key not in cache:
+            # steppers captured for an older parameter version of the same model object can never be hit again: drop
+            # them (each one owns a CUDA graph and its static buffers)
+            for stale in [k for k in cache if k[0][0] == sig[0] and k[0][1] != sig[1]]:
+                del cache[stale]
             st = GraphedStepper.maybe_create(diffusion, model, cond_fn, shape, device, model_kwargs, clip_denoised,
                                              ddim, eta)
             if st is None:
