@@ -79,3 +79,22 @@ def test_iteration_count_and_slices():
     assert dist_util.num_iterations(65, 8, 8) == 2
     assert dist_util.shard_slice(64, 8, 3) == (24, 32)
     assert [dist_util.rank_seed(7, r) for r in range(3)] == [7, 8, 9]
+
+
+def test_reference_arm_under_torchrun_prints_one_line_from_rank0():
+    """The driver launches `bench.py --impl reference --gpus N` through torchrun like the GPU arm: rank 0 alone measures
+    and prints the one JSON line, the other ranks exit 0 without work (CPU only, world size 2)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29547", os.path.join(root, "bench.py"),
+                        "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--image-size", "64"],
+                       capture_output=True, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
