@@ -300,3 +300,28 @@ def test_bench_reference_arm_prints_exactly_one_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["value"] > 0 and d["n_gpus"] == 1 and d["steps"] == 1
+
+
+def test_strided_conv_packing_algebra_on_cpu():
+    """The host-side algebra behind Downsample.op on the CUDA path, restated on CPU: (a) the stride-2 gather layout
+    [.., tap*C + ci] times pack_conv3x3's rows equals F.conv2d(stride=2, padding=1); (b) the data-gradient is the GEMM
+    with the transposed pack followed by the transpose of the gather (F.fold), as engine.ClassifierPlan emits it."""
+    import torch.nn.functional as F
+    from guided_diffusion_clip_b200.engine import pack_conv3x3
+    g = th.Generator().manual_seed(3)
+    n, c, co, h, w = 2, 16, 32, 9, 12
+    x = th.randn(n, c, h, w, generator=g)
+    wt = th.randn(co, c, 3, 3, generator=g) / 12
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    cols = F.unfold(x, 3, padding=1, stride=2).reshape(n, c, 9, ho * wo).permute(0, 3, 2, 1).reshape(n, ho * wo, 9 * c)
+    wp = pack_conv3x3(wt)[:co].float()                      # [co][tap*c + ci]
+    y = (cols @ wp.t()).permute(0, 2, 1).reshape(n, co, ho, wo)
+    ref = F.conv2d(x, wt.half().float(), stride=2, padding=1)
+    assert float((y - ref).abs().max()) < 1e-4
+    dy = th.randn(n, co, ho, wo, generator=g)
+    dcols = dy.reshape(n, co, ho * wo).permute(0, 2, 1) @ wp  # GEMM with the transposed pack: [n, L, 9c]
+    dx = F.fold(dcols.reshape(n, ho * wo, 9, c).permute(0, 3, 2, 1).reshape(n, c * 9, ho * wo), (h, w), 3, padding=1,
+                stride=2)
+    xr = x.clone().requires_grad_(True)
+    F.conv2d(xr, wt.half().float(), stride=2, padding=1).backward(dy)
+    assert float((dx - xr.grad).abs().max()) < 1e-4
