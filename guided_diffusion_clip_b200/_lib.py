@@ -52,6 +52,7 @@ class PosteriorDesc(C.Structure):
         ("coef", vp), ("t", vp),
         ("n", i32), ("c", i32), ("hw", i32),
         ("var_type", i32), ("mean_type", i32), ("clip_denoised", i32), ("ddim", i32), ("eta", f32),
+        ("num_timesteps", i32),
     ]
 
 

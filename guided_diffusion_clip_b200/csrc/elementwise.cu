@@ -27,6 +27,7 @@ struct PostArgs {
   int n, c, hw;
   int var_type, mean_type, clip, ddim;
   float eta;
+  int num_timesteps;
 };
 
 __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
@@ -109,7 +110,11 @@ __global__ void posterior_kernel(const PostArgs p) {
     const size_t i = iv * kVec;
     const size_t b = i / chw, r = i - b * chw;
     // per-sample timestep index into the coefficient table (_extract_into_tensor, gaussian_diffusion.py:904-917)
-    const float* co = p.coef + static_cast<size_t>(p.t[b]) * GD_COEF_STRIDE;
+    // An index outside [0, num_timesteps) raises IndexError in the reference; a kernel cannot raise, so it poisons
+    // this sample's outputs with NaN instead of reading past the table (the host checks user-supplied t eagerly).
+    const long long tb = p.t[b];
+    const bool t_ok = tb >= 0 && tb < p.num_timesteps;
+    const float* co = p.coef + static_cast<size_t>(t_ok ? tb : 0) * GD_COEF_STRIDE;
     const size_t mo = b * static_cast<size_t>(out_c) * p.hw + r;
     float x[kVec], m[kVec], v[kVec], g[kVec], z[kVec];
     if (kVec == 4) {
@@ -136,6 +141,7 @@ __global__ void posterior_kernel(const PostArgs p) {
       o_logvar[j] = e.logvar;
       o_x0[j] = e.x0;
       o_out[j] = e.out;
+      if (!t_ok) o_mean[j] = o_var[j] = o_logvar[j] = o_x0[j] = o_out[j] = __int_as_float(0x7fc00000);
     }
     if (kVec == 4) {
       if (p.mean_out != nullptr) *reinterpret_cast<float4*>(p.mean_out + i) = *reinterpret_cast<const float4*>(o_mean);
@@ -276,10 +282,10 @@ __global__ void embedding_gather_kernel(const float* __restrict__ table, const i
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * dim) return;
   const int b = i / dim, j = i - b * dim;
-  long long r = idx[b];
-  if (r < 0) r = 0;
-  if (r >= num_rows) r = num_rows - 1;
-  out[i] = table[static_cast<size_t>(r) * dim + j];
+  // nn.Embedding raises IndexError for a label outside [0, num_rows); here the row becomes NaN (never a clamped,
+  // plausible-looking embedding) and the host validates labels eagerly (unet.UNetModel.forward)
+  const long long r = idx[b];
+  out[i] = (r >= 0 && r < num_rows) ? table[static_cast<size_t>(r) * dim + j] : __int_as_float(0x7fc00000);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -438,6 +444,7 @@ extern "C" int gd_posterior_step(const gd_posterior_desc* d, void* stream) {
   GD_REQUIRE(d->ddim != GD_DDIM_REVERSE || (d->sample != nullptr && d->eta == 0.0f && d->grad == nullptr),
              "gd_posterior_step: the reverse ODE step needs a sample output, eta == 0 and takes no guidance gradient");
   GD_REQUIRE(d->n > 0 && d->c > 0 && d->hw > 0, "gd_posterior_step: bad shape");
+  GD_REQUIRE(d->num_timesteps > 0, "gd_posterior_step: num_timesteps (rows of the coefficient table) must be > 0");
   GD_REQUIRE(d->var_type >= GD_VAR_LEARNED_RANGE && d->var_type <= GD_VAR_LEARNED, "gd_posterior_step: bad var_type");
   GD_REQUIRE(d->mean_type == GD_MEAN_EPSILON || d->mean_type == GD_MEAN_START_X,
              "gd_posterior_step: model_mean_type PREVIOUS_X is not on the sampling path built here");
@@ -447,6 +454,7 @@ extern "C" int gd_posterior_step(const gd_posterior_desc* d, void* stream) {
   p.mean_out = d->mean_out; p.var_out = d->var_out; p.logvar_out = d->logvar_out;
   p.n = d->n; p.c = d->c; p.hw = d->hw;
   p.var_type = d->var_type; p.mean_type = d->mean_type; p.clip = d->clip_denoised; p.ddim = d->ddim; p.eta = d->eta;
+  p.num_timesteps = d->num_timesteps;
   const size_t total = static_cast<size_t>(d->n) * d->c * d->hw;
   uintptr_t align = 0;
   for (const void* q : {static_cast<const void*>(d->x), static_cast<const void*>(d->model_out),

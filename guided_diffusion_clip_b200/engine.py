@@ -73,17 +73,23 @@ def new_act(n, h, w, c, device) -> View:
 
 
 class Program:
-    """A recorded list of (C function, args) — replayed on whatever stream is current."""
+    """A recorded list of (C function, args) — replayed on the current stream of the plan's device."""
 
-    def __init__(self):
+    def __init__(self, device=None):
         self.calls: List[Tuple[object, tuple, str]] = []
         self.keep: List[object] = []
+        self.device = device
 
     def add(self, name: str, *args) -> None:
         fn = getattr(L.load(), name)
         self.calls.append((fn, args, name))
 
     def run(self) -> None:
+        # the recorded launches embed raw pointers of the plan's device: always launch there, whatever device is
+        # current in the caller (a launch on another GPU's stream would fault and poison the context)
+        if self.device is not None and th.cuda.current_device() != self.device.index:
+            with th.cuda.device(self.device):
+                return self.run()
         stream = C.c_void_p(th.cuda.current_stream().cuda_stream)
         if os.environ.get("GD_B200_DEBUG_SYNC", "0") == "1":  # locate a faulting launch: sync after every call
             for i, (fn, args, name) in enumerate(self.calls):
@@ -173,9 +179,15 @@ class Emitter:
         L.load()
         self.model = model
         self.n = n
-        self.device = device
+        self.device = device = norm_device(device)
         self.P: Dict[str, th.Tensor] = {k: v.detach() for k, v in model.named_parameters()}
-        self.prog = Program()
+        for k, v in self.P.items():
+            if norm_device(v.device) != device:
+                # same situations in which the reference raises a device-mismatch RuntimeError; here the kernels would
+                # otherwise receive a host / foreign-GPU pointer
+                raise L.GdError(f"parameter {k} lives on {v.device} but the input is on {device}: move the model with "
+                                ".to(device) before calling it")
+        self.prog = Program(device)
         self._scratch: Dict[str, th.Tensor] = {}
         self._f32: Dict[str, th.Tensor] = {}
         self.keep: List[th.Tensor] = []
@@ -252,6 +264,7 @@ class Emitter:
         d.stats_out = None
         self.keep += [wpack, bias, d]
         self.prog.add("gd_conv_igemm", C.byref(d))
+        self.last_scale_slot = ("desc", d, None)
         if out_mode == L.OUT_NHWC_F16 and cout == out.c and cout % 64 == 0 and wpack.shape[0] == cout:
             # latest writer of this channel view: a later GroupNorm over it can ask this conv for fused statistics
             self._producers[(out.buf.data_ptr(), out.off, out.c)] = (d, n, h, w)
@@ -268,6 +281,7 @@ class Emitter:
         self.keep.append(bias)
         self.prog.add("gd_tap_gather3x3", C.c_void_p(ytap.ptr), ytap.ld, _p(bias), _p(out), n, cout, h, w,
                       C.c_float(float(out_scale)))
+        self.last_scale_slot = ("arg", len(self.prog.calls) - 1, 8)
 
     def _producers_of(self, x: View):
         """The conv launch(es) that wrote view x: one conv, or two convs writing adjacent channel slices (skip concat)."""
@@ -612,14 +626,18 @@ class UNetPlan:
 def bilinear_concat(x: th.Tensor, low_res: th.Tensor) -> th.Tensor:
     """cat([x, F.interpolate(low_res, (H,W), mode='bilinear')], 1) (unet.py:677-680) via the CUDA kernel."""
     _require_cuda(x.device)
+    if low_res.device != x.device:
+        raise L.GdError(f"low_res lives on {low_res.device} but x on {x.device} (load_data_for_worker yields CPU tensors: "
+                        "move them with .to(device) like scripts/super_res_sample.py:46)")
     n, c, h, w = x.shape
     cl = low_res.shape[1]
     out = th.empty((n, c + cl, h, w), dtype=th.float32, device=x.device)
     out[:, :c].copy_(x)
     lr = low_res.float().contiguous()
-    stream = C.c_void_p(th.cuda.current_stream().cuda_stream)
-    L.check(L.load().gd_bilinear_upsample_nchw(_p(lr), _p(out), n, cl, lr.shape[2], lr.shape[3], h, w, c + cl, c, stream),
-            "gd_bilinear_upsample_nchw")
+    with th.cuda.device(x.device):
+        stream = C.c_void_p(th.cuda.current_stream().cuda_stream)
+        L.check(L.load().gd_bilinear_upsample_nchw(_p(lr), _p(out), n, cl, lr.shape[2], lr.shape[3], h, w, c + cl, c,
+                                                   stream), "gd_bilinear_upsample_nchw")
     return out
 
 
@@ -690,7 +708,7 @@ class ClassifierPlan:
         self.fwd = em.prog
 
         # ------------------------------------------------------------------ backward program
-        em.prog = Program()
+        em.prog = Program(em.device)
         bw = em
         wqkv_t = wqkv.t().contiguous()
         wc_t = wc.t().contiguous()
@@ -756,7 +774,7 @@ class ClassifierPlan:
                 bw.prog.add("gd_col2im3x3_s2_nhwc", C.c_void_p(dcols.ptr), dcols.ld, C.c_void_p(g_in.ptr), g_in.ld, n, x.h,
                             x.w, l.ch)
                 g = g_in
-            else:  # conv_in: dX in fp32 NCHW, loss scale undone, user scale applied at run time by self.scale
+            else:  # conv_in: dX in fp32 NCHW; its fp32 epilogue undoes the loss scale and applies the user's scale
                 _, l, o = entry
                 wk = em.P[f"{l.key}.weight"]
                 if l.cin <= NARROW_COUT:  # dX = conv3x3 of dY with the flipped, transposed weights
@@ -766,17 +784,38 @@ class ClassifierPlan:
                     bw.conv(g, pack_conv3x3_bwd(wk), None, l.cin, self.dx, out_mode=L.OUT_NCHW_F32,
                             out_scale=1.0 / self.LOSS_SCALE, geom=(n, o.h, o.w))
         self.bwd = em.prog
+        self._scale_slot = em.last_scale_slot  # the launch whose fp32 epilogue carries out_scale
+        self._scale = 1.0
+        self.fwd_version = 0
+
+    def set_scale(self, scale: float) -> None:
+        """The user's classifier_scale is folded into the LAST launch's fp32 epilogue (out_scale = scale / LOSS_SCALE):
+        the fp16 gradient chain always carries exactly LOSS_SCALE x the true gradient, whatever the guidance scale, so a
+        large scale (ADM configs use up to 10) cannot overflow fp16 on the way."""
+        scale = float(scale)
+        if scale == self._scale:
+            return
+        kind, a, pos = self._scale_slot
+        val = scale / self.LOSS_SCALE
+        if kind == "desc":
+            a.out_scale = val
+        else:
+            fn, args, name = self.bwd.calls[a]
+            self.bwd.calls[a] = (fn, args[:pos] + (C.c_float(val),) + args[pos + 1:], name)
+        self._scale = scale
 
     # -- execution --------------------------------------------------------------------------------
     def forward(self, x, timesteps) -> th.Tensor:
         self.x_in.copy_(x)
         self.t_in.copy_(timesteps)
+        self.fwd_version += 1
         self.fwd.run()
         return self.logits
 
     def backward(self, dlogits: th.Tensor) -> th.Tensor:
         """dlogits: fp32 [n, classes] gradient w.r.t. the logits. Returns d/dx in fp32 NCHW (static buffer)."""
         self.dlogits.copy_(dlogits)
+        self.set_scale(1.0)
         self.bwd.run()
         return self.dx
 
@@ -785,9 +824,12 @@ class ClassifierPlan:
         self.forward(x, timesteps)
         stream = C.c_void_p(th.cuda.current_stream().cuda_stream)
         yy = y.to(th.int64).contiguous()
+        if yy.device != self.logits.device:
+            raise L.GdError(f"labels live on {yy.device} but the classifier runs on {self.logits.device}")
         L.check(L.load().gd_logsoftmax_select_bwd(_p(self.logits), _p(yy), _p(self.dlogits), self.n,
-                                                   self.logits.shape[1], C.c_float(float(scale)), stream),
+                                                   self.logits.shape[1], C.c_float(1.0), stream),
                 "gd_logsoftmax_select_bwd")
+        self.set_scale(scale)
         self.bwd.run()
         return self.dx
 
@@ -798,10 +840,17 @@ class _ClassifierFn(th.autograd.Function):
         n, c, h, w = x.shape
         plan = model.plan(n, h, w, x.device)
         ctx.plan = plan
-        return plan.forward(x.detach(), timesteps).clone()
+        out = plan.forward(x.detach(), timesteps).clone()
+        ctx.version = plan.fwd_version
+        return out
 
     @staticmethod
     def backward(ctx, dlogits):
+        if ctx.version != ctx.plan.fwd_version:
+            # the plan keeps ONE set of saved activations: a second forward on the same (batch, resolution) plan has
+            # overwritten what this backward needs
+            raise L.GdError("classifier backward after another forward of the same shape: the saved activations were "
+                            "overwritten; call backward (autograd.grad) before the next forward")
         return ctx.plan.backward(dlogits.float().contiguous()).clone(), None, None
 
 

@@ -5,8 +5,9 @@ condition_mean / condition_score, p_sample, ddim_sample and the two sampling loo
 What is different underneath: the ~25 pointwise ATen kernels and >=6 tiny H2D copies per step of the
 reference collapse into ONE fused kernel (csrc/elementwise.cu: posterior_kernel) that indexes a device
 table of per-step coefficients, uploaded once per device.  Training / likelihood methods
-(q_mean_variance, training_losses, _vb_terms_bpd, calc_bpd_loop, ddim_reverse_sample) are out of scope
- and are not provided.
+(training_losses, _vb_terms_bpd, calc_bpd_loop) are out of scope
+ and are not provided; q_sample (needed by the fork's denoise_start_point start), q_mean_variance
+and ddim_reverse_sample exist as thin helpers over the same fused kernel.
 """
 from __future__ import annotations
 
@@ -157,6 +158,11 @@ class GaussianDiffusion:
         hw = int(np.prod(x.shape[2:]))
         learned = self.model_var_type in (ModelVarType.LEARNED, ModelVarType.LEARNED_RANGE)
         assert model_out.shape == (B, Cc * 2 if learned else Cc, *x.shape[2:]), model_out.shape
+        for nm, tt in (("x", x), ("model_out", model_out), ("grad", grad), ("noise", noise), ("t", t), ("sample", sample),
+                       ("pred_xstart", pred_xstart), ("mean", mean), ("var", var), ("logvar", logvar)):
+            if tt is not None and tt.device != x.device:
+                # the kernels only see raw pointers: a host or foreign-GPU pointer would fault and poison the context
+                raise L.GdError(f"posterior update: `{nm}` lives on {tt.device} but x lives on {x.device}")
         for tt in (x, model_out, grad, noise):
             assert tt is None or (tt.dtype == th.float32 and tt.is_contiguous())
         assert t.dtype == th.int64 and t.shape == (B,) and t.is_contiguous()
@@ -169,8 +175,21 @@ class GaussianDiffusion:
         d.n, d.c, d.hw = B, Cc, hw
         d.var_type, d.mean_type = self._var_code(), (self._mean_code() if mean_type is None else mean_type)
         d.clip_denoised, d.ddim, d.eta = int(bool(clip_denoised)), int(ddim), float(eta)
-        stream = C.c_void_p(th.cuda.current_stream().cuda_stream)
-        L.check(L.load().gd_posterior_step(C.byref(d), stream), "gd_posterior_step")
+        d.num_timesteps = int(self.num_timesteps)
+        with th.cuda.device(x.device):
+            stream = C.c_void_p(th.cuda.current_stream().cuda_stream)
+            L.check(L.load().gd_posterior_step(C.byref(d), stream), "gd_posterior_step")
+
+    def _check_t(self, t) -> None:
+        """User-supplied step indices must lie in [0, num_timesteps) — the reference raises IndexError in
+        _extract_into_tensor (gaussian_diffusion.py:904-917), e.g. for an un-respaced t = 999 on a 250-step
+        SpacedDiffusion.  One host read; skipped during graph capture and by the loops (which generate t themselves)."""
+        if t.is_cuda and th.cuda.is_current_stream_capturing():
+            return
+        lo, hi = int(t.min()), int(t.max())
+        if lo < 0 or hi >= self.num_timesteps:
+            raise IndexError(f"timestep index out of range: t in [{lo}, {hi}] but this diffusion has "
+                             f"{self.num_timesteps} steps (pass respaced indices 0..{self.num_timesteps - 1})")
 
     # ------------------------------------------------------------------------------------------
     # q(x_t | x_0): needed by the fork's `denoise_start_point` start (gaussian_diffusion.py:188-206, 517-521)
@@ -225,6 +244,7 @@ class GaussianDiffusion:
         x = x.float().contiguous()
         t = t.to(th.int64).contiguous()
         assert t.shape == (x.shape[0],)
+        self._check_t(t)
         model_out = self._call_model(model, x, t, model_kwargs)
         mean_type = None
         if denoised_fn is not None:
@@ -261,12 +281,16 @@ class GaussianDiffusion:
         out["mean"], _, _ = self.q_posterior_mean_variance(x_start=out["pred_xstart"], x_t=x, t=t)
         return out
 
-    def _sample_step(self, model, x, t, clip_denoised, denoised_fn, cond_fn, model_kwargs, ddim, eta, noise=None):
-        """One reverse step = model call, optional cond_fn call, one fused kernel.  The noise is drawn by
-        torch AFTER the model call and before cond_fn, in the reference's order (:430 / :585), so the RNG
-        stream position per step is identical."""
+    def _sample_step(self, model, x, t, clip_denoised, denoised_fn, cond_fn, model_kwargs, ddim, eta, noise=None,
+                     check_t=True):
+        """One reverse step = model call, optional cond_fn call, one fused kernel.  The noise is drawn by torch in
+        the reference's order, so the RNG stream position per step is identical even for a cond_fn that consumes
+        random numbers: p_sample draws after the model call and BEFORE cond_fn (:430, :434-437); ddim_sample runs
+        condition_score (cond_fn) first and draws afterwards (:571-585)."""
         x = x.float().contiguous()
         t = t.to(th.int64).contiguous()
+        if check_t:
+            self._check_t(t)
         # fast path: our own UNet (+ our own guidance object) -> the whole step is one CUDA-graph replay
         from .sampler import GraphedStepper
         stepper = None if denoised_fn is not None else GraphedStepper.cached(
@@ -277,11 +301,13 @@ class GaussianDiffusion:
         mean_type = None
         if denoised_fn is not None:
             model_out, mean_type = self._apply_denoised_fn(denoised_fn, x, t, model_out), L.MEAN_START_X
-        if noise is None:
+        if noise is None and not ddim:
             noise = th.randn_like(x)
         grad = None
         if cond_fn is not None:
             grad = self._wrap(cond_fn)(x, self._scale_timesteps(t), **model_kwargs).float().contiguous()
+        if noise is None:
+            noise = th.randn_like(x)
         sample, x0 = th.empty_like(x), th.empty_like(x)
         self._launch_posterior(x=x, t=t, model_out=model_out, grad=grad, noise=noise, sample=sample, pred_xstart=x0,
                                clip_denoised=clip_denoised, ddim=ddim, eta=eta, mean_type=mean_type)
@@ -332,7 +358,8 @@ class GaussianDiffusion:
         for i in indices:
             t.fill_(i)
             with th.no_grad():
-                out = self._sample_step(model, img, t, clip_denoised, denoised_fn, cond_fn, model_kwargs, ddim, eta)
+                out = self._sample_step(model, img, t, clip_denoised, denoised_fn, cond_fn, model_kwargs, ddim, eta,
+                                        check_t=False)
                 yield out
                 img = out["sample"]
 

@@ -354,18 +354,72 @@ class UNetModel(_GdModule):
     def _extra_params(self, ps: _ParamSpec) -> None:
         pass
 
+    # -- checkpoints of the other label variant ---------------------------------------------------
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        """The reference fork's factory always builds the CLIP-feature variant (label_emb = Linear-SiLU-Linear over a
+        512-d feature, script_util.py:168, unet_other.py:25-41) while upstream checkpoints carry an nn.Embedding table.
+        A checkpoint of the OTHER variant than the one this model was built with is adopted: the label parameters are
+        re-created in the checkpoint's layout (and the model then expects `clip_feat` resp. integer `y`), so
+        reference-trained weights load with strict=True whichever `conditioning` the factory was called with."""
+        if self.num_classes is not None:
+            ck_mlp, ck_emb = "label_emb.0.weight" in state_dict, "label_emb.weight" in state_dict
+            if (ck_mlp and not self.label_mlp) or (ck_emb and self.label_mlp):
+                if ("bias_feat" in state_dict) != hasattr(self, "bias_feat"):
+                    raise RuntimeError(
+                        "checkpoint and model are different super-resolution variants (SRImageModel_Feat carries "
+                        "`bias_feat` and takes clip_feat / clip_feat2 / img2; SuperResModel takes low_res): build the "
+                        "model with sr_create_model(..., conditioning='clip_feat' | 'low_res') to match the checkpoint")
+                self._adopt_label_variant(state_dict, ck_mlp)
+        return super().load_state_dict(state_dict, strict=strict, **kw)
+
+    def _adopt_label_variant(self, state_dict, to_mlp: bool) -> None:
+        ref = next(self.parameters())
+        self._modules.pop("label_emb", None)
+        names = (["label_emb.0.weight", "label_emb.0.bias", "label_emb.2.weight", "label_emb.2.bias"] if to_mlp
+                 else ["label_emb.weight"])
+        for nm in names:
+            _register(self, nm, nn.Parameter(th.zeros(tuple(state_dict[nm].shape), dtype=th.float32, device=ref.device)))
+        self.label_mlp = to_mlp
+        self.num_classes = int(state_dict[names[0]].shape[1 if to_mlp else 0])
+        self._invalidate()
+
     # -- conditioning vector -------------------------------------------------------------------
     def _cond(self, y, kwargs):
+        feat = kwargs.get("clip_feat")
+        if self.label_mlp and feat is not None:  # UNetModel_clip_feat.forward (unet_other.py:36-41)
+            return feat.squeeze().float().reshape(-1, self.num_classes)
         return y
+
+    def _check_labels(self, y) -> None:
+        """nn.Embedding raises IndexError for labels outside [0, num_classes); the gather kernel cannot, so labels are
+        validated on the host once per distinct tensor (not while a CUDA graph is being captured)."""
+        key = (y.data_ptr(), y._version, tuple(y.shape))
+        if getattr(self, "_labels_ok", None) == key or (y.is_cuda and th.cuda.is_current_stream_capturing()):
+            return
+        if y.dtype not in (th.int64, th.int32, th.int16, th.uint8, th.int8):
+            raise TypeError(
+                f"this model embeds integer class labels (nn.Embedding, unet.py:478-479) but got y of dtype {y.dtype}; "
+                "for the fork's CLIP-feature conditioning build it with conditioning='clip_feat' or load a fork checkpoint")
+        lo, hi = int(y.min()), int(y.max())
+        if lo < 0 or hi >= self.num_classes:
+            raise IndexError(f"class label out of range: y in [{lo}, {hi}], num_classes = {self.num_classes}")
+        self._labels_ok = key
 
     def forward(self, x, timesteps, y=None, **kwargs):
         """x: [N, C, H, W] fp32; timesteps: [N]; y: [N] int64 labels (or [N,num_classes] features when
         label_mlp).  Returns [N, out_channels, H, W] fp32 (unet.py:635-664)."""
         y = self._cond(y, kwargs)
+        if y is None and self.num_classes is not None and not self.label_mlp and kwargs.get("clip_feat") is not None:
+            raise TypeError("clip_feat was passed to a model built for integer class labels (conditioning='labels'); "
+                            "build it with conditioning='clip_feat' or load a fork checkpoint (label_emb.0/2.*)")
         assert (y is not None) == (self.num_classes is not None), \
             "must specify y if and only if the model is class-conditional"
         if y is not None:
             assert y.shape[0] == x.shape[0], f"{y.shape} != {x.shape}"
+            if not self.label_mlp:
+                self._check_labels(y)
+            if y.device != x.device:
+                raise RuntimeError(f"y lives on {y.device} but x on {x.device}")
         from .engine import UNetPlan, norm_device
         n, c, h, w = x.shape
         assert c == self.in_channels, f"expected {self.in_channels} input channels, got {c}"
@@ -394,11 +448,6 @@ class UNetModel_clip_feat(UNetModel):
         kwargs["label_mlp"] = True
         super().__init__(image_size, in_channels, *args, **kwargs)
 
-    def _cond(self, y, kwargs):
-        feat = kwargs.get("clip_feat")
-        if feat is not None:
-            return feat.squeeze().float().reshape(-1, self.num_classes)
-        return y
 
 
 class SRImageModel_Feat(UNetModel):

@@ -280,6 +280,8 @@ typedef struct gd_posterior_desc {
   int32_t var_type, mean_type, clip_denoised;
   int32_t ddim;           /* 0 ancestral p_sample, 1 ddim_sample, GD_DDIM_REVERSE ddim_reverse_sample (no noise / grad) */
   float eta;
+  int32_t num_timesteps;  /* rows of `coef`; a t[b] outside [0, num_timesteps) yields NaN outputs for sample b
+                           * (the reference raises IndexError in _extract_into_tensor, gaussian_diffusion.py:904-917) */
 } gd_posterior_desc;
 enum { GD_DDIM_REVERSE = 2 };
 int gd_posterior_step(const gd_posterior_desc* desc, void* stream);

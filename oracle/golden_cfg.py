@@ -310,3 +310,88 @@ CLF_PLAIN_SEED = 45
 CLF_PLAIN_KW = dict(CLASSIFIER_KW, classifier_use_scale_shift_norm=False)
 CLF_CONVDOWN_SEED = 46
 CLF_CONVDOWN_KW = dict(CLASSIFIER_KW, classifier_resblock_updown=False)  # Downsample.op = 3x3 stride-2 conv
+
+
+# ---- FULL-SIZE one-step fixtures of BASELINE configs[1..4] (oracle/make_golden_fullsize.py -> tests/golden/fullsize_*.npz)
+# One guided step at batch 1 through the REAL reference in fp32, on make_state_dict weights; the GPU tests rebuild the
+# same weights from the seed and compare eps|v, the guidance gradient and x_{t-1} at the real widths.
+FS_SEED = 61  # weights: FS_SEED + k; inputs: FS_SEED + 10 + k; step noise: FS_SEED + 20 + k
+UNET256U_KW = dict(UNET256_KW, class_cond=False)
+UNET512_KW = dict(UNET256_KW, image_size=512, use_fp16=False)   # channel_mult (0.5,1,1,2,2,4,4), script_util.py:149-151
+CLF512_KW = dict(CLF256_KW, image_size=512)
+CLIP_B16 = dict(hidden_size=768, intermediate_size=3072, num_hidden_layers=12, num_attention_heads=12, image_size=224,
+                patch_size=16, projection_dim=512)
+FULLSIZE_CASES = {
+    # configs[1]: 256x256 class-cond ADM + classifier-256 guidance (scale 1.0), ancestral step 120 of 250
+    "cfg2": dict(image=256, k=0, diffusion=dict(_TR, timestep_respacing="250"), ddim=False, index=120, label=207,
+                 scale=1.0),
+    # configs[2]: 256x256 unconditional ADM + CLIP ViT-B/16 guidance, DDIM step 30 of 50
+    "cfg3": dict(image=256, k=1, diffusion=dict(_TR, timestep_respacing="ddim50"), ddim=True, index=30, label=None,
+                 scale=100.0),
+    # configs[3]: 128 -> 512 upsampler, ancestral step 100 of 250, unguided
+    "cfg4": dict(image=512, k=2, diffusion=dict(_TR, timestep_respacing="250"), ddim=False, index=100, label=77,
+                 scale=0.0),
+    # configs[4]: 512x512 class-cond ADM (use_fp16 False) + classifier-512 guidance (scale 4.0), DDIM step 12 of 25
+    "cfg5": dict(image=512, k=3, diffusion=dict(_TR, timestep_respacing="ddim25"), ddim=True, index=12, label=931,
+                 scale=4.0),
+}
+
+
+def ref_unet512_kwargs():
+    return dict(ref_unet256_kwargs(), image_size=512, attention_resolutions=(16, 32, 64),
+                channel_mult=(0.5, 1, 1, 2, 2, 4, 4), use_fp16=False)
+
+
+def fullsize_inputs(name: str):
+    """x_t (unit normal, as at a mid-chain step), the low-res conditioning of the upsampler and the CLIP text vector."""
+    c = FULLSIZE_CASES[name]
+    g = th.Generator().manual_seed(FS_SEED + 10 + c["k"])
+    x = th.randn(1, 3, c["image"], c["image"], generator=g)
+    low = th.rand(1, 3, 128, 128, generator=g) * 2 - 1
+    txt = th.randn(1, 512, generator=g)
+    return x, low, txt / txt.norm(dim=-1, keepdim=True)
+
+
+def fullsize_noise(name: str):
+    """The CPU-generator draw of the reference's p_sample / ddim_sample (th.randn_like, gaussian_diffusion.py:430,585)."""
+    c = FULLSIZE_CASES[name]
+    th.manual_seed(FS_SEED + 20 + c["k"])
+    return th.randn(1, 3, c["image"], c["image"])
+
+
+def fs_pack(a):
+    """fixture storage: fp16 mantissa at a per-array power-of-two scale (5e-4 relative, far inside the 2e-2 budget)."""
+    import numpy as np
+    a = np.asarray(a, dtype=np.float32)
+    m = float(np.abs(a).max())
+    e = 0 if m == 0 else int(np.ceil(np.log2(m / 32768.0)))
+    return (a / np.float32(2.0 ** e)).astype(np.float16), np.int32(e)
+
+
+def fs_unpack(h, e):
+    import numpy as np
+    return h.astype(np.float32) * np.float32(2.0 ** int(e))
+
+
+# ---- §8f row 3: the fork's SRImageModel_Feat (unet_other.py:43-77) and the denoise_start_point / q_sample(img2) start
+# of p_sample_loop (gaussian_diffusion.py:517-523); oracle/make_golden_fork.py -> tests/golden/fork_golden.npz ------
+SRFEAT_SEED, SRFEAT_LOOP_SEED = 71, 72
+SRFEAT_KW = dict(SR_KW)                       # sr_create_model(..., conditioning="clip_feat")
+SRFEAT_DIFFUSION = dict(_TR, timestep_respacing="250")
+SRFEAT_START = 40                             # denoise_start_point: q_sample(img2, t=40) (SDEdit-style partial noising,
+SRFEAT_RECORD = (1, 10, 40)                   # original t = 160), then steps 39 .. 0; samples recorded after these counts
+
+
+def ref_srfeat_kwargs():
+    kw = ref_sr_kwargs()
+    kw.update(num_classes=512)
+    return kw
+
+
+def srfeat_inputs():
+    g = th.Generator().manual_seed(INPUT_SEED + 4)
+    x = th.randn(2, 3, IMAGE, IMAGE, generator=g)
+    img2 = th.rand(2, 3, IMAGE, IMAGE, generator=g) * 2 - 1
+    f1 = th.randn(2, 1, 512, generator=g)
+    f2 = th.randn(2, 1, 512, generator=g)
+    return (x, th.tensor([640, 15]), f1 / f1.norm(dim=-1, keepdim=True), f2 / f2.norm(dim=-1, keepdim=True), img2)

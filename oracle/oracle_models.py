@@ -222,3 +222,11 @@ def make_state_dict(shapes: Dict[str, tuple], seed: int) -> Dict[str, th.Tensor]
             v = th.randn(shape, generator=g) / math.sqrt(fan_in)
         sd[name] = v
     return sd
+
+
+def srfeat_forward(sd, x, t, clip_feat, clip_feat2, img2, **kw) -> th.Tensor:
+    """SRImageModel_Feat.forward (unet_other.py:56-77): y = clip_feat - clip_feat2 + bias_feat feeds the label MLP,
+    the reference image img2 is concatenated to x_t."""
+    n = x.shape[0]
+    y = clip_feat.reshape(n, -1).float() - clip_feat2.reshape(n, -1).float() + sd["bias_feat"].float()
+    return unet_forward(sd, th.cat([x, img2], dim=1), t, y, **kw)

@@ -1,0 +1,135 @@
+"""FULL-SIZE parity of BASELINE configs[1..4] against the real reference (tests/golden/fullsize_*.npz, produced by
+oracle/make_golden_fullsize.py: the reference's own fp32 modules at batch 1 on seeded weights, one guided step).
+
+The CUDA path (fp16 storage, fp32 accumulate) is compared at the REAL widths — 1 024-channel blocks, the 2 048-channel
+concat GroupNorm, K = 18 432 convolutions, T = 1024 legacy-order attention inside the model, the 512x512 geometry, the
+full ViT-B/16 — for the model output eps|v, the guidance gradient and x_{t-1}.
+Tolerance (BASELINE.json north_star): max-abs error relative to the reference's max-abs <= 2e-2."""
+import os
+
+import numpy as np
+import pytest
+import torch as th
+
+from guided_diffusion_clip_b200 import script_util as su
+from guided_diffusion_clip_b200.sampler import ClassifierGuidance, ModelFn
+from oracle import golden_cfg as cfg
+from oracle import oracle_models as om
+from tests import gpu_helpers as H
+
+TOL = 2e-2
+
+
+def _fixture(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, f"fullsize_{name}.npz"))
+    out = {}
+    for k in z.files:
+        if k.endswith("_exp"):
+            continue
+        out[k] = th.from_numpy(cfg.fs_unpack(z[k], z[k + "_exp"])) if k + "_exp" in z.files else z[k]
+    return out
+
+
+def _load(model, seed):
+    sd = om.make_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed)
+    model.load_state_dict(sd, strict=True)
+    return sd
+
+
+def _build(name, dev):
+    """Our models for a full-size case, on the weights the reference ran with (same seeds, same generator)."""
+    c = cfg.FULLSIZE_CASES[name]
+    seed = cfg.FS_SEED + c["k"]
+    cond = None
+    if name == "cfg4":
+        kw = su.sr_model_and_diffusion_defaults()
+        kw.update({k: v for k, v in cfg.SR512_KW.items() if k in kw})
+        kw.update(c["diffusion"])
+        kw["diffusion_steps"] = kw.pop("steps")
+        model, d = su.sr_create_model_and_diffusion(**kw)
+    else:
+        mkw = {"cfg2": cfg.UNET256_KW, "cfg3": cfg.UNET256U_KW, "cfg5": cfg.UNET512_KW}[name]
+        model = su.create_model(**mkw)
+        d = su.create_gaussian_diffusion(**c["diffusion"])
+    _load(model, seed)
+    model.to(dev)
+    if model.dtype == th.float16:
+        model.convert_to_fp16()
+    model.eval()
+    if name in ("cfg2", "cfg5"):
+        clf = su.create_classifier(**(cfg.CLF256_KW if name == "cfg2" else cfg.CLF512_KW))
+        _load(clf, seed + 100)
+        clf.to(dev).eval()
+        cond = ClassifierGuidance(clf, c["scale"])
+    elif name == "cfg3":
+        from guided_diffusion_clip_b200 import clip as gclip
+        enc = gclip.CLIPVisionEncoder(**cfg.CLIP_B16)
+        enc.load_state_dict(cfg.clip_state_dict({k: tuple(v.shape) for k, v in enc.state_dict().items()}), strict=True)
+        enc.to(dev).eval()
+        cond = gclip.CLIPGuidance(enc, cfg.fullsize_inputs(name)[2].to(dev), c["scale"])
+    return model, d, cond
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cfg2", "cfg3", "cfg4", "cfg5"])
+def test_fullsize_guided_step_matches_reference(lib, golden_dir, name):
+    dev = th.device("cuda", 0)
+    c = cfg.FULLSIZE_CASES[name]
+    G = _fixture(golden_dir, name)
+    model, d, cond = _build(name, dev)
+    x, low, _ = cfg.fullsize_inputs(name)
+    x = x.to(dev)
+    t = th.tensor([c["index"]], device=dev)
+    mk = {}
+    if c["label"] is not None:
+        mk["y"] = th.tensor([c["label"]], device=dev)
+    if name == "cfg4":
+        mk["low_res"] = low.to(dev)
+    mf = ModelFn(model, c["label"] is not None) if name != "cfg4" else model
+    z = cfg.fullsize_noise(name).to(dev)
+    t_model = th.tensor([int(G["t_model"])], device=dev)
+    assert int(d.timestep_map[c["index"]]) == int(G["t_model"])  # the wrapped model saw the same original timestep
+    with th.no_grad():
+        eps = (model(x, t_model, low_res=mk["low_res"], y=mk["y"]) if name == "cfg4"
+               else model(x, t_model, mk.get("y")))
+        errs = {"eps": H.rel_err(eps, G["eps"].to(dev))}
+        if cond is not None:
+            grad = cond(x, t_model, **mk)
+            errs["grad"] = H.rel_err(grad, G["grad"].to(dev))
+        out = d._sample_step(mf, x, t, True, None, cond, mk, c["ddim"], 0.0, noise=z)
+    errs["sample"] = H.rel_err(out["sample"], G["sample"].to(dev))
+    th.cuda.synchronize()
+    print(f"FULLSIZE {name}: " + "  ".join(f"{k} {v:.3e}" for k, v in errs.items()))
+    gp = os.path.join(os.path.dirname(golden_dir), "..", "gpurun_out")
+    if os.path.isdir(gp):
+        with open(os.path.join(gp, "fullsize_parity.txt"), "a") as f:
+            f.write(f"{name} " + " ".join(f"{k}={v:.3e}" for k, v in errs.items()) + "\n")
+    for k, v in errs.items():
+        assert v < TOL, f"{name}: {k} rel err {v:.3e} exceeds {TOL}"
+    del model, cond
+    th.cuda.empty_cache()
+
+
+def test_oracle_matches_reference_at_full_size_cfg2(golden_dir):
+    """CPU: the oracle restatement against the reference's configs[1] fixture at the REAL widths (UNet-256 forward +
+    classifier-256 gradient, batch 1, ~20 s of host time) — pins oracle/oracle_models.py where the bench runs."""
+    name = "cfg2"
+    c = cfg.FULLSIZE_CASES[name]
+    G = _fixture(golden_dir, name)
+    with th.device("meta"):
+        shapes_u = {k: tuple(v.shape) for k, v in su.create_model(**cfg.UNET256_KW).state_dict().items()}
+        shapes_c = {k: tuple(v.shape) for k, v in su.create_classifier(**cfg.CLF256_KW).state_dict().items()}
+    seed = cfg.FS_SEED + c["k"]
+    x, _, _ = cfg.fullsize_inputs(name)
+    tt = th.tensor([int(G["t_model"])])
+    y = th.tensor([c["label"]])
+    struct = dict(num_res_blocks=2, channel_mult_len=6, head_dim=64)
+    usd = om.make_state_dict(shapes_u, seed)
+    with th.no_grad():
+        eps = om.unet_forward(usd, x, tt, y, new_order=False, **struct)
+    del usd
+    csd = om.make_state_dict(shapes_c, seed + 100)
+    grad = om.classifier_guidance(csd, x, tt, y, c["scale"], **struct)
+    e1, e2 = H.rel_err(eps, G["eps"]), H.rel_err(grad, G["grad"])
+    print(f"oracle vs reference at full size: eps {e1:.3e} grad {e2:.3e}")
+    assert e1 < 2e-3 and e2 < 2e-3  # fp32 vs fp32; the fixture is stored with an fp16 mantissa (5e-4)

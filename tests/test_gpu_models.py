@@ -365,3 +365,53 @@ def test_split_batch_step_graph_is_bit_identical(lib, unet, clf, monkeypatch):
                 img = out["sample"]
         outs.append((img.clone(), out["pred_xstart"].clone()))
     assert th.equal(outs[0][0], outs[1][0]) and th.equal(outs[0][1], outs[1][1])
+
+
+def test_out_of_range_timesteps_and_labels_fail_like_the_reference(lib, unet):
+    """an un-respaced t (999 on a 250-step SpacedDiffusion) raises IndexError in the reference's
+    _extract_into_tensor (gaussian_diffusion.py:904-917) and nn.Embedding raises for a label >= num_classes; here the
+    host validates user-supplied indices and the kernels poison (NaN) instead of reading out of bounds."""
+    model, _ = unet
+    d = su.create_gaussian_diffusion(steps=1000, learn_sigma=True, noise_schedule="linear", timestep_respacing="250")
+    x, _, y = (v.cuda() for v in cfg.model_inputs())
+    with pytest.raises(IndexError):
+        d.p_sample(ModelFn(model, True), x, th.tensor([999, 3], device="cuda"), model_kwargs={"y": y})
+    with pytest.raises(IndexError):
+        d.p_mean_variance(ModelFn(model, True), x, th.tensor([-1, 3], device="cuda"), model_kwargs={"y": y})
+    with pytest.raises(IndexError):
+        model(x, th.tensor([5, 5], device="cuda"), th.tensor([3, 1000], device="cuda"))
+    # kernel-level behaviour (what a captured graph would do): NaN for the offending sample only
+    mo = th.randn(2, 6, 64, 64, device="cuda")
+    s, x0 = th.empty_like(x), th.empty_like(x)
+    d._launch_posterior(x=x, t=th.tensor([250, 3], device="cuda"), model_out=mo, noise=th.randn_like(x), sample=s,
+                        pred_xstart=x0)
+    assert th.isnan(s[0]).all() and th.isfinite(s[1]).all()
+
+
+def test_device_mismatch_raises_instead_of_faulting(lib, unet):
+    """CPU parameters / CPU low_res / CPU labels must raise (the reference raises a device-mismatch error),
+    never hand a host pointer to a kernel."""
+    from guided_diffusion_clip_b200 import _lib as L
+    m = su.create_model(**cfg.UNET_KW)  # still on the CPU
+    x, t, y = (v.cuda() for v in cfg.model_inputs())
+    with pytest.raises(L.GdError, match="lives on"):
+        m(x, t, y)
+    model, _ = unet
+    with pytest.raises(RuntimeError):
+        model(x, t, y.cpu())
+    sr = su.sr_create_model(**cfg.SR_KW).cuda()
+    xs, ts, ys, low = cfg.sr_inputs()
+    with pytest.raises(L.GdError, match="low_res lives on"):
+        sr(xs.cuda(), ts.cuda(), low_res=low, y=ys.cuda())
+
+
+def test_large_guidance_scale_is_applied_in_the_fp32_epilogue(lib, clf):
+    """the user's classifier_scale multiplies the fp32 result of the last launch, not the fp16 gradient
+    chain: scale 1000 x gradient(scale 1) holds to fp32 rounding and nothing overflows."""
+    classifier, _ = clf
+    x, t, y = (v.cuda() for v in cfg.model_inputs())
+    g1 = ClassifierGuidance(classifier, 1.0)(x, t, y=y)
+    g1000 = ClassifierGuidance(classifier, 1000.0)(x, t, y=y)
+    assert th.isfinite(g1000).all()
+    assert H.rel_err(g1000, 1000.0 * g1) < 1e-6
+    assert th.equal(ClassifierGuidance(classifier, 1.0)(x, t, y=y), g1)  # the scale slot is restored per call

@@ -325,3 +325,27 @@ def test_strided_conv_packing_algebra_on_cpu():
     xr = x.clone().requires_grad_(True)
     F.conv2d(xr, wt.half().float(), stride=2, padding=1).backward(dy)
     assert float((dx - xr.grad).abs().max()) < 1e-4
+
+
+def test_checkpoint_of_the_other_label_variant_is_adopted():
+    """the reference factory always builds the fork's CLIP-feature variant (script_util.py:168); a model
+    built here with the default conditioning='labels' must still load such a checkpoint with strict=True (and vice
+    versa), switching its label path to the checkpoint's layout."""
+    from guided_diffusion_clip_b200 import script_util as su
+    from oracle import golden_cfg as cfg
+    fork = su.create_model(**cfg.FEAT_KW, conditioning="clip_feat")
+    sd_fork = {k: v.clone() for k, v in fork.state_dict().items()}
+    m = su.create_model(**cfg.FEAT_KW)  # nn.Embedding variant, 1000 classes
+    assert "label_emb.weight" in m.state_dict() and not m.label_mlp
+    m.load_state_dict(sd_fork, strict=True)
+    assert m.label_mlp and m.num_classes == 512 and "label_emb.weight" not in m.state_dict()
+    assert all(th.equal(v, sd_fork[k]) for k, v in m.state_dict().items())
+    # ... and back: an upstream (Embedding) checkpoint into a fork-built model
+    up = su.create_model(**cfg.FEAT_KW)
+    fork.load_state_dict(up.state_dict(), strict=True)
+    assert not fork.label_mlp and fork.num_classes == 1000
+    # super-resolution variants differ in their forward signature: a clear error instead of a silent mismatch
+    sr = su.sr_create_model(**cfg.SR_KW)
+    srf = su.sr_create_model(**cfg.SR_KW, conditioning="clip_feat")
+    with pytest.raises(RuntimeError, match="super-resolution variants"):
+        sr.load_state_dict(srf.state_dict(), strict=True)
