@@ -13,6 +13,7 @@ LIB_PATH = os.environ.get("GD_B200_LIB") or os.path.join(_HERE, "libgd_b200.so")
 RES_NONE, RES_SAME, RES_UPSAMPLE2, RES_AVGPOOL2 = 0, 1, 2, 3
 OUT_NHWC_F16, OUT_NCHW_F32 = 0, 1
 GN_SAME, GN_AVGPOOL2, GN_UPSAMPLE2 = 0, 1, 2
+CONV_GN_OFF, CONV_GN_SAME, CONV_GN_UPSAMPLE2 = 0, 1, 2
 QKV_LEGACY, QKV_NEW = 0, 1
 VAR_LEARNED_RANGE, VAR_FIXED, VAR_LEARNED = 0, 1, 2
 MEAN_EPSILON, MEAN_START_X = 0, 1
@@ -35,6 +36,7 @@ class ConvDesc(C.Structure):
         ("out", vp), ("ld_out", i32), ("out_mode", i32),
         ("bn", i32), ("out_scale", f32),
         ("stats_out", vp),
+        ("gn_mode", i32), ("gn_silu", i32), ("gn_coef", vp),
     ]
 
 
@@ -66,7 +68,10 @@ SIGNATURES = {
     "gd_bw_probe": (C.c_int, [i32, i32, vp, vp, i64, vp]),
     "gd_conv_igemm": (C.c_int, [C.POINTER(ConvDesc), vp]),
     "gd_conv_stats_rows": (i64, [i32, i32, i32, C.POINTER(i32)]),
-    "gd_groupnorm_finalize_partials": (C.c_int, [vp, i32, i32, vp, i32, i32, i32, i32, i32, f32, vp, vp]),
+    "gd_conv_gn_fusable": (C.c_int, [i32, i32]),
+    "gd_groupnorm_finalize_partials": (C.c_int, [vp, i32, i32, vp, i32, i32, i32, i32, i32, f32, vp, vp, vp, vp, i32, vp,
+                                                 vp]),
+    "gd_groupnorm_coef": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, vp, vp]),
     "gd_im2col3x3_small_cin": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, vp]),
     "gd_groupnorm_stats": (C.c_int, [vp, i32, i32, i32, i32, f32, vp, vp, vp]),
     "gd_groupnorm_ws_floats": (i64, [i32, i32, i32]),

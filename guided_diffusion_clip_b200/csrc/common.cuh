@@ -89,6 +89,39 @@ __device__ __forceinline__ float silu_f(float v) {
   return fmaf(h, tanh_approx(h), h);
 }
 
+// GroupNorm32 (+FiLM) folded into one per-channel affine y = x * a + b:
+//   a = rstd * gamma [* (1 + scale)],  b = (beta - mean * rstd * gamma) [* (1 + scale) + shift]
+// (nn.py:17-19 + unet.py:248-252; scale = first half of the FiLM row).  ONE definition with pinned roundings, shared by
+// gd_groupnorm_apply, by the coefficient table of gd_groupnorm_coef / gd_groupnorm_finalize_partials and through it by
+// the convolution that normalises its operand on the fly, so all paths produce the same bits.
+__device__ __forceinline__ void gn_affine(float mean, float rstd, float ga, float be, bool film, float scale, float shift,
+                                          float& a, float& b) {
+  float aa = __fmul_rn(rstd, ga);
+  float bb = __fmaf_rn(-mean, aa, be);
+  if (film) {
+    const float sc = __fadd_rn(1.0f, scale);
+    aa = __fmul_rn(aa, sc);
+    bb = __fmaf_rn(bb, sc, shift);
+  }
+  a = aa;
+  b = bb;
+}
+__device__ __forceinline__ void gn_load_affine(const float* mean_rstd, const float* gamma, const float* beta,
+                                               const float* film, int film_ld, int n, int c, int ch0, float (&a)[8],
+                                               float (&b)[8]) {
+  const int cpg = c / 32;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = ch0 + j;
+    const int g = ch / cpg;
+    const float mean = mean_rstd[(static_cast<size_t>(n) * 32 + g) * 2];
+    const float rstd = mean_rstd[(static_cast<size_t>(n) * 32 + g) * 2 + 1];
+    const bool has_film = film != nullptr;
+    gn_affine(mean, rstd, gamma[ch], beta[ch], has_film, has_film ? film[static_cast<size_t>(n) * film_ld + ch] : 0.f,
+              has_film ? film[static_cast<size_t>(n) * film_ld + c + ch] : 0.f, a[j], b[j]);
+  }
+}
+
 // ---- mbarrier --------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -114,6 +147,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// acquire at cluster scope: the data the barrier guards was written by the OTHER CTA of a pair (generic-proxy stores
+// followed by a release.cluster arrive)
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug must surface as a trap (launch failure), never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
@@ -124,6 +170,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       __trap();
     }
   }
+}
+
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("gd: mbarrier (cluster) wait timeout block %d thread %d parity %u\n", blockIdx.x, threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void mbar_arrive_count(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 
 // One lane of a converged warp (elect.sync); used so that single-thread issue sits inside warp-uniform control flow.
@@ -220,6 +280,18 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   // order; a .release here costs a MEMBAR that waits for every outstanding global store of the thread (7-10% of
   // the epilogue's stall samples in profiles/ncu_conv_r01f)
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// release at cluster scope: publishes this thread's (and, after __syncwarp, its warp's) shared-memory stores to the
+// CTA that waits on the barrier
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// default semantics (release at CTA scope) on a barrier of another CTA of the cluster: what a producer warp uses after
+// fence.proxy.async to hand shared-memory tiles to the pair's MMA issuer (the tiles are read by the async proxy of the
+// CTA that wrote them; a cluster-scope release / acquire pair costs a full fence on both sides — measured: the MMA
+// issuer lost ~800 cycles per slot to the acquire)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA loads issued by either CTA of a pair; completion bytes are signalled on the barrier at `bar_cluster_addr`
 // (the leader CTA's barrier, in the shared::cluster window)

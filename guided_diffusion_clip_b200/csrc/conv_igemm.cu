@@ -37,6 +37,13 @@ constexpr int kMaxA = 8;   // activation-ring slots (barrier array size)
 constexpr int kMaxB = 32;  // weight-ring slots
 constexpr int kThreads = 320;  // warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 epilogue
 constexpr int kEpiThreads = 256;
+// Fused-GroupNorm variant (kGn): warps 2..7 normalise the main operand on its way into shared memory, the epilogue
+// moves to warps 8..15 (four whole warpgroups, so setmaxnreg can shift registers from the light roles to the epilogue)
+constexpr int kThreadsGn = 512;
+constexpr int kGnWarps = 6;
+constexpr int kGnHaloW = 18, kGnHaloH = 10;                    // (BW + 2) x (BH + 2) pixels of a 16 x 8 tile
+constexpr int kGnRows = kGnHaloW * kGnHaloH * 8 / 32;          // 45 warp-rows of 32 16-byte chunks per channel block
+constexpr int kGnIters = (kGnRows + kGnWarps - 1) / kGnWarps;  // 8 chunks per lane
 constexpr int kSmemBudget = 227 * 1024;
 constexpr int kBarrierBytes = 1024;
 constexpr int kBiasBytes = 1024;            // 256 floats
@@ -75,6 +82,13 @@ struct ConvArgs {
   int stats_ld;  // n_pad / 4
   int stats_per_tile;  // 1: one partial row per 128-pixel tile (tile inside one image); 4: one per 32-pixel quarter
   int debug;    // 0 = normal; 1 = epilogue skipped (barriers only); 2 = TMEM loads only (timing experiments)
+  // fused GroupNorm (+FiLM, +SiLU, + nearest x2) on the main operand (kGn kernels only)
+  int gn_mode, gn_silu;
+  const __half* gn_src;  // raw a0
+  int gn_ld;
+  const __half* gn_src1;  // a1 (fused 1x1-skip operand), read by the same warps
+  int gn_ld1;
+  const float* gn_coef;  // [n][c0/8][16]: a[8], b[8] per 8-channel chunk
 };
 
 __device__ __forceinline__ void tile_coords(const ConvArgs& p, int m_tile, int& n0, int& y0, int& x0) {
@@ -222,8 +236,8 @@ __device__ __forceinline__ void epi_chunk_direct(const ConvArgs& p, uint32_t tad
 // pixel tile 2*pair + r and loads its own A tile plus HALF of the weight tile; the leader's single thread issues
 // M=256 MMAs that read both CTAs' shared memory and write both CTAs' TMEM.  Halving the B traffic per SM is what
 // lifts the mainloop off the shared-memory / L2->SM bandwidth limit.
-template <bool kTwo>
-__global__ void __launch_bounds__(kThreads, 1)
+template <bool kTwo, bool kGn>
+__global__ void __launch_bounds__(kGn ? kThreadsGn : kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                   const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out,
                   const __grid_constant__ CUtensorMap map_res, const ConvArgs p) {
@@ -269,7 +283,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       tma_prefetch_desc(&map_res);
     }
     for (int s = 0; s < p.n_a; ++s) {
-      mbar_init(&full_a[s], 1);
+      // kGn: every transform warp (of both CTAs of a pair) arrives once per slot
+      mbar_init(&full_a[s], kGn ? (kTwo ? 2 * kGnWarps : kGnWarps) : 1);
       mbar_init(&empty_a[s], 1);
     }
     for (int s = 0; s < p.n_b; ++s) {
@@ -293,6 +308,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   if (kTwo) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  constexpr int kEpiWarp0 = kGn ? 8 : 2;  // first epilogue warp
   // everything above touched only shared memory, TMEM and the kernel parameters: it overlaps the predecessor's tail
   pdl_enter();
 
@@ -308,6 +324,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   const int nt0 = halo ? 3 : 1;        // taps per group
   const uint32_t tap_stride = static_cast<uint32_t>(p.bw) * 128u;  // smem bytes between ky views of a halo tile
 
+  if (warp < kEpiWarp0) {
+  // kGn: 512 threads start with 128 registers each; the producer / MMA / transform warpgroups (warps 0..7) hand 40 of
+  // them to the two epilogue warpgroups, which need ~168 for a 32-column sub-tile with residual and statistics
+  if (kGn) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     // The whole warp walks the loop (warp-uniform control flow keeps addresses and coordinates in uniform
@@ -348,17 +368,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             } else {
               kcol = p.kb0 * kBK + cb * kBK;
             }
-            mbar_wait(&empty_a[sa], pa ^ 1);
-            __syncwarp();
-            if (elect_one()) {
-              uint8_t* dst = a_ring + sa * a_slot;
-              if (kTwo) {
-                // both CTAs' loads complete on the LEADER's barrier, which expects the bytes of the whole pair
-                if (lead_cta) mbar_arrive_expect_tx(&full_a[sa], 2 * a_bytes);
-                tma_load_4d_2sm(dst, ma, full_a0_cluster + static_cast<uint32_t>(sa) * 8u, cb * kBK, cx, cy, n0);
-              } else {
-                mbar_arrive_expect_tx(&full_a[sa], a_bytes);
-                tma_load_4d(dst, ma, &full_a[sa], cb * kBK, cx, cy, n0);
+            // kGn: EVERY activation slot (main operand and fused 1x1-skip operand) is filled by the transform warps.
+            // One owner per ring: a second producer alternating on the same slots could fall two phases behind a
+            // parity wait and overwrite a slot that has not been consumed yet.
+            if (!kGn) {
+              mbar_wait(&empty_a[sa], pa ^ 1);
+              __syncwarp();
+              if (elect_one()) {
+                uint8_t* dst = a_ring + sa * a_slot;
+                if (kTwo) {
+                  // both CTAs' loads complete on the LEADER's barrier, which expects the bytes of the whole pair
+                  if (lead_cta) mbar_arrive_expect_tx(&full_a[sa], 2 * a_bytes);
+                  tma_load_4d_2sm(dst, ma, full_a0_cluster + static_cast<uint32_t>(sa) * 8u, cb * kBK, cx, cy, n0);
+                } else {
+                  mbar_arrive_expect_tx(&full_a[sa], a_bytes);
+                  tma_load_4d(dst, ma, &full_a[sa], cb * kBK, cx, cy, n0);
+                }
               }
             }
             if (++sa == n_a) {
@@ -457,16 +482,216 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         }
       }
     }
+  } else if (kGn) {
+    // ------------------------------------------------------------------ GroupNorm transform (warps 2..7, kGn only)
+    // A producer of the MAIN operand.  Per (tile, 64-channel block) the six warps read the RAW (BH+2) x (BW+2) halo of
+    // the tile straight from global memory (16-byte chunks, one per lane and iteration, all in flight while the warp
+    // waits for free slots), apply y = act(x * a + b) — the same arithmetic as gd_groupnorm_apply — ONCE per element
+    // and write the result into the three kx-shifted (BH+2) x BW halo slots the MMA consumes as row-shifted ky views,
+    // in the 128-byte-swizzled K-major layout a TMA box would have produced.  Pixels outside the image stay exactly 0:
+    // the reference pads the NORMALISED tensor (unet.py:184-185 -> conv padding=1).  GD_CONV_GN_UPSAMPLE2 reads source
+    // pixel (y/2, x/2): nearest x2 of the activated tensor (unet.py:191-195) without materialising it.
+    // The loop is issue-bound (six warps, ~1.5 per scheduler), so everything that does not depend on the tile is
+    // hoisted: per iteration a lane keeps its halo coordinates and its three destination offsets' ingredients packed
+    // in one register, validity is a mask (no branches), and the per-channel affine comes from a precomputed table.
+    const int tw = warp - 2;
+    const int cch = lane & 7, sub = lane >> 3;
+    const uint32_t a_ring_u32 = smem_base_u32 + static_cast<uint32_t>(kBarrierBytes + kBiasBytes);
+    const uint32_t full_a0_cluster = kTwo ? mapa_u32(&full_a[0], 0) : 0u;
+    const bool up = p.gn_mode == GD_CONV_GN_UPSAMPLE2;
+    const int hs = up ? (p.h >> 1) : p.h, ws = up ? (p.w >> 1) : p.w;
+    const size_t img_stride = static_cast<size_t>(hs) * ws * p.gn_ld;
+    const float act_scale = p.gn_silu != 0 ? 0.5f : 1.0f;  // SiLU(z) = h + h * tanh(h), h = z / 2: fold the 1/2 into a, b
+    const bool silu = p.gn_silu != 0;
+    // rel[i]: element offset of this lane's i-th halo pixel relative to the tile's first pixel (tile independent:
+    // y0 is a multiple of 8 and x0 of 16, so (y0 - 1 + yy) >> 1 == (y0 >> 1) + ((yy - 1) >> 1) for the x2 mode)
+    const int pidx0 = tw * 4 + sub;  // halo pixel of iteration 0; iteration i adds 4 * kGnWarps
+    int rel[kGnIters];
+#pragma unroll
+    for (int i = 0; i < kGnIters; ++i) {
+      const int pidx = pidx0 + 4 * kGnWarps * i;
+      const int yy = pidx / kGnHaloW, xx = pidx - yy * kGnHaloW;
+      rel[i] = up ? (((yy - 1) >> 1) * ws + ((xx - 1) >> 1)) * p.gn_ld : ((yy - 1) * ws + (xx - 1)) * p.gn_ld;
+    }
+    int sa = 0;
+    uint32_t pa = 0;
+    for (int tile = work0; tile < total_tiles; tile += work_step) {
+      const int m_tile = kTwo ? 2 * (tile / p.n_tiles) + static_cast<int>(rank) : tile / p.n_tiles;
+      int n0, y0, x0;
+      tile_coords(p, m_tile, n0, y0, x0);
+      const bool img_ok = n0 < p.n_img;  // (an odd tile count leaves the last pair half empty)
+      const int n_c = img_ok ? n0 : p.n_img - 1;
+      // first pixel of the tile in the source (only lanes whose pixel lies inside the image dereference img + rel[i])
+      const __half* img = p.gn_src + static_cast<size_t>(n_c) * img_stride + cch * 8 +
+                          static_cast<ptrdiff_t>(up ? ((y0 >> 1) * ws + (x0 >> 1)) : (y0 * ws + x0)) * p.gn_ld;
+      const float4* coef = reinterpret_cast<const float4*>(p.gn_coef) +
+                           (static_cast<size_t>(n_c) * (c0_total >> 3) + cch) * 4;  // + cb * 8 chunks * 4 float4
+      uint32_t vmask = 0;
+#pragma unroll
+      for (int i = 0; i < kGnIters; ++i) {
+        const int pidx = pidx0 + 4 * kGnWarps * i;
+        const int yy = pidx / kGnHaloW, xx = pidx - yy * kGnHaloW;
+        const int y = y0 - 1 + yy, x = x0 - 1 + xx;
+        const bool ok = img_ok && pidx < kGnHaloW * kGnHaloH && static_cast<unsigned>(y) < static_cast<unsigned>(p.h) &&
+                        static_cast<unsigned>(x) < static_cast<unsigned>(p.w);
+        vmask |= (ok ? 1u : 0u) << i;
+      }
+      for (int cb = 0; cb < kb0_per_tap; ++cb) {
+        // raw chunks: predicated loads, zeros where the pixel lies outside the image
+        uint32_t raw[kGnIters][4];
+#pragma unroll
+        for (int i = 0; i < kGnIters; ++i) {
+          const __half* src = img + rel[i] + cb * kBK;
+          asm volatile(
+              "{\n\t.reg .pred p;\n\t"
+              "setp.ne.b32 p, %5, 0;\n\t"
+              "mov.b32 %0, 0;\n\tmov.b32 %1, 0;\n\tmov.b32 %2, 0;\n\tmov.b32 %3, 0;\n\t"
+              "@p ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}"
+              : "=r"(raw[i][0]), "=r"(raw[i][1]), "=r"(raw[i][2]), "=r"(raw[i][3])
+              : "l"(src), "r"((vmask >> i) & 1u));
+        }
+        // the 8 channels' affine (a[8], b[8]) of this lane's chunk
+        const float4* cp = coef + cb * 32;
+        const float4 a0 = __ldg(cp), a1 = __ldg(cp + 1), b0 = __ldg(cp + 2), b1 = __ldg(cp + 3);
+        const float ga[8] = {a0.x * act_scale, a0.y * act_scale, a0.z * act_scale, a0.w * act_scale,
+                             a1.x * act_scale, a1.y * act_scale, a1.z * act_scale, a1.w * act_scale};
+        const float gb[8] = {b0.x * act_scale, b0.y * act_scale, b0.z * act_scale, b0.w * act_scale,
+                             b1.x * act_scale, b1.y * act_scale, b1.z * act_scale, b1.w * act_scale};
+        // normalise in registers while the slots are still being consumed ...
+#pragma unroll
+        for (int i = 0; i < kGnIters; ++i) {
+          const uint32_t keep = 0u - ((vmask >> i) & 1u);  // all ones for pixels inside the image
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&raw[i][q]));
+            // h = z / 2 (exact: a and b were halved); SiLU(z) = h + h * tanh(h) — gd_groupnorm_apply's silu_f
+            const float h0 = fmaf(f.x, ga[2 * q], gb[2 * q]), h1 = fmaf(f.y, ga[2 * q + 1], gb[2 * q + 1]);
+            const float r0 = silu ? fmaf(h0, tanh_approx(h0), h0) : h0;
+            const float r1 = silu ? fmaf(h1, tanh_approx(h1), h1) : h1;
+            const __half2 o = __floats2half2_rn(r0, r1);
+            raw[i][q] = *reinterpret_cast<const uint32_t*>(&o) & keep;
+          }
+        }
+        // ... then wait for the three slots of this channel block (kx = 0, 1, 2), in ring order
+        const int s0 = sa;
+        mbar_wait(&empty_a[s0], pa ^ 1);
+        if (++sa == n_a) {
+          sa = 0;
+          pa ^= 1;
+        }
+        const int s1 = sa;
+        mbar_wait(&empty_a[s1], pa ^ 1);
+        if (++sa == n_a) {
+          sa = 0;
+          pa ^= 1;
+        }
+        const int s2 = sa;
+        mbar_wait(&empty_a[s2], pa ^ 1);
+        if (++sa == n_a) {
+          sa = 0;
+          pa ^= 1;
+        }
+        const uint32_t slot0 = a_ring_u32 + static_cast<uint32_t>(s0 * a_slot);
+        const uint32_t slot1 = a_ring_u32 + static_cast<uint32_t>(s1 * a_slot) - 128u;  // kx = 1: one pixel to the left
+        const uint32_t slot2 = a_ring_u32 + static_cast<uint32_t>(s2 * a_slot) - 256u;
+#pragma unroll
+        for (int i = 0; i < kGnIters; ++i) {
+          const int pidx = pidx0 + 4 * kGnWarps * i;
+          const uint32_t yy = static_cast<uint32_t>(pidx / kGnHaloW), xx = static_cast<uint32_t>(pidx) - yy * kGnHaloW;
+          const uint32_t dst0 = (yy << 11) + (xx << 7);  // (yy * 16 + xx) * 128
+          const bool exists = pidx < kGnHaloW * kGnHaloH;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            // row (yy*16 + xx - k) of the slot, 16-byte chunk cch ^ (row & 7) = cch ^ ((xx - k) & 7)
+            const uint32_t slot = k == 0 ? slot0 : (k == 1 ? slot1 : slot2);
+            const uint32_t dst = slot + dst0 + (((static_cast<uint32_t>(cch) ^ (xx - k)) & 7u) << 4);
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "setp.ne.b32 p, %5, 0;\n\t"
+                "@p st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n\t}"
+                ::"r"(dst), "r"(raw[i][0]), "r"(raw[i][1]), "r"(raw[i][2]), "r"(raw[i][3]),
+                  "r"(static_cast<uint32_t>(exists && (xx - k) < 16u))
+                : "memory");
+          }
+        }
+        fence_proxy_async();  // generic-proxy stores -> visible to tcgen05.mma (async proxy)
+        __syncwarp();
+        if (lane == 0) {
+          if (kTwo) {
+            mbar_arrive_remote(full_a0_cluster + static_cast<uint32_t>(s0) * 8u);
+            mbar_arrive_remote(full_a0_cluster + static_cast<uint32_t>(s1) * 8u);
+            mbar_arrive_remote(full_a0_cluster + static_cast<uint32_t>(s2) * 8u);
+          } else {
+            mbar_arrive(&full_a[s0]);
+            mbar_arrive(&full_a[s1]);
+            mbar_arrive(&full_a[s2]);
+          }
+        }
+      }
+      // fused 1x1-skip operand (raw): the tile's own 16 x 8 pixels, copied global -> registers -> swizzled slot
+      if (nblk1 > 0) {
+        constexpr int kSkipIters = (128 * 8 / 32 + kGnWarps - 1) / kGnWarps;  // 32 warp-rows over 6 warps
+        const __half* img1 = p.gn_src1 + static_cast<size_t>(n_c) * p.h * p.w * p.gn_ld1 + cch * 8;
+        uint32_t off1[kSkipIters];
+        uint32_t vmask1 = 0;
+#pragma unroll
+        for (int i = 0; i < kSkipIters; ++i) {
+          const int pidx = (tw + kGnWarps * i) * 4 + sub;  // pixel of the 16 x 8 tile
+          const int y = y0 + (pidx >> 4), x = x0 + (pidx & 15);
+          const bool ok = img_ok && pidx < 128 && y < p.h && x < p.w;
+          off1[i] = ok ? static_cast<uint32_t>((y * p.w + x) * p.gn_ld1) : 0u;
+          vmask1 |= (ok ? 1u : 0u) << i;
+        }
+        for (int sb = 0; sb < nblk1; ++sb) {
+          Half8 raw[kSkipIters];
+#pragma unroll
+          for (int i = 0; i < kSkipIters; ++i) {
+            if ((vmask1 >> i) & 1u) {
+              raw[i] = ld_half8_stream(img1 + off1[i] + sb * kBK);
+            } else {
+              uint32_t* z = reinterpret_cast<uint32_t*>(&raw[i]);
+              z[0] = z[1] = z[2] = z[3] = 0u;
+            }
+          }
+          const int s0 = sa;
+          mbar_wait(&empty_a[s0], pa ^ 1);
+          if (++sa == n_a) {
+            sa = 0;
+            pa ^= 1;
+          }
+          const uint32_t slot0 = a_ring_u32 + static_cast<uint32_t>(s0 * a_slot);
+#pragma unroll
+          for (int i = 0; i < kSkipIters; ++i) {
+            const int pidx = (tw + kGnWarps * i) * 4 + sub;
+            if (pidx < 128) {
+              const uint32_t* ow = reinterpret_cast<const uint32_t*>(&raw[i]);
+              const uint32_t dst = slot0 + static_cast<uint32_t>(pidx * 128 + ((cch ^ (pidx & 7)) << 4));
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(ow[0]), "r"(ow[1]), "r"(ow[2]),
+                           "r"(ow[3])
+                           : "memory");
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            if (kTwo) mbar_arrive_remote(full_a0_cluster + static_cast<uint32_t>(s0) * 8u);
+            else mbar_arrive(&full_a[s0]);
+          }
+        }
+      }
+    }
+  }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ epilogue (warps 2..9 / kGn: 8..15)
+    if (kGn) asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
     const int quarter = warp & 3;          // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;   // row of the 128-row tile == pixel within the patch
     // Two independent epilogue groups (warps 2..5 and 6..9, one warp per TMEM lane quarter each) take alternate
     // 32-column sub-tiles of every accumulator, each with its own staging buffers, residual barrier and named
     // barrier: while one group waits (TMEM load, residual, TMA store read-out) the other computes.
-    const int group = (warp - 2) >> 2;
-    const bool leader = (threadIdx.x - 64 - group * 128) == 0;
-    const bool first_warp = ((warp - 2) & 3) == 0;  // the warp that holds the group's leader thread
+    const int group = (warp - kEpiWarp0) >> 2;
+    const bool leader = (static_cast<int>(threadIdx.x) - kEpiWarp0 * 32 - group * 128) == 0;
+    const bool first_warp = ((warp - kEpiWarp0) & 3) == 0;  // the warp that holds the group's leader thread
     uint8_t* so = s_out + group * kEpiTileBytes;
     uint8_t* sr = s_res + group * kEpiTileBytes;
     uint64_t* rbar = &res_bar[group];
@@ -787,6 +1012,25 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
 
   int bw, bh, bi;
   GD_REQUIRE(patch_shape(d->h, d->w, bw, bh, bi), "gd_conv_igemm: cannot tile %dx%d into 128-pixel patches", d->h, d->w);
+  const bool gn = d->gn_mode != GD_CONV_GN_OFF;
+  if (gn) {
+    GD_REQUIRE(d->gn_mode == GD_CONV_GN_SAME || d->gn_mode == GD_CONV_GN_UPSAMPLE2, "gd_conv_igemm: bad gn_mode %d",
+               d->gn_mode);
+    GD_REQUIRE(d->taps == 9 && gd_conv_gn_fusable(d->h, d->w) && g_halo_mode != 0,
+               "gd_conv_igemm: a fused GroupNorm operand needs a 3x3 conv over images gd_conv_gn_fusable() accepts (%dx%d)",
+               d->h, d->w);
+    GD_REQUIRE(d->gn_coef != nullptr && reinterpret_cast<uintptr_t>(d->gn_coef) % 16 == 0,
+               "gd_conv_igemm: fused GroupNorm needs the 16-byte aligned affine table gn_coef (gd_groupnorm_coef)");
+    GD_REQUIRE(reinterpret_cast<uintptr_t>(d->a0) % 16 == 0, "gd_conv_igemm: fused GroupNorm operand must be 16-byte aligned");
+    if (d->gn_mode == GD_CONV_GN_UPSAMPLE2)
+      GD_REQUIRE(d->h % 2 == 0 && d->w % 2 == 0, "gd_conv_igemm: fused upsample needs even output size");
+    const long long src_px = static_cast<long long>(d->gn_mode == GD_CONV_GN_UPSAMPLE2 ? d->h / 2 : d->h) *
+                             (d->gn_mode == GD_CONV_GN_UPSAMPLE2 ? d->w / 2 : d->w);
+    GD_REQUIRE(src_px * d->ld0 < (1ll << 31), "gd_conv_igemm: fused GroupNorm operand image too large for 32-bit offsets");
+    if (d->a1)
+      GD_REQUIRE(reinterpret_cast<uintptr_t>(d->a1) % 16 == 0 && static_cast<long long>(d->h) * d->w * d->ld1 < (1ll << 31),
+                 "gd_conv_igemm: fused GroupNorm: the 1x1 source must be 16-byte aligned and < 2^31 elements per image");
+  }
   const bool want_stats = d->stats_out != nullptr;
   if (want_stats)
     GD_REQUIRE(d->out_mode == GD_OUT_NHWC_F16 && d->cout % 64 == 0 && d->n_pad == d->cout && bw * bh >= 32 &&
@@ -832,7 +1076,21 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
   const int a_slot = halo ? (bh + 2) * bw * kBK * 2 : kATileBytes;
   const int ring_budget = kSmemBudget - kBarrierBytes - kBiasBytes - kEpiBytes - 1024;
   int n_a, n_b;
-  if (halo) {
+  if (gn) {
+    // the transform warps fill the three kx slots of a channel block at once: at least one spare slot so that they
+    // can start the next block while the last slot of the previous one is being consumed; a full second group when
+    // the weight tiles are small enough to leave room (narrow N tiles drain a slot in half the time)
+    n_a = 4;
+    n_b = (ring_budget - n_a * a_slot) / b_tile;
+    for (int na = 6; na > 4; --na) {
+      const int nb = (ring_budget - na * a_slot) / b_tile;
+      if (nb >= 6) {
+        n_a = na;
+        n_b = nb;
+        break;
+      }
+    }
+  } else if (halo) {
     // every activation slot feeds 3 taps: pick the split that keeps the most taps in flight (narrow N tiles are
     // latency-bound on the 20 KiB halo copies unless many of them are outstanding)
     int best = -1;
@@ -883,9 +1141,21 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
   p.stats = d->stats_out;
   p.stats_ld = d->n_pad / 4;
   p.stats_per_tile = bi == 1 ? 1 : 4;
+  p.gn_mode = d->gn_mode;
+  p.gn_silu = d->gn_silu;
+  p.gn_src = reinterpret_cast<const __half*>(d->a0);
+  p.gn_ld = d->ld0;
+  p.gn_src1 = reinterpret_cast<const __half*>(d->a1);
+  p.gn_ld1 = d->a1 ? d->ld1 : 0;
+  p.gn_coef = d->gn_coef;
 
   CUtensorMap ma0, ma1, mb, mout, mres;
-  int rc = encode_act_map(&ma0, d->a0, d->c0, d->ld0, d->n, d->h, d->w, bi, halo ? bh + 2 : bh, bw);
+  // (a fused-GroupNorm operand is read with plain loads; its tensor map is only a placeholder, encoded over the source
+  //  geometry so that it stays valid)
+  const int a0_h = d->gn_mode == GD_CONV_GN_UPSAMPLE2 ? d->h / 2 : d->h;
+  const int a0_w = d->gn_mode == GD_CONV_GN_UPSAMPLE2 ? d->w / 2 : d->w;
+  int rc = gn ? encode_act_map(&ma0, d->a0, d->c0, d->ld0, d->n, a0_h, a0_w, 1, 1, 8)
+              : encode_act_map(&ma0, d->a0, d->c0, d->ld0, d->n, d->h, d->w, bi, halo ? bh + 2 : bh, bw);
   if (rc) return rc;
   if (d->a1) {
     rc = encode_act_map(&ma1, d->a1, c1, d->ld1, d->n, d->h, d->w, bi, bh, bw);
@@ -911,12 +1181,20 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
 
   // Always request (almost) the full shared memory so exactly one CTA owns an SM and its 512 TMEM columns.
   const int smem_bytes = kSmemBudget;
-  static bool attr_set = false;
-  if (!attr_set) {
-    GD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    GD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_set = true;
+  {
+    // function attributes are per device: remember which devices of this process have them
+    static bool attr_set[64] = {};
+    int dev = 0;
+    GD_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+      GD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+      GD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+      GD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+      GD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+      if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
   }
+  const int threads = gn ? kThreadsGn : kThreads;
   if (two_cta) {
     // one cluster of 2 CTAs per pixel-tile pair; persistent over (pair, n tile) work items
     const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
@@ -924,7 +1202,7 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
     const int clusters = pairs < max_clusters ? pairs : max_clusters;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * clusters);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = reinterpret_cast<cudaStream_t>(stream);
     cudaLaunchAttribute attr[2];
@@ -936,16 +1214,27 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
     attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
-    GD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true>, ma0, ma1, mb, mout, mres, p));
+    if (gn) GD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true, true>, ma0, ma1, mb, mout, mres, p));
+    else GD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true, false>, ma0, ma1, mb, mout, mres, p));
   } else {
     const int total_tiles = p.m_tiles * p.n_tiles;
     const int grid = total_tiles < g_num_sms ? total_tiles : g_num_sms;
-    GD_CHECK_CUDA(launch_pdl(conv_igemm_kernel<false>, dim3(grid), dim3(kThreads), smem_bytes,
-                             reinterpret_cast<cudaStream_t>(stream), ma0, ma1, mb, mout, mres, p));
+    if (gn)
+      GD_CHECK_CUDA(launch_pdl(conv_igemm_kernel<false, true>, dim3(grid), dim3(threads), smem_bytes,
+                               reinterpret_cast<cudaStream_t>(stream), ma0, ma1, mb, mout, mres, p));
+    else
+      GD_CHECK_CUDA(launch_pdl(conv_igemm_kernel<false, false>, dim3(grid), dim3(threads), smem_bytes,
+                               reinterpret_cast<cudaStream_t>(stream), ma0, ma1, mb, mout, mres, p));
   }
   GD_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
   return 0;
+}
+
+extern "C" int gd_conv_gn_fusable(int32_t h, int32_t w) {
+  int bw, bh, bi;
+  if (h <= 0 || w <= 0 || !gd::patch_shape(h, w, bw, bh, bi)) return 0;
+  return (bi == 1 && bw == 16 && bh == 8) ? 1 : 0;
 }
 
 extern "C" int64_t gd_conv_stats_rows(int32_t n, int32_t h, int32_t w, int32_t* rows_per_image) {

@@ -154,29 +154,11 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int chunks
   }
 }
 
-// per-thread affine: y = x * a + b for the thread's 8 channels
+// per-thread affine: y = x * a + b for the thread's 8 channels (shared with the fused conv operand path)
 __device__ __forceinline__ void load_affine(const float* mean_rstd, const float* gamma, const float* beta,
                                             const float* film, int film_ld, int n, int c, int ch0, float (&a)[8],
                                             float (&b)[8]) {
-  const int cpg = c / kGroups;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int ch = ch0 + j;
-    const int g = ch / cpg;
-    const float mean = mean_rstd[(static_cast<size_t>(n) * kGroups + g) * 2];
-    const float rstd = mean_rstd[(static_cast<size_t>(n) * kGroups + g) * 2 + 1];
-    float ga = gamma[ch], be = beta[ch];
-    float aa = rstd * ga;
-    float bb = be - mean * aa;
-    if (film != nullptr) {
-      const float sc = 1.0f + film[static_cast<size_t>(n) * film_ld + ch];
-      const float sh = film[static_cast<size_t>(n) * film_ld + c + ch];
-      aa *= sc;
-      bb = bb * sc + sh;
-    }
-    a[j] = aa;
-    b[j] = bb;
-  }
+  gn_load_affine(mean_rstd, gamma, beta, film, film_ld, n, c, ch0, a, b);
 }
 
 template <bool kSilu>
@@ -556,7 +538,9 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_apply_kernel(const __half* __re
 template <int kW>
 __global__ void __launch_bounds__(128)
 gn_finalize_partials_kernel(const float* __restrict__ p0, int c0, int ld0, const float* __restrict__ p1, int c1,
-                            int ld1, int rows_per_image, int n_img, double inv_count, float eps, float* __restrict__ out) {
+                            int ld1, int rows_per_image, int n_img, double inv_count, float eps, float* __restrict__ out,
+                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                            const float* __restrict__ film, int film_ld, float* __restrict__ coef) {
   pdl_enter();
   __shared__ double sh[2][4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -594,14 +578,52 @@ gn_finalize_partials_kernel(const float* __restrict__ p0, int c0, int ld0, const
     ss = (sh[1][0] + sh[1][1]) + (sh[1][2] + sh[1][3]);
     if (warp != 0) return;
   }
-  if (active && lane == 0) {
+  if (active) {
+    // (every lane holds the full sums after the butterfly)
     const double mean = s * inv_count;
     double var = ss * inv_count - mean * mean;
     if (var < 0.0) var = 0.0;
-    float* o = out + (static_cast<size_t>(n) * kGroups + g) * 2;
-    o[0] = static_cast<float>(mean);
-    o[1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float mean_f = static_cast<float>(mean);
+    const float rstd_f = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    if (lane == 0) {
+      float* o = out + (static_cast<size_t>(n) * kGroups + g) * 2;
+      o[0] = mean_f;
+      o[1] = rstd_f;
+    }
+    if (coef != nullptr) {
+      // optional: the per-channel affine of this group, consumed by a conv that normalises its operand on the fly
+      const int c = c0 + c1;
+      for (int ch = ch_lo + lane; ch < ch_hi; ch += 32) {
+        float a, b;
+        const bool has_film = film != nullptr;
+        gn_affine(mean_f, rstd_f, gamma[ch], beta[ch], has_film,
+                  has_film ? film[static_cast<size_t>(n) * film_ld + ch] : 0.f,
+                  has_film ? film[static_cast<size_t>(n) * film_ld + c + ch] : 0.f, a, b);
+        float* o = coef + (static_cast<size_t>(n) * (c >> 3) + (ch >> 3)) * 16 + (ch & 7);
+        o[0] = a;
+        o[8] = b;
+      }
+    }
   }
+}
+
+// coef[n][c/8][16] = (a[8], b[8]) per 8-channel chunk from finished statistics (the path without fused partials)
+__global__ void gn_coef_kernel(const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
+                               const float* __restrict__ beta, const float* __restrict__ film, int film_ld, int n_img,
+                               int c, float* __restrict__ coef) {
+  pdl_enter();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_img * c) return;
+  const int n = i / c, ch = i - n * c;
+  const int g = ch / (c / kGroups);
+  float a, b;
+  const bool has_film = film != nullptr;
+  gn_affine(mean_rstd[(static_cast<size_t>(n) * kGroups + g) * 2], mean_rstd[(static_cast<size_t>(n) * kGroups + g) * 2 + 1],
+            gamma[ch], beta[ch], has_film, has_film ? film[static_cast<size_t>(n) * film_ld + ch] : 0.f,
+            has_film ? film[static_cast<size_t>(n) * film_ld + c + ch] : 0.f, a, b);
+  float* o = coef + (static_cast<size_t>(n) * (c >> 3) + (ch >> 3)) * 16 + (ch & 7);
+  o[0] = a;
+  o[8] = b;
 }
 
 }  // namespace
@@ -611,8 +633,12 @@ using namespace gd;
 
 extern "C" int gd_groupnorm_finalize_partials(const float* p0, int32_t c0, int32_t ld0, const float* p1, int32_t c1,
                                               int32_t ld1, int32_t rows_per_image, int32_t n, int32_t hw, float eps,
-                                              float* mean_rstd, void* stream) {
+                                              float* mean_rstd, const float* gamma, const float* beta, const float* film,
+                                              int32_t film_ld, float* coef_out, void* stream) {
   GD_REQUIRE(p0 && mean_rstd && n > 0 && hw > 0 && rows_per_image > 0, "gd_groupnorm_finalize_partials: bad arguments");
+  if (coef_out != nullptr)
+    GD_REQUIRE(gamma && beta && (film == nullptr || film_ld >= 2 * (c0 + (p1 ? c1 : 0))),
+               "gd_groupnorm_finalize_partials: coef_out needs gamma, beta and (if FiLM) film_ld >= 2*C");
   if (p1 == nullptr) c1 = 0;
   const int c = c0 + c1;
   GD_REQUIRE(c0 > 0 && c0 % 4 == 0 && c1 % 4 == 0 && c % 32 == 0 && (c / 32) % 4 == 0,
@@ -622,11 +648,22 @@ extern "C" int gd_groupnorm_finalize_partials(const float* p0, int32_t c0, int32
   if (rows_per_image >= 128)
     GD_CHECK_CUDA(launch_pdl(gn_finalize_partials_kernel<4>, dim3(kGroups * n), dim3(128), 0,
                              reinterpret_cast<cudaStream_t>(stream), p0, c0, ld0, p1, c1, ld1, rows_per_image, n,
-                             inv_count, eps, mean_rstd));
+                             inv_count, eps, mean_rstd, gamma, beta, film, film_ld, coef_out));
   else
     GD_CHECK_CUDA(launch_pdl(gn_finalize_partials_kernel<1>, dim3((kGroups * n + 3) / 4), dim3(128), 0,
                              reinterpret_cast<cudaStream_t>(stream), p0, c0, ld0, p1, c1, ld1, rows_per_image, n,
-                             inv_count, eps, mean_rstd));
+                             inv_count, eps, mean_rstd, gamma, beta, film, film_ld, coef_out));
+  count_launch(1);
+  return 0;
+}
+
+extern "C" int gd_groupnorm_coef(const float* mean_rstd, const float* gamma, const float* beta, const float* film,
+                                 int32_t film_ld, int32_t n, int32_t c, float* coef_out, void* stream) {
+  GD_REQUIRE(mean_rstd && gamma && beta && coef_out && n > 0, "gd_groupnorm_coef: bad arguments");
+  GD_REQUIRE(c > 0 && c % 32 == 0 && (film == nullptr || film_ld >= 2 * c), "gd_groupnorm_coef: bad channel count %d / film stride %d",
+             c, film_ld);
+  GD_CHECK_CUDA(launch_pdl(gn_coef_kernel, dim3((n * c + 255) / 256), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
+                           mean_rstd, gamma, beta, film, film_ld, n, c, coef_out));
   count_launch(1);
   return 0;
 }

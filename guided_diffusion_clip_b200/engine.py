@@ -237,7 +237,9 @@ class Emitter:
     # ---- op emitters --------------------------------------------------------------------------
     def conv(self, a0: View, wpack: th.Tensor, bias: Optional[th.Tensor], cout: int, out, *, taps=9,
              a1: Optional[View] = None, res: Optional[View] = None, res_mode=L.RES_NONE, out_mode=L.OUT_NHWC_F16,
-             out_scale=1.0, geom: Optional[Tuple[int, int, int]] = None) -> None:
+             out_scale=1.0, geom: Optional[Tuple[int, int, int]] = None, gn: Optional[dict] = None) -> None:
+        """gn = dict(mode, coef, silu): a0 is the RAW tensor and GroupNorm (+FiLM, +SiLU, + nearest x2 for mode
+        CONV_GN_UPSAMPLE2) is applied on its way into the tensor cores (gd_conv_desc.gn_*; coef from gn_stats)."""
         n, h, w = geom if geom is not None else (a0.n, a0.h, a0.w)
         d = L.ConvDesc()
         d.a0, d.c0, d.ld0, d.taps = a0.ptr, a0.c, a0.ld, taps
@@ -262,6 +264,10 @@ class Emitter:
         d.bn = 0
         d.out_scale = out_scale
         d.stats_out = None
+        if gn is not None:
+            d.gn_mode, d.gn_silu = gn["mode"], int(gn.get("silu", True))
+            d.gn_coef = gn["coef"].data_ptr()
+            self.keep.append(gn["coef"])
         self.keep += [wpack, bias, d]
         self.prog.add("gd_conv_igemm", C.byref(d))
         self.last_scale_slot = ("desc", d, None)
@@ -296,11 +302,22 @@ class Emitter:
                     return [(prod, c), (rest, x.c - c)]
         return None
 
-    def gn_stats(self, x: View, stats: th.Tensor) -> None:
+    def gn_stats(self, x: View, stats: th.Tensor, affine: Optional[dict] = None) -> Optional[th.Tensor]:
         """GroupNorm32 statistics of x.  Preferred: the producing conv(s) emit per-row-block partial sums from their
         epilogue (no extra pass over the tensor) and a tiny finalize kernel turns them into mean/rstd; otherwise the
-        two-launch statistics kernels read the tensor once."""
+        two-launch statistics kernels read the tensor once.
+        affine = dict(gamma, beta, film, film_ld): additionally produce (and return) the per-channel affine table
+        [n][C/8][16] a conv with a fused GroupNorm operand consumes — written by the finalize kernel itself where it
+        runs, by gd_groupnorm_coef otherwise."""
         lib = L.load()
+        coef = None
+        aff = (None, None, None, 0, None)
+        if affine is not None:
+            coef = th.empty((x.n, x.c // 8, 16), dtype=th.float32, device=self.device)
+            self.keep += [coef, affine["gamma"], affine["beta"]]
+            film = affine.get("film")
+            aff = (_p(affine["gamma"]), _p(affine["beta"]), C.c_void_p(film) if film else None,
+                   affine.get("film_ld", 0) if film else 0, _p(coef))
         parts = self._producers_of(x) if os.environ.get("GD_B200_NO_FUSED_STATS", "0") != "1" else None
         rpi = C.c_int32(0)
         rows = int(lib.gd_conv_stats_rows(x.n, x.h, x.w, C.byref(rpi))) if parts else 0
@@ -316,10 +333,13 @@ class Emitter:
                 bufs.append((buf, c))
             (p0, c0), (p1, c1) = bufs[0], (bufs[1] if len(bufs) > 1 else (None, 0))
             self.prog.add("gd_groupnorm_finalize_partials", _p(p0), c0, c0 // 4, _p(p1), c1, c1 // 4, rpi.value, x.n,
-                          x.h * x.w, C.c_float(GN_EPS), _p(stats))
-            return
+                          x.h * x.w, C.c_float(GN_EPS), _p(stats), *aff)
+            return coef
         self.prog.add("gd_groupnorm_stats", C.c_void_p(x.ptr), x.ld, x.n, x.h * x.w, x.c, C.c_float(GN_EPS),
                       _p(self._gn_workspace()), _p(stats))
+        if coef is not None:
+            self.prog.add("gd_groupnorm_coef", _p(stats), aff[0], aff[1], aff[2], aff[3], x.n, x.c, aff[4])
+        return coef
 
     def gn_apply(self, x: View, stats, gamma, beta, out: View, *, silu: bool, film=None, film_ld=0,
                  mode=L.GN_SAME, aux: Optional[View] = None) -> None:
@@ -413,15 +433,26 @@ class Emitter:
         assert (out.h, out.w, out.c) == (ho, wo, r.cout), (out.buf.shape, ho, wo, r.cout)
         k = r.key
         st1, st2 = self.stats_buf(), self.stats_buf()
-        a = self.scratch("gn_out", n, ho, wo, r.cin)
-        self.gn_stats(x, st1)
-        # down blocks: the same pass that pools SiLU(GN(x)) also emits avgpool(x), the block's identity residual
-        x_pool = self.scratch("x_pool", n, ho, wo, r.cin) if r.mode == "down" else None
-        self.gn_apply(x, st1, self.f32(f"{k}.in_layers.0.weight"), self.f32(f"{k}.in_layers.0.bias"), a, silu=True,
-                      mode=gmode, aux=x_pool)
+        # GroupNorm -> SiLU (-> nearest x2) -> conv: the normalisation runs inside the conv's operand path wherever the
+        # conv tiles whole 16 x 8 patches (every resolution >= 16 x 16); the normalised tensor then never exists in HBM.
+        # Down blocks average 4 activated pixels per conv input and keep the separate pass (which also emits
+        # avgpool(x), the block's identity residual, as a side output).
+        fuse = (os.environ.get("GD_B200_NO_GN_FUSE", "0") != "1" and bool(L.load().gd_conv_gn_fusable(ho, wo))
+                and x.ld % 8 == 0 and x.off % 8 == 0)
+        g1, b1 = self.f32(f"{k}.in_layers.0.weight"), self.f32(f"{k}.in_layers.0.bias")
+        fuse1 = fuse and r.mode != "down"
+        coef1 = self.gn_stats(x, st1, affine=dict(gamma=g1, beta=b1) if fuse1 else None)
         h1 = self.act(n, ho, wo, r.cout) if tape is not None else self.scratch("h1", n, ho, wo, r.cout)
         w1 = pack_conv3x3(self.P[f"{k}.in_layers.2.weight"])
-        self.conv(a, w1, self.f32(f"{k}.in_layers.2.bias"), r.cout, h1)
+        x_pool = None
+        if fuse1:
+            self.conv(x, w1, self.f32(f"{k}.in_layers.2.bias"), r.cout, h1, geom=(n, ho, wo),
+                      gn=dict(mode=L.CONV_GN_UPSAMPLE2 if r.mode == "up" else L.CONV_GN_SAME, coef=coef1, silu=True))
+        else:
+            a = self.scratch("gn_out", n, ho, wo, r.cin)
+            x_pool = self.scratch("x_pool", n, ho, wo, r.cin) if r.mode == "down" else None
+            self.gn_apply(x, st1, g1, b1, a, silu=True, mode=gmode, aux=x_pool)
+            self.conv(a, w1, self.f32(f"{k}.in_layers.2.bias"), r.cout, h1)
         film_ptr = film_all.data_ptr() + 4 * r.film_offset
         film = self.model.use_scale_shift_norm
         if not film:
@@ -430,21 +461,30 @@ class Emitter:
             self.prog.add("gd_add_emb_nhwc", C.c_void_p(h1.ptr), h1.ld, C.c_void_p(film_ptr), film_all.shape[1], n,
                           ho * wo, r.cout)
             self._producers.pop((h1.buf.data_ptr(), h1.off, h1.c), None)
-        self.gn_stats(h1, st2)
-        b = self.scratch("gn_out2", n, ho, wo, r.cout)
-        self.gn_apply(h1, st2, self.f32(f"{k}.out_layers.0.weight"), self.f32(f"{k}.out_layers.0.bias"), b, silu=True,
-                      film=film_ptr if film else None, film_ld=film_all.shape[1] if film else 0)
+        g2, b2 = self.f32(f"{k}.out_layers.0.weight"), self.f32(f"{k}.out_layers.0.bias")
+        coef2 = self.gn_stats(h1, st2, affine=dict(gamma=g2, beta=b2, film=film_ptr if film else None,
+                                                   film_ld=film_all.shape[1]) if fuse else None)
+        if fuse:
+            b, gn2 = h1, dict(mode=L.CONV_GN_SAME, coef=coef2, silu=True)
+            self.keep.append(film_all)
+        else:
+            b, gn2 = self.scratch("gn_out2", n, ho, wo, r.cout), None
+            self.gn_apply(h1, st2, g2, b2, b, silu=True, film=film_ptr if film else None,
+                          film_ld=film_all.shape[1] if film else 0)
         if r.has_skip_conv:
             assert r.mode == "none"
             w2 = pack_conv3x3(self.P[f"{k}.out_layers.3.weight"], self.P[f"{k}.skip_connection.weight"])
             bias2 = (self.f32(f"{k}.out_layers.3.bias") + self.f32(f"{k}.skip_connection.bias")).contiguous()
-            self.conv(b, w2, bias2, r.cout, out, a1=x)
+            self.conv(b, w2, bias2, r.cout, out, a1=x, gn=gn2)
         else:
             w2 = pack_conv3x3(self.P[f"{k}.out_layers.3.weight"])
             if x_pool is not None:
-                self.conv(b, w2, self.f32(f"{k}.out_layers.3.bias"), r.cout, out, res=x_pool, res_mode=L.RES_SAME)
+                self.conv(b, w2, self.f32(f"{k}.out_layers.3.bias"), r.cout, out, res=x_pool, res_mode=L.RES_SAME,
+                          gn=gn2)
+            elif r.mode == "down":
+                raise AssertionError("down block without the pooled residual")
             else:
-                self.conv(b, w2, self.f32(f"{k}.out_layers.3.bias"), r.cout, out, res=x, res_mode=rmode)
+                self.conv(b, w2, self.f32(f"{k}.out_layers.3.bias"), r.cout, out, res=x, res_mode=rmode, gn=gn2)
         if tape is not None:
             # without FiLM the saved h1 already holds h + emb_out (what the second GroupNorm saw): d(h + e)/dh = 1
             tape.append(("res", r, x, st1, h1, st2, film_ptr if film else None, film_all.shape[1] if film else 0, out))

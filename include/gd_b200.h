@@ -78,7 +78,20 @@ typedef struct gd_conv_desc {
    * is a 128-pixel tile when the tile lies inside one image, else a 32-pixel quarter of it.
    * Requires fp16 NHWC output, cout % 64 == 0 and h*w >= 32 per image; NULL = not produced. */
   float* stats_out;
+  /* Optional GroupNorm32 (+FiLM) (+SiLU) applied to the MAIN operand a0 on its way into the tensor cores
+   * (ResBlock in_layers / out_layers: GN -> SiLU -> conv, unet.py:184-185, 205-211, 248-252): a0 is then the RAW tensor
+   * and the conv computes conv3x3(pad0(act(GN(a0)))) — the zero padding applies to the NORMALISED tensor, exactly like
+   * gd_groupnorm_apply followed by this conv, bit for bit, without the normalised tensor ever touching HBM.
+   * gn_mode 0 = off; GD_CONV_GN_SAME: a0 is [n,h,w,c0]; GD_CONV_GN_UPSAMPLE2: a0 is [n,h/2,w/2,c0] and is nearest-
+   * upsampled x2 after the activation (h_upd of an "up" ResBlock, unet.py:191-195).  Requires gd_conv_gn_fusable(h,w)
+   * and taps == 9.  gn_coef: the affine table of gd_groupnorm_coef / gd_groupnorm_finalize_partials, fp32 [n][c0/8][16].
+   * The optional 1x1 source a1 stays raw. */
+  int32_t gn_mode, gn_silu;
+  const float* gn_coef;
 } gd_conv_desc;
+enum { GD_CONV_GN_OFF = 0, GD_CONV_GN_SAME = 1, GD_CONV_GN_UPSAMPLE2 = 2 };
+/* 1 if a 3x3 conv over h x w images can normalise its operand on the fly (16 x 8 pixel tiles of one image). */
+int gd_conv_gn_fusable(int32_t h, int32_t w);
 int gd_conv_igemm(const gd_conv_desc* desc, void* stream);
 /* Geometry of the fused statistics: number of row blocks the conv writes (rows of stats_out), and how many
  * consecutive rows belong to one image (rows_per_image * n == rows).  Returns 0 rows if the geometry is ineligible. */
@@ -87,7 +100,15 @@ int64_t gd_conv_stats_rows(int32_t n, int32_t h, int32_t w, int32_t* rows_per_im
  * unet.py:661) from their fused partials: c0 (+ c1) channels, 32 groups, biased variance.  p1 may be NULL. */
 int gd_groupnorm_finalize_partials(const float* p0, int32_t c0, int32_t ld0, const float* p1, int32_t c1, int32_t ld1,
                                    int32_t rows_per_image, int32_t n, int32_t hw, float eps, float* mean_rstd,
-                                   void* stream);
+                                   const float* gamma, const float* beta, const float* film, int32_t film_ld,
+                                   float* coef_out, void* stream);
+/* Per-channel affine of GroupNorm32 (+FiLM) as a table: coef_out fp32 [n][c/8][16] = for every 8-channel chunk
+ * a[8] then b[8] with  y = x*a + b,  a = rstd*gamma[*(1+scale)],  b = (beta - mean*rstd*gamma)[*(1+scale) + shift]
+ * (nn.py:17-19, unet.py:248-252; film rows are (scale[c], shift[c]) with stride film_ld, or NULL).  Consumed by
+ * gd_conv_desc.gn_coef.  gd_groupnorm_finalize_partials writes the same table when coef_out != NULL (gamma / beta /
+ * film are only read then). */
+int gd_groupnorm_coef(const float* mean_rstd, const float* gamma, const float* beta, const float* film, int32_t film_ld,
+                      int32_t n, int32_t c, float* coef_out, void* stream);
 
 /* im2col for the first layer input_blocks.0.0 (unet.py:483,741), C_in = 3 or 6: fp32 NCHW [n,cin,h,w] -> fp16 NHWC
  * [n,h,w,64] with channel k = (ky*3+kx)*cin + ci, zero padded; the conv itself then runs on gd_conv_igemm with taps=1. */

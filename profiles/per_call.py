@@ -25,7 +25,7 @@ def describe(name, args):
         k = d.k_total
         flops = 2.0 * d.n * d.h * d.w * d.cout * k
         tag = f"conv {d.h}x{d.w} K={k} (C0={d.c0} taps={d.taps} C1={d.c1}) -> {d.cout} res={d.res_mode} out={d.out_mode}" \
-              f"{' +stats' if d.stats_out else ''}"
+              f"{' +stats' if d.stats_out else ''}{' +gn%d' % d.gn_mode if d.gn_mode else ''}"
         return tag, flops
     def val(a):
         return a.value if hasattr(a, "value") else a

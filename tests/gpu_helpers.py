@@ -27,7 +27,8 @@ def nhwc_half(x_nchw: th.Tensor, ld: int = None, off: int = 0) -> th.Tensor:
 
 def conv_igemm(a0_buf, c0, off0, wpack, bias, cout, n, h, w, *, taps=9, a1_buf=None, c1=0, off1=0, res_buf=None,
                res_off=0, res_mode=L.RES_NONE, out_mode=L.OUT_NHWC_F16, ld_out=None, out_off=0, out_scale=1.0, bn=0,
-               stats_out=None, out_buf=None):
+               stats_out=None, out_buf=None, gn=None):
+    """gn = dict(mode, silu, coef): GroupNorm fused into the main operand (a0 is the raw tensor; coef from gn_coef)."""
     lib = L.load()
     d = L.ConvDesc()
     d.a0, d.c0, d.ld0, d.taps = a0_buf.data_ptr() + 2 * off0, c0, a0_buf.shape[-1], taps
@@ -48,6 +49,9 @@ def conv_igemm(a0_buf, c0, off0, wpack, bias, cout, n, h, w, *, taps=9, a1_buf=N
         d.out, d.ld_out = out.data_ptr(), 0
     d.out_mode, d.bn, d.out_scale = out_mode, bn, out_scale
     d.stats_out = stats_out.data_ptr() if stats_out is not None else None
+    if gn is not None:
+        d.gn_mode, d.gn_silu = gn["mode"], int(gn.get("silu", True))
+        d.gn_coef = gn["coef"].data_ptr()
     L.check(lib.gd_conv_igemm(C.byref(d), stream()), "gd_conv_igemm")
     return out
 
@@ -60,6 +64,14 @@ def gn_stats(x_buf, c, off=0):
     L.check(lib.gd_groupnorm_stats(C.c_void_p(x_buf.data_ptr() + 2 * off), ld, n, h * w, c, C.c_float(1e-5), vp(ws),
                                    vp(st), stream()), "gd_groupnorm_stats")
     return st
+
+
+def gn_coef(st, gamma, beta, film, n, c):
+    """Affine table [n][c/8][16] of GroupNorm32 (+FiLM) from finished statistics (gd_groupnorm_coef)."""
+    coef = th.empty((n, c // 8, 16), dtype=th.float32, device=st.device)
+    L.check(L.load().gd_groupnorm_coef(vp(st), vp(gamma), vp(beta), vp(film), film.shape[1] if film is not None else 0,
+                                       n, c, vp(coef), stream()), "gd_groupnorm_coef")
+    return coef
 
 
 def gn_apply(x_buf, c, st, gamma, beta, *, film=None, silu=True, mode=L.GN_SAME, off=0, ld_out=None, out_off=0,

@@ -238,7 +238,7 @@ def test_conv_fused_groupnorm_statistics(lib, n, h, w, c_a, c_b):
     for (p0, c0, p1, c1, t) in ((parts[0], c_a, None, 0, stored[:, :c_a]), (parts[0], c_a, parts[1], c_b, stored)):
         out = th.zeros((n, 32, 2), dtype=th.float32, device="cuda")
         L.check(lib.gd_groupnorm_finalize_partials(H.vp(p0), c0, c0 // 4, H.vp(p1), c1, c1 // 4, rpi.value, n, h * w,
-                                                   C.c_float(1e-5), H.vp(out), H.stream()))
+                                                   C.c_float(1e-5), H.vp(out), None, None, None, 0, None, H.stream()))
         th.cuda.synchronize()
         mean, rstd = ref_stats(t)
         assert float((out[..., 0] - mean).abs().max()) < 2e-4
@@ -286,9 +286,84 @@ def test_conv_in3x3_direct_first_layer(lib, n, h, w, cin, cout, ld, off):
     if (cout // 32) % 4:
         return  # the finalize kernel sums whole 4-channel chunks per group: groups of 2 channels use gd_groupnorm_stats
     st = th.empty((n, 32, 2), device="cuda")
+    g = th.Generator().manual_seed(5)
+    gamma, beta = (1 + 0.1 * th.randn(cout, generator=g)).cuda(), (0.1 * th.randn(cout, generator=g)).cuda()
+    film = (0.2 * th.randn(n, 2 * cout + 4, generator=g)).cuda()
+    coef = th.empty((n, cout // 8, 16), device="cuda")
     L.check(lib.gd_groupnorm_finalize_partials(H.vp(part), cout, cout // 4, None, 0, 0, rpi.value, n, h * w,
-                                               C.c_float(1e-5), H.vp(st), H.stream()))
+                                               C.c_float(1e-5), H.vp(st), H.vp(gamma), H.vp(beta), H.vp(film),
+                                               film.shape[1], H.vp(coef), H.stream()))
     st_ref = H.gn_stats(out, cout, off)
     th.cuda.synchronize()
     assert float((st[..., 0] - st_ref[..., 0]).abs().max()) < 1e-4
     assert H.rel_err(st[..., 1], st_ref[..., 1]) < 1e-4
+    # the affine table written next to the statistics == the standalone table kernel on the same statistics, bit for bit
+    assert th.equal(coef, H.gn_coef(st, gamma, beta, film, n, cout))
+
+
+# ---- GroupNorm (+FiLM, +SiLU, + nearest x2) fused into the conv's operand path -----------------------------------
+GN_FUSED_CASES = [
+    # n, h, w, c0, cout, c1 (fused 1x1 skip), film, residual, upsample
+    (3, 32, 32, 128, 128, 0, True, False, False),    # N = 128 tiles (6-slot ring), odd tile count in pair mode
+    (2, 64, 64, 256, 256, 0, True, True, False),     # N = 256 tiles (4-slot ring), identity residual
+    (2, 24, 40, 64, 128, 0, False, False, False),    # neither H nor W a multiple of the 16 x 8 tile
+    (2, 32, 32, 192, 64, 128, True, False, False),   # fused 1x1-skip operand shares the activation ring (TMA slots)
+    (2, 32, 32, 128, 128, 0, True, True, True),      # "up" block: source 16 x 16, nearest x2 folded into the gather
+    (1, 8, 16, 64, 64, 0, False, False, False),      # a single tile: one CTA, no pair
+    (1, 16, 16, 320, 64, 0, True, False, False),     # 5 channel blocks: ring positions wrap out of step
+    (1, 48, 16, 64, 576, 64, True, False, False),    # 3 N tiles of 192 columns per pixel tile + skip operand
+    (4, 128, 128, 256, 256, 0, True, True, False),   # 512 tiles: every CTA pair walks several tiles (4-slot ring)
+    (2, 128, 128, 128, 256, 192, True, False, False),  # several tiles per pair AND a 3-block skip operand in the ring
+    (3, 64, 64, 64, 128, 320, False, False, False),  # skip operand longer than the ring (5 blocks, 6 slots)
+]
+
+
+@pytest.mark.parametrize("n,h,w,c0,cout,c1,film,res,up", GN_FUSED_CASES)
+def test_conv_fused_groupnorm_operand_is_bit_identical_to_apply_then_conv(lib, n, h, w, c0, cout, c1, film, res, up):
+    """conv3x3(pad0(SiLU(FiLM(GN(x))))) with the normalisation done inside the conv's operand path must equal
+    gd_groupnorm_apply followed by the plain conv BIT FOR BIT (same affine, same activation, same fp16 rounding, same
+    MMA order), including the zero padding of the NORMALISED tensor at the image border (unet.py:184-185, 205-211)."""
+    assert lib.gd_conv_gn_fusable(h, w) == 1
+    hs, ws = (h // 2, w // 2) if up else (h, w)
+    x = _h(_rand((n, c0, hs, ws), 21, 1.5)) + 0.3
+    x_buf = H.nhwc_half(x, ld=c0 + 64, off=32)          # a channel slice of a wider buffer
+    gamma = (1.0 + 0.2 * _rand((c0,), 22)).contiguous()
+    beta = (0.2 * _rand((c0,), 23)).contiguous()
+    fl = (0.3 * _rand((n, 2 * c0 + 8), 24)).contiguous() if film else None
+    x_view = x_buf[..., 32:32 + c0]
+    st = H.gn_stats(x_buf, c0, off=32)
+    coef = H.gn_coef(st, gamma, beta, fl, n, c0)
+    wt = _h(_rand((cout, c0, 3, 3), 25, (c0 * 9) ** -0.5))
+    w1 = _h(_rand((cout, c1, 1, 1), 26, c1 ** -0.5)) if c1 else None
+    s_buf = H.nhwc_half(_h(_rand((n, c1, h, w), 27)), ld=c1 + 64, off=64) if c1 else None
+    r_buf = H.nhwc_half(_h(_rand((n, cout, hs, ws), 28))) if res else None
+    b = _rand((cout,), 29, 0.1)
+    pack = pack_conv3x3(wt, w1)
+    kw = dict(a1_buf=s_buf, c1=c1, off1=64 if c1 else 0, res_buf=r_buf,
+              res_mode=(L.RES_UPSAMPLE2 if up else L.RES_SAME) if res else L.RES_NONE)
+    normed = H.gn_apply(x_buf, c0, st, gamma, beta, film=fl, silu=True, mode=L.GN_UPSAMPLE2 if up else L.GN_SAME, off=32)
+    two = H.conv_igemm(normed, c0, 0, pack, b, cout, n, h, w, **kw)
+    fused = H.conv_igemm(x_buf, c0, 32, pack, b, cout, n, h, w,
+                         gn=dict(mode=L.CONV_GN_UPSAMPLE2 if up else L.CONV_GN_SAME, silu=True, coef=coef), **kw)
+    th.cuda.synchronize()
+    assert th.isfinite(fused.float()).all()
+    diff = (fused.float() - two.float()).abs().max().item()
+    print(f"fused GN conv n={n} {h}x{w} {c0}->{cout} skip={c1} film={film} res={res} up={up}: max |diff| {diff}")
+    assert th.equal(fused, two)
+    # and against torch in fp32 (the two-kernel path is already covered; this guards the test itself)
+    xn = F.group_norm(x, 32, gamma, beta, eps=1e-5)
+    if film:
+        xn = xn * (1 + fl[:, :c0, None, None]) + fl[:, c0:2 * c0, None, None]
+    xn = F.silu(xn)
+    if up:
+        xn = F.interpolate(xn, scale_factor=2, mode="nearest")
+    ref = F.conv2d(_h(xn), wt, b, padding=1)
+    assert H.rel_err(fused.permute(0, 3, 1, 2), ref) < 2e-2 or c1 or res
+
+
+def test_conv_fused_groupnorm_rejects_ineligible_geometry(lib):
+    assert lib.gd_conv_gn_fusable(8, 8) == 0 and lib.gd_conv_gn_fusable(16, 8) == 0 and lib.gd_conv_gn_fusable(64, 64) == 1
+    x_buf = th.zeros((2, 8, 8, 64), dtype=th.float16, device="cuda")
+    with pytest.raises(L.GdError, match="fusable"):
+        H.conv_igemm(x_buf, 64, 0, pack_conv3x3(th.zeros(64, 64, 3, 3)).cuda(), None, 64, 2, 8, 8,
+                     gn=dict(mode=L.CONV_GN_SAME, coef=th.zeros(2, 8, 16, device="cuda")))
