@@ -253,7 +253,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   uint64_t* tmem_full = empty_b + kMaxB;
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* res_bar = tmem_empty + 2;  // one per epilogue group
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(res_bar + 2);
+  uint64_t* main_done = res_bar + 2;   // kGn: hand-shakes between the two producers of the activation ring
+  uint64_t* skip_done = main_done + 1;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(skip_done + 1);
   float* s_stat = reinterpret_cast<float*>(smem + kBarrierBytes);  // [2 groups][4 quarters][16] parked GN partial sums
   uint8_t* a_ring = smem + kBarrierBytes + kBiasBytes;
   const int b_rows = kTwo ? (p.bn >> 1) : p.bn;  // weight rows this CTA stages per K block
@@ -297,6 +299,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     }
     mbar_init(&res_bar[0], 1);
     mbar_init(&res_bar[1], 1);
+    mbar_init(main_done, kGnWarps);
+    mbar_init(skip_done, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -338,6 +342,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     const uint32_t halo_bytes = static_cast<uint32_t>(a_slot);
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
+    uint32_t hs_phase = 0;
     for (int tile = work0; tile < total_tiles; tile += work_step) {
       const int n_tile = tile % n_tiles;
       const int m_tile = kTwo ? 2 * (tile / n_tiles) + static_cast<int>(rank) : tile / n_tiles;
@@ -368,23 +373,32 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             } else {
               kcol = p.kb0 * kBK + cb * kBK;
             }
-            // kGn: EVERY activation slot (main operand and fused 1x1-skip operand) is filled by the transform warps.
-            // One owner per ring: a second producer alternating on the same slots could fall two phases behind a
-            // parity wait and overwrite a slot that has not been consumed yet.
-            if (!kGn) {
+            // kGn: the transform warps fill the main operand's slots, this warp only the fused 1x1-skip operand's.
+            // Two producers on one ring must not pass each other (a parity wait that falls two phases behind a
+            // barrier returns early and the slot would be overwritten before it was consumed): before its first skip
+            // slot of a tile this warp waits until every transform warp has acquired the tile's last main slot
+            // (main_done), and it announces when it has acquired the tile's last skip slot (skip_done).
+            if (!(kGn && main_src)) {
+              if (kGn && cb == 0) mbar_wait(main_done, hs_phase);
               mbar_wait(&empty_a[sa], pa ^ 1);
               __syncwarp();
               if (elect_one()) {
                 uint8_t* dst = a_ring + sa * a_slot;
                 if (kTwo) {
                   // both CTAs' loads complete on the LEADER's barrier, which expects the bytes of the whole pair
-                  if (lead_cta) mbar_arrive_expect_tx(&full_a[sa], 2 * a_bytes);
+                  if (lead_cta) {
+                    mbar_arrive_expect_tx(&full_a[sa], 2 * a_bytes);
+                    if (kGn) mbar_arrive_count(&full_a[sa], 2 * kGnWarps - 1);  // stands in for the transform warps
+                  }
                   tma_load_4d_2sm(dst, ma, full_a0_cluster + static_cast<uint32_t>(sa) * 8u, cb * kBK, cx, cy, n0);
                 } else {
                   mbar_arrive_expect_tx(&full_a[sa], a_bytes);
+                  if (kGn) mbar_arrive_count(&full_a[sa], kGnWarps - 1);
                   tma_load_4d(dst, ma, &full_a[sa], cb * kBK, cx, cy, n0);
                 }
+                if (kGn && cb == nblk - 1) mbar_arrive(skip_done);
               }
+              if (kGn && cb == nblk - 1) hs_phase ^= 1;
             }
             if (++sa == n_a) {
               sa = 0;
@@ -501,8 +515,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     const bool up = p.gn_mode == GD_CONV_GN_UPSAMPLE2;
     const int hs = up ? (p.h >> 1) : p.h, ws = up ? (p.w >> 1) : p.w;
     const size_t img_stride = static_cast<size_t>(hs) * ws * p.gn_ld;
-    const float act_scale = p.gn_silu != 0 ? 0.5f : 1.0f;  // SiLU(z) = h + h * tanh(h), h = z / 2: fold the 1/2 into a, b
-    const bool silu = p.gn_silu != 0;
+    constexpr float act_scale = 0.5f;  // SiLU(z) = h + h * tanh(h), h = z / 2: the 1/2 is folded into a and b (exact)
     // rel[i]: element offset of this lane's i-th halo pixel relative to the tile's first pixel (tile independent:
     // y0 is a multiple of 8 and x0 of 16, so (y0 - 1 + yy) >> 1 == (y0 >> 1) + ((yy - 1) >> 1) for the x2 mode)
     const int pidx0 = tw * 4 + sub;  // halo pixel of iteration 0; iteration i adds 4 * kGnWarps
@@ -515,6 +528,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     }
     int sa = 0;
     uint32_t pa = 0;
+    uint32_t hs_phase = 0;
     for (int tile = work0; tile < total_tiles; tile += work_step) {
       const int m_tile = kTwo ? 2 * (tile / p.n_tiles) + static_cast<int>(rank) : tile / p.n_tiles;
       int n0, y0, x0;
@@ -566,8 +580,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&raw[i][q]));
             // h = z / 2 (exact: a and b were halved); SiLU(z) = h + h * tanh(h) — gd_groupnorm_apply's silu_f
             const float h0 = fmaf(f.x, ga[2 * q], gb[2 * q]), h1 = fmaf(f.y, ga[2 * q + 1], gb[2 * q + 1]);
-            const float r0 = silu ? fmaf(h0, tanh_approx(h0), h0) : h0;
-            const float r1 = silu ? fmaf(h1, tanh_approx(h1), h1) : h1;
+            const float r0 = fmaf(h0, tanh_approx(h0), h0);
+            const float r1 = fmaf(h1, tanh_approx(h1), h1);
             const __half2 o = __floats2half2_rn(r0, r1);
             raw[i][q] = *reinterpret_cast<const uint32_t*>(&o) & keep;
           }
@@ -591,6 +605,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           sa = 0;
           pa ^= 1;
         }
+        if (nblk1 > 0 && cb == kb0_per_tap - 1 && lane == 0) mbar_arrive(main_done);  // last main slot acquired
         const uint32_t slot0 = a_ring_u32 + static_cast<uint32_t>(s0 * a_slot);
         const uint32_t slot1 = a_ring_u32 + static_cast<uint32_t>(s1 * a_slot) - 128u;  // kx = 1: one pixel to the left
         const uint32_t slot2 = a_ring_u32 + static_cast<uint32_t>(s2 * a_slot) - 256u;
@@ -628,56 +643,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           }
         }
       }
-      // fused 1x1-skip operand (raw): the tile's own 16 x 8 pixels, copied global -> registers -> swizzled slot
+      // The fused 1x1-skip operand's slots are filled by the TMA producer.  Two producers on one ring must not pass
+      // each other (a parity wait that falls two phases behind a barrier returns early): this side announces that it
+      // has acquired the tile's last main slot (main_done, see above) and, before touching the next tile's slots, waits
+      // until the TMA producer has acquired this tile's last skip slot (skip_done).
       if (nblk1 > 0) {
-        constexpr int kSkipIters = (128 * 8 / 32 + kGnWarps - 1) / kGnWarps;  // 32 warp-rows over 6 warps
-        const __half* img1 = p.gn_src1 + static_cast<size_t>(n_c) * p.h * p.w * p.gn_ld1 + cch * 8;
-        uint32_t off1[kSkipIters];
-        uint32_t vmask1 = 0;
-#pragma unroll
-        for (int i = 0; i < kSkipIters; ++i) {
-          const int pidx = (tw + kGnWarps * i) * 4 + sub;  // pixel of the 16 x 8 tile
-          const int y = y0 + (pidx >> 4), x = x0 + (pidx & 15);
-          const bool ok = img_ok && pidx < 128 && y < p.h && x < p.w;
-          off1[i] = ok ? static_cast<uint32_t>((y * p.w + x) * p.gn_ld1) : 0u;
-          vmask1 |= (ok ? 1u : 0u) << i;
-        }
-        for (int sb = 0; sb < nblk1; ++sb) {
-          Half8 raw[kSkipIters];
-#pragma unroll
-          for (int i = 0; i < kSkipIters; ++i) {
-            if ((vmask1 >> i) & 1u) {
-              raw[i] = ld_half8_stream(img1 + off1[i] + sb * kBK);
-            } else {
-              uint32_t* z = reinterpret_cast<uint32_t*>(&raw[i]);
-              z[0] = z[1] = z[2] = z[3] = 0u;
-            }
-          }
-          const int s0 = sa;
-          mbar_wait(&empty_a[s0], pa ^ 1);
+        for (int s1 = 0; s1 < nblk1; ++s1)
           if (++sa == n_a) {
             sa = 0;
             pa ^= 1;
           }
-          const uint32_t slot0 = a_ring_u32 + static_cast<uint32_t>(s0 * a_slot);
-#pragma unroll
-          for (int i = 0; i < kSkipIters; ++i) {
-            const int pidx = (tw + kGnWarps * i) * 4 + sub;
-            if (pidx < 128) {
-              const uint32_t* ow = reinterpret_cast<const uint32_t*>(&raw[i]);
-              const uint32_t dst = slot0 + static_cast<uint32_t>(pidx * 128 + ((cch ^ (pidx & 7)) << 4));
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(ow[0]), "r"(ow[1]), "r"(ow[2]),
-                           "r"(ow[3])
-                           : "memory");
-            }
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            if (kTwo) mbar_arrive_remote(full_a0_cluster + static_cast<uint32_t>(s0) * 8u);
-            else mbar_arrive(&full_a[s0]);
-          }
-        }
+        mbar_wait(skip_done, hs_phase);
+        hs_phase ^= 1;
       }
     }
   }
@@ -939,6 +916,7 @@ int g_force_bn = 0;
 int g_disable_tma_epi = 0;
 int g_two_cta_mode = 1;
 int g_halo_mode = 1;
+int g_gn_na = 0;  // experiments: force the activation-ring depth of the fused-GroupNorm kernels
 
 }  // namespace
 
@@ -948,6 +926,7 @@ void conv_debug_set(int key, int value) {
   if (key == 2) g_disable_tma_epi = value;
   if (key == 3) g_two_cta_mode = value;
   if (key == 4) g_halo_mode = value;
+  if (key == 7) g_gn_na = value;
 }
 
 // N tile: the largest divisor of n_pad (multiple of 16, <= 256) that still yields enough tiles to fill the SMs;
@@ -1019,6 +998,8 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
     GD_REQUIRE(d->taps == 9 && gd_conv_gn_fusable(d->h, d->w) && g_halo_mode != 0,
                "gd_conv_igemm: a fused GroupNorm operand needs a 3x3 conv over images gd_conv_gn_fusable() accepts (%dx%d)",
                d->h, d->w);
+    GD_REQUIRE(d->gn_silu == 1, "gd_conv_igemm: the fused GroupNorm operand always ends in SiLU (gn_silu must be 1): "
+               "every GroupNorm that feeds a 3x3 conv in the reference is followed by one (unet.py:184, 208)");
     GD_REQUIRE(d->gn_coef != nullptr && reinterpret_cast<uintptr_t>(d->gn_coef) % 16 == 0,
                "gd_conv_igemm: fused GroupNorm needs the 16-byte aligned affine table gn_coef (gd_groupnorm_coef)");
     GD_REQUIRE(reinterpret_cast<uintptr_t>(d->a0) % 16 == 0, "gd_conv_igemm: fused GroupNorm operand must be 16-byte aligned");
@@ -1077,18 +1058,22 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
   const int ring_budget = kSmemBudget - kBarrierBytes - kBiasBytes - kEpiBytes - 1024;
   int n_a, n_b;
   if (gn) {
-    // the transform warps fill the three kx slots of a channel block at once: at least one spare slot so that they
-    // can start the next block while the last slot of the previous one is being consumed; a full second group when
-    // the weight tiles are small enough to leave room (narrow N tiles drain a slot in half the time)
+    // the transform warps fill the three kx slots of a channel block at once: two whole groups (6 slots) decouple them
+    // from the MMA completely (measured at N = 256: 1480 / 1500 / 1532 TFLOP/s for 4 / 5 / 6 slots, with only 4 weight
+    // slots left in the last case); fewer slots only where not even 4 weight slots would fit
     n_a = 4;
     n_b = (ring_budget - n_a * a_slot) / b_tile;
     for (int na = 6; na > 4; --na) {
       const int nb = (ring_budget - na * a_slot) / b_tile;
-      if (nb >= 6) {
+      if (nb >= 4) {
         n_a = na;
         n_b = nb;
         break;
       }
+    }
+    if (g_gn_na >= 4 && g_gn_na <= kMaxA && (ring_budget - g_gn_na * a_slot) / b_tile >= 2) {
+      n_a = g_gn_na;
+      n_b = (ring_budget - n_a * a_slot) / b_tile;
     }
   } else if (halo) {
     // every activation slot feeds 3 taps: pick the split that keeps the most taps in flight (narrow N tiles are

@@ -96,14 +96,46 @@ def to_uint8_nhwc(sample: th.Tensor) -> th.Tensor:
 
 
 def all_gather_batch(sample_u8: th.Tensor, labels: th.Tensor) -> Tuple[List[th.Tensor], List[th.Tensor]]:
-    """The one collective of the path (classifier_sample.py:91-96): per-rank lists in rank order."""
+    """The one collective of the path (classifier_sample.py:91-96): per-rank lists in rank order.  One
+    all_gather_into_tensor per tensor into a single [world * B, ...] buffer (no per-rank zeros_like lists)."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return [sample_u8], [labels]
-    imgs = [th.zeros_like(sample_u8) for _ in range(dist.get_world_size())]
-    dist.all_gather(imgs, sample_u8)
-    labs = [th.zeros_like(labels) for _ in range(dist.get_world_size())]
-    dist.all_gather(labs, labels)
-    return imgs, labs
+    w = dist.get_world_size()
+    imgs = th.empty((w * sample_u8.shape[0],) + tuple(sample_u8.shape[1:]), dtype=sample_u8.dtype, device=sample_u8.device)
+    labs = th.empty((w * labels.shape[0],) + tuple(labels.shape[1:]), dtype=labels.dtype, device=labels.device)
+    dist.all_gather_into_tensor(imgs, sample_u8.contiguous())
+    dist.all_gather_into_tensor(labs, labels.contiguous())
+    return list(imgs.chunk(w, 0)), list(labs.chunk(w, 0))
+
+
+class GatherBuffer:
+    """Output stage of the sampling driver (classifier_sample.py:87-96) without intermediate copies: ONE preallocated
+    [world * B, H, W, C] uint8 buffer (and [world * B] int64 labels); the uint8-NHWC pack kernel of rank r writes its
+    finished batch straight into rows [r * B, (r + 1) * B) and one in-place all_gather_into_tensor per tensor (NCCL
+    over NVLink) fills in the other ranks' rows.  Bit-identical to to_uint8_nhwc + all_gather_batch."""
+
+    def __init__(self, batch: int, c: int, h: int, w: int, device):
+        self.world, self.rank, self.batch = world_size(), rank(), batch
+        self.images = th.empty((self.world * batch, h, w, c), dtype=th.uint8, device=device)
+        self.labels = th.empty((self.world * batch,), dtype=th.int64, device=device)
+
+    def pack_and_gather(self, sample: th.Tensor, labels: th.Tensor) -> Tuple[List[th.Tensor], List[th.Tensor]]:
+        if sample.device.type != "cuda":
+            raise L.GdError("GatherBuffer only runs on CUDA; there is no CPU path")
+        n, c, h, w = sample.shape
+        assert n == self.batch and (h, w, c) == tuple(self.images.shape[1:]), (sample.shape, self.images.shape)
+        lo, hi = self.rank * n, (self.rank + 1) * n
+        x = sample.float().contiguous()
+        mine = self.images[lo:hi]
+        with th.cuda.device(sample.device):
+            stream = C.c_void_p(th.cuda.current_stream().cuda_stream)
+            L.check(L.load().gd_to_uint8_nhwc(C.c_void_p(x.data_ptr()), C.c_void_p(mine.data_ptr()), n, c, h, w, stream),
+                    "gd_to_uint8_nhwc")
+        self.labels[lo:hi].copy_(labels)
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.images, mine)          # in place: `mine` is this rank's slice
+            dist.all_gather_into_tensor(self.labels, self.labels[lo:hi])
+        return list(self.images.chunk(self.world, 0)), list(self.labels.chunk(self.world, 0))
 
 
 def sample_sharded(sample_batch: Callable[[th.Tensor], th.Tensor], *, num_samples: int, batch_size: int,
@@ -116,11 +148,18 @@ def sample_sharded(sample_batch: Callable[[th.Tensor], th.Tensor], *, num_sample
     generator.  Returns (arr uint8 [num_samples,H,W,3], label_arr int64 [num_samples]) — identical on all ranks."""
     all_images: List[np.ndarray] = []
     all_labels: List[np.ndarray] = []
+    gbuf: Optional[GatherBuffer] = None
     while len(all_images) * batch_size < num_samples:
         classes = th.randint(low=0, high=num_classes, size=(batch_size,), device=device, generator=generator)
         sample = sample_batch(classes)
-        u8 = to_uint8(sample).contiguous()
-        imgs, labs = all_gather_batch(u8, classes)
+        if to_uint8 is to_uint8_nhwc and sample.device.type == "cuda":
+            # fused output stage: the pack kernel writes into this rank's rows of the gather buffer
+            if gbuf is None:
+                gbuf = GatherBuffer(batch_size, sample.shape[1], sample.shape[2], sample.shape[3], sample.device)
+            imgs, labs = gbuf.pack_and_gather(sample, classes)
+        else:
+            u8 = to_uint8(sample).contiguous()
+            imgs, labs = all_gather_batch(u8, classes)
         all_images.extend(t.cpu().numpy() for t in imgs)
         all_labels.extend(t.cpu().numpy() for t in labs)
     arr = np.concatenate(all_images, axis=0)[:num_samples]

@@ -82,6 +82,7 @@ typedef struct gd_conv_desc {
    * (ResBlock in_layers / out_layers: GN -> SiLU -> conv, unet.py:184-185, 205-211, 248-252): a0 is then the RAW tensor
    * and the conv computes conv3x3(pad0(act(GN(a0)))) — the zero padding applies to the NORMALISED tensor, exactly like
    * gd_groupnorm_apply followed by this conv, bit for bit, without the normalised tensor ever touching HBM.
+   * gn_silu must be 1 (every GroupNorm in front of a 3x3 conv of the reference is followed by SiLU).
    * gn_mode 0 = off; GD_CONV_GN_SAME: a0 is [n,h,w,c0]; GD_CONV_GN_UPSAMPLE2: a0 is [n,h/2,w/2,c0] and is nearest-
    * upsampled x2 after the activation (h_upd of an "up" ResBlock, unet.py:191-195).  Requires gd_conv_gn_fusable(h,w)
    * and taps == 9.  gn_coef: the affine table of gd_groupnorm_coef / gd_groupnorm_finalize_partials, fp32 [n][c0/8][16].

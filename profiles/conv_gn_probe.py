@@ -39,6 +39,11 @@ def timed(fn):
 
 
 fl = 2.0 * n * hw * hw * cout * 9 * cin
+for na in (int(v) for v in os.environ.get("GN_NA", "").split(",") if v):
+    L.load().gd_debug_set(7, na)
+    t = timed(lambda: H.conv_igemm(x, cin, 0, pack, b, cout, n, hw, hw, out_buf=out, gn=gn))
+    print(f"  activation ring depth {na}: fused {t:.3f} ms ({fl / t / 1e9:.0f} TF)")
+L.load().gd_debug_set(7, 0)
 t_f = timed(lambda: H.conv_igemm(x, cin, 0, pack, b, cout, n, hw, hw, out_buf=out, gn=gn))
 normed = H.gn_apply(x, cin, st, gamma, beta, film=film, silu=True)
 t_c = timed(lambda: H.conv_igemm(normed, cin, 0, pack, b, cout, n, hw, hw, out_buf=out))

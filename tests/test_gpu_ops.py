@@ -216,6 +216,30 @@ def test_uint8_pack_truncates_like_reference(lib):
     assert th.equal(to_uint8_nhwc(x), ref)  # integer output: bit-exact
 
 
+def test_gather_buffer_output_stage_is_bit_exact(lib):
+    """SURVEY 8f row 4: the pack kernel writes this rank's rows of the single gather buffer (classifier_sample.py:87-96);
+    sample_sharded through it == the reference's expression, order and truncation (single process here; the
+    world-size-2 order is covered on CPU by test_sharding_gloo.py and on GPUs by bench.py --gpus N)."""
+    from guided_diffusion_clip_b200 import dist_util as du
+    x = _rand((4, 3, 32, 32), 22, 0.9)
+    y = th.tensor([1, 2, 3, 4], device="cuda")
+    ref = ((x + 1) * 127.5).clamp(0, 255).to(th.uint8).permute(0, 2, 3, 1).contiguous()
+    gb = du.GatherBuffer(4, 3, 32, 32, x.device)
+    imgs, labs = gb.pack_and_gather(x, y)
+    assert len(imgs) == 1 and th.equal(imgs[0], ref) and th.equal(labs[0], y)
+    calls = []
+
+    def sample_batch(classes):
+        calls.append(classes.clone())
+        return x
+
+    arr, lab = du.sample_sharded(sample_batch, num_samples=6, batch_size=4, num_classes=1000, device=x.device)
+    assert arr.shape == (6, 32, 32, 3) and arr.dtype.name == "uint8" and len(calls) == 2
+    import numpy as np
+    assert np.array_equal(arr, th.cat([ref, ref])[:6].cpu().numpy())
+    assert np.array_equal(lab, th.cat(calls)[:6].cpu().numpy())
+
+
 def test_logsoftmax_select_bwd(lib):
     n, k = 4, 1000
     logits = _rand((n, k), 21, 3.0).requires_grad_(True)
