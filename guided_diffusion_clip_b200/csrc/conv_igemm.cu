@@ -122,6 +122,17 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // named barrier of one epilogue group (4 warps); ids 1 and 2
 __device__ __forceinline__ void epi_barrier(int group) { asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory"); }
 
+// predicated 16-byte shared-memory store at a compile-time byte offset from `addr` (the offset folds into the instruction)
+template <int kOff>
+__device__ __forceinline__ void st_shared_v4_pred(uint32_t addr, const uint32_t (&v)[4], uint32_t pred) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "@p st.shared.v4.b32 [%0 + %6], {%1, %2, %3, %4};\n\t}"
+      ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(pred), "n"(kOff)
+      : "memory");
+}
+
 // 16-byte chunk `chunk` (0..3) of row `row` inside a [rows][64 B] tile laid out with the 64-byte swizzle
 __device__ __forceinline__ uint8_t* sw64(uint8_t* tile, int row, int chunk) {
   return tile + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4);
@@ -516,77 +527,127 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     const int hs = up ? (p.h >> 1) : p.h, ws = up ? (p.w >> 1) : p.w;
     const size_t img_stride = static_cast<size_t>(hs) * ws * p.gn_ld;
     constexpr float act_scale = 0.5f;  // SiLU(z) = h + h * tanh(h), h = z / 2: the 1/2 is folded into a and b (exact)
-    // rel[i]: element offset of this lane's i-th halo pixel relative to the tile's first pixel (tile independent:
-    // y0 is a multiple of 8 and x0 of 16, so (y0 - 1 + yy) >> 1 == (y0 >> 1) + ((yy - 1) >> 1) for the x2 mode)
-    const int pidx0 = tw * 4 + sub;  // halo pixel of iteration 0; iteration i adds 4 * kGnWarps
-    int rel[kGnIters];
+    // Lane geometry.  Iteration i of a lane covers halo pixel pidx0 + 24 i; 24 = 18 + 6, so the pixel's column repeats
+    // with period 3 (xx_{i+3} = xx_i) while its row advances by 4: with j = i % 3 and m = i / 3 everything that depends
+    // on the pixel splits into a per-lane constant of j (3 values, computed once per kernel) plus m times a constant —
+    // source offsets, destination offsets (m * 4 rows * 16 pixels * 128 B = m * 8192, an immediate), swizzle terms and
+    // store predicates; the per-pass address arithmetic shrinks to a handful of adds.
+    // (y0 is a multiple of 8 and x0 of 16, so (y0 - 1 + yy) >> 1 == (y0 >> 1) + ((yy - 1) >> 1) for the x2 mode.)
+    static_assert(kGnWarps * 4 == 24 && kGnHaloW == 18, "period-3 decomposition of the halo walk");
+    const int pidx0 = tw * 4 + sub;  // halo pixel of iteration 0
+    int relj[3];            // source element offset of (yy_j, xx_j) relative to the tile's first pixel
+    int xxj[3], yyj[3];
+    uint32_t dstj[3][3];    // [j][k]: byte offset inside the kx = k slot incl. the swizzle term, before + m * 8192
+    uint32_t stmask = 0;    // bit 3 j + k: column xx_j - k lies inside the kx = k slot
 #pragma unroll
-    for (int i = 0; i < kGnIters; ++i) {
-      const int pidx = pidx0 + 4 * kGnWarps * i;
+    for (int j = 0; j < 3; ++j) {
+      const int pidx = pidx0 + 24 * j;
       const int yy = pidx / kGnHaloW, xx = pidx - yy * kGnHaloW;
-      rel[i] = up ? (((yy - 1) >> 1) * ws + ((xx - 1) >> 1)) * p.gn_ld : ((yy - 1) * ws + (xx - 1)) * p.gn_ld;
+      yyj[j] = yy;
+      xxj[j] = xx;
+      relj[j] = up ? (((yy - 1) >> 1) * ws + ((xx - 1) >> 1)) * p.gn_ld : ((yy - 1) * ws + (xx - 1)) * p.gn_ld;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int xk = xx - k;
+        dstj[j][k] = static_cast<uint32_t>((yy * 16 + xk) * 128 + ((cch ^ (xk & 7)) << 4));
+        if (xk >= 0 && xk < 16) stmask |= 1u << (3 * j + k);
+      }
     }
+    const int rel_m = (up ? 2 : 4) * ws * p.gn_ld;  // source offset of 4 halo rows (2 source rows in the x2 mode)
+    const bool has7 = pidx0 + 24 * 7 < kGnHaloW * kGnHaloH;  // only the last iteration can fall off the 180-pixel halo
     int sa = 0;
     uint32_t pa = 0;
     uint32_t hs_phase = 0;
-    for (int tile = work0; tile < total_tiles; tile += work_step) {
+    // Software pipeline at HALF-pass granularity with one set of registers: a lane's 8 chunks form two halves; while
+    // half A of channel block cb is normalised and stored, the loads of half B are in flight, and while B is processed
+    // the loads of half A of the NEXT channel block (or of the next tile's first block) are in flight — the L2 latency
+    // of the raw loads hides behind the other half's arithmetic instead of adding to every pass.
+    uint32_t raw[kGnIters][4];
+    constexpr int kHalf = kGnIters / 2;
+    // source pointer (this lane's channel chunk of the tile's first pixel), affine table row and validity mask of a tile
+    auto tile_state = [&](int tile, const __half*& img, const float4*& coef, uint32_t& vmask) {
       const int m_tile = kTwo ? 2 * (tile / p.n_tiles) + static_cast<int>(rank) : tile / p.n_tiles;
       int n0, y0, x0;
       tile_coords(p, m_tile, n0, y0, x0);
       const bool img_ok = n0 < p.n_img;  // (an odd tile count leaves the last pair half empty)
       const int n_c = img_ok ? n0 : p.n_img - 1;
-      // first pixel of the tile in the source (only lanes whose pixel lies inside the image dereference img + rel[i])
-      const __half* img = p.gn_src + static_cast<size_t>(n_c) * img_stride + cch * 8 +
-                          static_cast<ptrdiff_t>(up ? ((y0 >> 1) * ws + (x0 >> 1)) : (y0 * ws + x0)) * p.gn_ld;
-      const float4* coef = reinterpret_cast<const float4*>(p.gn_coef) +
-                           (static_cast<size_t>(n_c) * (c0_total >> 3) + cch) * 4;  // + cb * 8 chunks * 4 float4
-      uint32_t vmask = 0;
+      // (only lanes whose pixel lies inside the image dereference img + rel[i])
+      img = p.gn_src + static_cast<size_t>(n_c) * img_stride + cch * 8 +
+            static_cast<ptrdiff_t>(up ? ((y0 >> 1) * ws + (x0 >> 1)) : (y0 * ws + x0)) * p.gn_ld;
+      coef = reinterpret_cast<const float4*>(p.gn_coef) + (static_cast<size_t>(n_c) * (c0_total >> 3) + cch) * 4;
+      vmask = 0;
 #pragma unroll
       for (int i = 0; i < kGnIters; ++i) {
-        const int pidx = pidx0 + 4 * kGnWarps * i;
-        const int yy = pidx / kGnHaloW, xx = pidx - yy * kGnHaloW;
-        const int y = y0 - 1 + yy, x = x0 - 1 + xx;
-        const bool ok = img_ok && pidx < kGnHaloW * kGnHaloH && static_cast<unsigned>(y) < static_cast<unsigned>(p.h) &&
+        const int y = y0 - 1 + yyj[i % 3] + 4 * (i / 3), x = x0 - 1 + xxj[i % 3];
+        const bool ok = img_ok && (i < 7 || has7) && static_cast<unsigned>(y) < static_cast<unsigned>(p.h) &&
                         static_cast<unsigned>(x) < static_cast<unsigned>(p.w);
         vmask |= (ok ? 1u : 0u) << i;
       }
+    };
+    // raw chunks of one half: predicated loads, zeros where the pixel lies outside the image
+    auto issue_half = [&](int first, const __half* img, uint32_t vmask, int cb) {
+#pragma unroll
+      for (int u = 0; u < kHalf; ++u) {
+        const int i = first + u;
+        const __half* src = img + (relj[i % 3] + (i / 3) * rel_m + cb * kBK);
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %5, 0;\n\t"
+            "mov.b32 %0, 0;\n\tmov.b32 %1, 0;\n\tmov.b32 %2, 0;\n\tmov.b32 %3, 0;\n\t"
+            "@p ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}"
+            : "=r"(raw[i][0]), "=r"(raw[i][1]), "=r"(raw[i][2]), "=r"(raw[i][3])
+            : "l"(src), "r"((vmask >> i) & 1u));
+      }
+    };
+    // normalise one half in registers and store it into the three kx-shifted slots
+    auto process_half = [&](int first, uint32_t vmask, const float (&ga)[8], const float (&gb)[8], uint32_t slot0,
+                            uint32_t slot1, uint32_t slot2) {
+#pragma unroll
+      for (int u = 0; u < kHalf; ++u) {
+        const int i = first + u;
+        const uint32_t keep = 0u - ((vmask >> i) & 1u);  // all ones for pixels inside the image
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&raw[i][q]));
+          // h = z / 2 (exact: a and b were halved); SiLU(z) = h + h * tanh(h) — gd_groupnorm_apply's silu_f
+          const float h0 = fmaf(f.x, ga[2 * q], gb[2 * q]), h1 = fmaf(f.y, ga[2 * q + 1], gb[2 * q + 1]);
+          const float r0 = fmaf(h0, tanh_approx(h0), h0);
+          const float r1 = fmaf(h1, tanh_approx(h1), h1);
+          const __half2 o = __floats2half2_rn(r0, r1);
+          raw[i][q] = *reinterpret_cast<const uint32_t*>(&o) & keep;
+        }
+        const bool exists = i < 7 || has7;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          // row (yy*16 + xx - k) of the kx = k slot, 16-byte chunk cch ^ (row & 7): dstj[j][k] + m * (4 rows of 2 KiB)
+          const uint32_t slot = k == 0 ? slot0 : (k == 1 ? slot1 : slot2);
+          const uint32_t dst = slot + dstj[i % 3][k];
+          const uint32_t pred = static_cast<uint32_t>(exists) & (stmask >> (3 * (i % 3) + k)) & 1u;
+          if (i / 3 == 0) st_shared_v4_pred<0>(dst, raw[i], pred);
+          else if (i / 3 == 1) st_shared_v4_pred<8192>(dst, raw[i], pred);
+          else st_shared_v4_pred<16384>(dst, raw[i], pred);
+        }
+      }
+    };
+    const __half* img = p.gn_src;
+    const float4* coef = reinterpret_cast<const float4*>(p.gn_coef);
+    uint32_t vmask = 0;
+    float4 cn0, cn1, cn2, cn3;  // affine (a[8], b[8]) of the NEXT channel block, prefetched
+    cn0 = cn1 = cn2 = cn3 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (work0 < total_tiles) {
+      tile_state(work0, img, coef, vmask);
+      issue_half(0, img, vmask, 0);
+      cn0 = __ldg(coef), cn1 = __ldg(coef + 1), cn2 = __ldg(coef + 2), cn3 = __ldg(coef + 3);
+    }
+    for (int tile = work0; tile < total_tiles; tile += work_step) {
       for (int cb = 0; cb < kb0_per_tap; ++cb) {
-        // raw chunks: predicated loads, zeros where the pixel lies outside the image
-        uint32_t raw[kGnIters][4];
-#pragma unroll
-        for (int i = 0; i < kGnIters; ++i) {
-          const __half* src = img + rel[i] + cb * kBK;
-          asm volatile(
-              "{\n\t.reg .pred p;\n\t"
-              "setp.ne.b32 p, %5, 0;\n\t"
-              "mov.b32 %0, 0;\n\tmov.b32 %1, 0;\n\tmov.b32 %2, 0;\n\tmov.b32 %3, 0;\n\t"
-              "@p ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}"
-              : "=r"(raw[i][0]), "=r"(raw[i][1]), "=r"(raw[i][2]), "=r"(raw[i][3])
-              : "l"(src), "r"((vmask >> i) & 1u));
-        }
-        // the 8 channels' affine (a[8], b[8]) of this lane's chunk
-        const float4* cp = coef + cb * 32;
-        const float4 a0 = __ldg(cp), a1 = __ldg(cp + 1), b0 = __ldg(cp + 2), b1 = __ldg(cp + 3);
-        const float ga[8] = {a0.x * act_scale, a0.y * act_scale, a0.z * act_scale, a0.w * act_scale,
-                             a1.x * act_scale, a1.y * act_scale, a1.z * act_scale, a1.w * act_scale};
-        const float gb[8] = {b0.x * act_scale, b0.y * act_scale, b0.z * act_scale, b0.w * act_scale,
-                             b1.x * act_scale, b1.y * act_scale, b1.z * act_scale, b1.w * act_scale};
-        // normalise in registers while the slots are still being consumed ...
-#pragma unroll
-        for (int i = 0; i < kGnIters; ++i) {
-          const uint32_t keep = 0u - ((vmask >> i) & 1u);  // all ones for pixels inside the image
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&raw[i][q]));
-            // h = z / 2 (exact: a and b were halved); SiLU(z) = h + h * tanh(h) — gd_groupnorm_apply's silu_f
-            const float h0 = fmaf(f.x, ga[2 * q], gb[2 * q]), h1 = fmaf(f.y, ga[2 * q + 1], gb[2 * q + 1]);
-            const float r0 = fmaf(h0, tanh_approx(h0), h0);
-            const float r1 = fmaf(h1, tanh_approx(h1), h1);
-            const __half2 o = __floats2half2_rn(r0, r1);
-            raw[i][q] = *reinterpret_cast<const uint32_t*>(&o) & keep;
-          }
-        }
-        // ... then wait for the three slots of this channel block (kx = 0, 1, 2), in ring order
+        // ---- half A of this block: its loads were issued one half-step ago; half B's loads go out now
+        issue_half(kHalf, img, vmask, cb);
+        const float ga[8] = {cn0.x * act_scale, cn0.y * act_scale, cn0.z * act_scale, cn0.w * act_scale,
+                             cn1.x * act_scale, cn1.y * act_scale, cn1.z * act_scale, cn1.w * act_scale};
+        const float gb[8] = {cn2.x * act_scale, cn2.y * act_scale, cn2.z * act_scale, cn2.w * act_scale,
+                             cn3.x * act_scale, cn3.y * act_scale, cn3.z * act_scale, cn3.w * act_scale};
+        // the three slots of this channel block (kx = 0, 1, 2), in ring order
         const int s0 = sa;
         mbar_wait(&empty_a[s0], pa ^ 1);
         if (++sa == n_a) {
@@ -607,28 +668,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         }
         if (nblk1 > 0 && cb == kb0_per_tap - 1 && lane == 0) mbar_arrive(main_done);  // last main slot acquired
         const uint32_t slot0 = a_ring_u32 + static_cast<uint32_t>(s0 * a_slot);
-        const uint32_t slot1 = a_ring_u32 + static_cast<uint32_t>(s1 * a_slot) - 128u;  // kx = 1: one pixel to the left
-        const uint32_t slot2 = a_ring_u32 + static_cast<uint32_t>(s2 * a_slot) - 256u;
-#pragma unroll
-        for (int i = 0; i < kGnIters; ++i) {
-          const int pidx = pidx0 + 4 * kGnWarps * i;
-          const uint32_t yy = static_cast<uint32_t>(pidx / kGnHaloW), xx = static_cast<uint32_t>(pidx) - yy * kGnHaloW;
-          const uint32_t dst0 = (yy << 11) + (xx << 7);  // (yy * 16 + xx) * 128
-          const bool exists = pidx < kGnHaloW * kGnHaloH;
-#pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            // row (yy*16 + xx - k) of the slot, 16-byte chunk cch ^ (row & 7) = cch ^ ((xx - k) & 7)
-            const uint32_t slot = k == 0 ? slot0 : (k == 1 ? slot1 : slot2);
-            const uint32_t dst = slot + dst0 + (((static_cast<uint32_t>(cch) ^ (xx - k)) & 7u) << 4);
-            asm volatile(
-                "{\n\t.reg .pred p;\n\t"
-                "setp.ne.b32 p, %5, 0;\n\t"
-                "@p st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n\t}"
-                ::"r"(dst), "r"(raw[i][0]), "r"(raw[i][1]), "r"(raw[i][2]), "r"(raw[i][3]),
-                  "r"(static_cast<uint32_t>(exists && (xx - k) < 16u))
-                : "memory");
-          }
+        const uint32_t slot1 = a_ring_u32 + static_cast<uint32_t>(s1 * a_slot);
+        const uint32_t slot2 = a_ring_u32 + static_cast<uint32_t>(s2 * a_slot);
+        process_half(0, vmask, ga, gb, slot0, slot1, slot2);
+        // ---- half B: meanwhile half A of the next channel block (or of the next tile's first block) is fetched
+        const __half* img_n = img;
+        const float4* coef_n = coef;
+        uint32_t vmask_n = vmask;
+        int cb_n = cb + 1;
+        if (cb_n == kb0_per_tap) {
+          cb_n = 0;
+          if (tile + work_step < total_tiles) tile_state(tile + work_step, img_n, coef_n, vmask_n);
+          else vmask_n = 0;  // nothing left: no loads (the table row stays a valid address)
         }
+        issue_half(0, img_n, vmask_n, cb_n);
+        {
+          const float4* cp = coef_n + cb_n * 32;
+          cn0 = __ldg(cp), cn1 = __ldg(cp + 1), cn2 = __ldg(cp + 2), cn3 = __ldg(cp + 3);
+        }
+        process_half(kHalf, vmask, ga, gb, slot0, slot1, slot2);
         fence_proxy_async();  // generic-proxy stores -> visible to tcgen05.mma (async proxy)
         __syncwarp();
         if (lane == 0) {
@@ -642,6 +700,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             mbar_arrive(&full_a[s2]);
           }
         }
+        img = img_n;
+        coef = coef_n;
+        vmask = vmask_n;
       }
       // The fused 1x1-skip operand's slots are filled by the TMA producer.  Two producers on one ring must not pass
       // each other (a parity wait that falls two phases behind a barrier returns early): this side announces that it
