@@ -25,6 +25,9 @@ NVCC_FLAGS = [
     "--use_fast_math" if False else "-DGD_NO_FAST_MATH",  # fp32 elementwise paths mirror the reference bit-for-bit
     "-Xptxas", "-v",
 ]
+# development hooks (include/gd_b200_devtools.h: gd_debug_set, gd_bw_probe) — not part of the product ABI
+if os.environ.get("GD_B200_NO_DEVTOOLS", "0") != "1":
+    NVCC_FLAGS.append("-DGD_B200_DEVTOOLS")
 
 
 def _nvcc() -> str:
@@ -36,7 +39,7 @@ def _nvcc() -> str:
 
 def _digest() -> str:
     h = hashlib.sha256()
-    for name in sorted(os.listdir(CSRC)) + ["../../include/gd_b200.h"]:
+    for name in sorted(os.listdir(CSRC)) + ["../../include/gd_b200.h", "../../include/gd_b200_devtools.h"]:
         path = os.path.join(CSRC, name)
         if os.path.isfile(path):
             with open(path, "rb") as f:

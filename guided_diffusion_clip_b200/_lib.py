@@ -64,8 +64,6 @@ SIGNATURES = {
     "gd_version": (C.c_int, []),
     "gd_launch_count": (i64, []),
     "gd_launch_count_reset": (None, []),
-    "gd_debug_set": (None, [C.c_int, C.c_int]),
-    "gd_bw_probe": (C.c_int, [i32, i32, vp, vp, i64, vp]),
     "gd_conv_igemm": (C.c_int, [C.POINTER(ConvDesc), vp]),
     "gd_conv_stats_rows": (i64, [i32, i32, i32, C.POINTER(i32)]),
     "gd_conv_gn_fusable": (C.c_int, [i32, i32]),
@@ -110,6 +108,12 @@ SIGNATURES = {
     "gd_bilinear_upsample_nchw": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
 }
 
+# development hooks (include/gd_b200_devtools.h), bound only if the library was built with them
+DEV_SIGNATURES = {
+    "gd_debug_set": (None, [C.c_int, C.c_int]),
+    "gd_bw_probe": (C.c_int, [i32, i32, vp, vp, i64, vp]),
+}
+
 _lib = None
 
 
@@ -132,6 +136,11 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the ABI and the header disagree
         fn.restype = res
         fn.argtypes = args
+    for name, (res, args) in DEV_SIGNATURES.items():
+        fn = getattr(lib, name, None)
+        if fn is not None:
+            fn.restype = res
+            fn.argtypes = args
     _lib = lib
     return lib
 

@@ -29,11 +29,13 @@ void conv_debug_set(int key, int value);
 void attn_debug_set(int value);
 }  // namespace gd
 
+#ifdef GD_B200_DEVTOOLS
 extern "C" void gd_debug_set(int key, int value) {
   if (key == 6) gd::g_pdl = value ? 1 : 0;
   else if (key == 5) gd::attn_debug_set(value);
   else gd::conv_debug_set(key, value);
 }
+#endif
 
 extern "C" const char* gd_last_error(void) { return gd::g_err; }
 extern "C" int gd_version(void) { return GD_B200_ABI_VERSION; }

@@ -2,6 +2,8 @@
 // same buffers, to separate "DRAM-bound" from "SM-side bound" behaviour when the board sits at its power cap.
 #include "common.cuh"
 #include "../../include/gd_b200.h"
+#include "../../include/gd_b200_devtools.h"
+#ifdef GD_B200_DEVTOOLS
 
 namespace gd {
 void count_launch(int n = 1);
@@ -95,3 +97,4 @@ extern "C" int gd_bw_probe(int32_t structure, int32_t math, const void* src, voi
   count_launch(1);
   return 0;
 }
+#endif  // GD_B200_DEVTOOLS

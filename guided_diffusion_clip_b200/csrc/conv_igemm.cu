@@ -342,7 +342,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   if (warp < kEpiWarp0) {
   // kGn: 512 threads start with 128 registers each; the producer / MMA / transform warpgroups (warps 0..7) hand 40 of
   // them to the two epilogue warpgroups, which need ~168 for a 32-column sub-tile with residual and statistics
-  if (kGn) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+  if (kGn) asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     // The whole warp walks the loop (warp-uniform control flow keeps addresses and coordinates in uniform
@@ -721,7 +721,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..9 / kGn: 8..15)
-    if (kGn) asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
+    if (kGn) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
     const int quarter = warp & 3;          // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;   // row of the 128-row tile == pixel within the patch
     // Two independent epilogue groups (warps 2..5 and 6..9, one warp per TMEM lane quarter each) take alternate
@@ -997,8 +997,12 @@ int conv_pick_bn(int n_pad, int m_tiles, int num_sms, int step) {
   // Measured (profiles/conv_sweep.py, r01): narrower N tiles never pay off, even when they would fill more SMs —
   // every extra N tile re-streams the whole A operand from L2 and drops the MMA below its shared-memory-bound rate
   // (32x32x512ch: 37 us at BN=256 vs 99 us at BN=64).  So: the widest tile that divides n_pad.
-  (void)m_tiles;
-  (void)num_sms;
+  // One exception (profiles/conv_small_probe.py, r02): when the widest tile leaves three quarters of the SM pairs
+  // without work — 16x16 layers at batch 8: 8 pixel-tile pairs x 4 N tiles — halving the tile to 128 columns doubles
+  // the CTAs at the same per-CTA load rate: 54 -> 35 us (C_in 1024), 93 -> 60 us (C_in 2048).  With even fewer tiles
+  // (8x8 at batch 8) the K loop of a single CTA is the floor either way; with more, 256 columns win (see above).
+  const int pairs = (m_tiles + 1) / 2;
+  if (n_pad % 256 == 0 && num_sms > 0 && pairs * (n_pad / 256) <= num_sms / 4) return 128;
   for (int bn = 256; bn >= step; bn -= step)
     if (n_pad % bn == 0) return bn;
   return 16;

@@ -143,8 +143,8 @@ def test_unsupported_configurations_raise():
 
 
 # ------------------------------------------------------------------------------------------------ C ABI
-def _declared_symbols():
-    with open(os.path.join(ROOT, "include", "gd_b200.h")) as f:
+def _declared_symbols(header="gd_b200.h"):
+    with open(os.path.join(ROOT, "include", header)) as f:
         src = f.read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(gd_[a-z0-9_]+)\s*\(", src)))
@@ -158,6 +158,9 @@ def test_library_exports_every_declared_symbol(lib):
         assert hasattr(lib, n), f"{n} declared in include/gd_b200.h but not exported"
     assert sorted(_lib.SIGNATURES) == names  # the ctypes binding covers exactly the header
     assert lib.gd_version() == 1
+    # measurement hooks are a separate header, compiled in only with -DGD_B200_DEVTOOLS, and not in the product ABI
+    dev = _declared_symbols("gd_b200_devtools.h")
+    assert dev == sorted(_lib.DEV_SIGNATURES) and not set(dev) & set(names)
 
 
 def test_abi_validates_arguments_without_gpu(lib):
