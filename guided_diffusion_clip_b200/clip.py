@@ -244,11 +244,12 @@ class CLIPPlan:
     def _head(self, text: th.Tensor, scale: float, want_grad: bool) -> None:
         m = self.model
         self.text.copy_(text.to(self.text.dtype).expand(self.n, m.proj))
-        stream = C.c_void_p(th.cuda.current_stream().cuda_stream)
-        L.check(L.load().gd_clip_head(_p(self.fcls), m.hidden, _p(self.wproj), _p(self.text), m.proj,
-                                      C.c_float(float(scale)), C.c_float(self.LOSS_SCALE), _p(self.sim),
-                                      _p(self.dfcls) if want_grad else None, m.hidden, self.n, m.hidden, m.proj, stream),
-                "gd_clip_head")
+        with th.cuda.device(self.fcls.device):  # launch on the plan's device whatever device is current
+            stream = C.c_void_p(th.cuda.current_stream().cuda_stream)
+            L.check(L.load().gd_clip_head(_p(self.fcls), m.hidden, _p(self.wproj), _p(self.text), m.proj,
+                                          C.c_float(float(scale)), C.c_float(self.LOSS_SCALE), _p(self.sim),
+                                          _p(self.dfcls) if want_grad else None, m.hidden, self.n, m.hidden, m.proj,
+                                          stream), "gd_clip_head")
 
     def similarity(self, x: th.Tensor, text: th.Tensor, scale: float) -> th.Tensor:
         self.forward(x)

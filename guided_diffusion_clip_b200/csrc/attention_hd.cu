@@ -218,10 +218,9 @@ template <int D>
 int launch_hd(const void* qkv, int ld_qkv, void* out, int ld_out, float* lse, int n, int t, int heads, int order,
               cudaStream_t st) {
   constexpr int kSmem = 5 * 64 * (2 * D + 16);
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured_on[2] = {0, 0};
+  if (gd::first_use_on_device(configured_on)) {
     GD_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_hd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    configured = true;
   }
   const float scale = 1.0f / sqrtf(static_cast<float>(D));
   attn_fwd_hd_kernel<D><<<dim3((t + kHQ - 1) / kHQ, heads, n), 128, kSmem, st>>>(

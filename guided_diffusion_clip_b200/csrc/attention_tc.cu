@@ -404,11 +404,10 @@ int attn_fwd_tc_launch(const void* qkv, int ld_qkv, void* out, int ld_out, float
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   GD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(qkv) failed: %d (heads=%d ld=%d n=%d t=%d)", (int)r, heads, ld_qkv,
              n, t);
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured_on[2] = {0, 0};
+  if (gd::first_use_on_device(configured_on)) {
     GD_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     GD_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    configured = true;
   }
   dim3 grid(t / kBQ, heads, n);
   GD_CHECK_CUDA(launch_pdl(attn_fwd_tc_kernel, grid, dim3(kTcThreads), kSmemBytes, stream, map,

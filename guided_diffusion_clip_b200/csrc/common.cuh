@@ -43,6 +43,16 @@ void set_error(const char* fmt, ...);
 // the step gets SLOWER with the attribute on -- 166.6 -> 169.8 ms at batch 64, 22.0 -> 22.4 ms at batch 8 -- so it is
 // OFF by default; GD_B200_PDL=1 (or gd_debug_set(6, 1)) turns it on.  Without the attribute griddepcontrol.* are no-ops.
 bool pdl_enabled();
+// Function attributes (opt-in dynamic shared memory) are per DEVICE: true the first time this call site runs on the
+// current device (one process may drive several GPUs), false afterwards.  `seen` is a zero-initialised static bitmap.
+inline bool first_use_on_device(unsigned long long (&seen)[2]) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 128) return true;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (seen[dev >> 6] & bit) return false;
+  seen[dev >> 6] |= bit;
+  return true;
+}
 
 #ifdef __CUDACC__
 

@@ -220,18 +220,16 @@ extern "C" int gd_conv_in3x3(const gd_conv_in_desc* d, void* stream) {
   const __half* wp = reinterpret_cast<const __half*>(d->wpack);
   __half* op = reinterpret_cast<__half*>(d->out);
   if (ks == 2) {
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured_on[2] = {0, 0};
+    if (gd::first_use_on_device(configured_on)) {
       GD_CHECK_CUDA(cudaFuncSetAttribute(conv_in3x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      configured = true;
     }
     GD_CHECK_CUDA(launch_pdl(conv_in3x3_kernel<2>, dim3(grid), dim3(kCiThreads), smem_bytes, st, d->x, wp, d->bias, op,
                              d->ld_out, d->stats_out, rpi, d->n, d->cin, d->h, d->w, d->cout));
   } else {
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured_on[2] = {0, 0};
+    if (gd::first_use_on_device(configured_on)) {
       GD_CHECK_CUDA(cudaFuncSetAttribute(conv_in3x3_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
-      configured = true;
     }
     GD_CHECK_CUDA(launch_pdl(conv_in3x3_kernel<4>, dim3(grid), dim3(kCiThreads), smem_bytes, st, d->x, wp, d->bias, op,
                              d->ld_out, d->stats_out, rpi, d->n, d->cin, d->h, d->w, d->cout));

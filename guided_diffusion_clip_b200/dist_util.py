@@ -89,9 +89,10 @@ def to_uint8_nhwc(sample: th.Tensor) -> th.Tensor:
     n, c, h, w = sample.shape
     x = sample.float().contiguous()
     out = th.empty((n, h, w, c), dtype=th.uint8, device=sample.device)
-    stream = C.c_void_p(th.cuda.current_stream().cuda_stream)
-    L.check(L.load().gd_to_uint8_nhwc(C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), n, c, h, w, stream),
-            "gd_to_uint8_nhwc")
+    with th.cuda.device(sample.device):
+        stream = C.c_void_p(th.cuda.current_stream().cuda_stream)
+        L.check(L.load().gd_to_uint8_nhwc(C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), n, c, h, w, stream),
+                "gd_to_uint8_nhwc")
     return out
 
 

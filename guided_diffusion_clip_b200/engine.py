@@ -862,13 +862,14 @@ class ClassifierPlan:
     def guidance(self, x, timesteps, y, scale: float) -> th.Tensor:
         """scale * d/dx sum_b log_softmax(classifier(x,t))[b, y_b]   (scripts/classifier_sample.py:54-61)."""
         self.forward(x, timesteps)
-        stream = C.c_void_p(th.cuda.current_stream().cuda_stream)
         yy = y.to(th.int64).contiguous()
         if yy.device != self.logits.device:
             raise L.GdError(f"labels live on {yy.device} but the classifier runs on {self.logits.device}")
-        L.check(L.load().gd_logsoftmax_select_bwd(_p(self.logits), _p(yy), _p(self.dlogits), self.n,
-                                                   self.logits.shape[1], C.c_float(1.0), stream),
-                "gd_logsoftmax_select_bwd")
+        with th.cuda.device(self.logits.device):  # launch on the plan's device whatever device is current
+            stream = C.c_void_p(th.cuda.current_stream().cuda_stream)
+            L.check(L.load().gd_logsoftmax_select_bwd(_p(self.logits), _p(yy), _p(self.dlogits), self.n,
+                                                       self.logits.shape[1], C.c_float(1.0), stream),
+                    "gd_logsoftmax_select_bwd")
         self.set_scale(scale)
         self.bwd.run()
         return self.dx

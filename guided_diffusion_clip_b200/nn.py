@@ -17,9 +17,10 @@ def timestep_embedding(timesteps, dim, max_period=10000):
         raise L.GdError("timestep_embedding only runs on CUDA; there is no CPU path")
     t = timesteps.float().contiguous()
     out = th.empty((t.shape[0], dim), dtype=th.float32, device=t.device)
-    stream = C.c_void_p(th.cuda.current_stream().cuda_stream)
-    L.check(L.load().gd_timestep_embedding(C.c_void_p(t.data_ptr()), C.c_void_p(out.data_ptr()), t.shape[0], dim, stream),
-            "gd_timestep_embedding")
+    with th.cuda.device(t.device):
+        stream = C.c_void_p(th.cuda.current_stream().cuda_stream)
+        L.check(L.load().gd_timestep_embedding(C.c_void_p(t.data_ptr()), C.c_void_p(out.data_ptr()), t.shape[0], dim,
+                                               stream), "gd_timestep_embedding")
     return out
 
 

@@ -415,3 +415,27 @@ def test_large_guidance_scale_is_applied_in_the_fp32_epilogue(lib, clf):
     assert th.isfinite(g1000).all()
     assert H.rel_err(g1000, 1000.0 * g1) < 1e-6
     assert th.equal(ClassifierGuidance(classifier, 1.0)(x, t, y=y), g1)  # the scale slot is restored per call
+
+
+@pytest.mark.skipif(th.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_two_devices_in_one_process(lib, G):
+    """function attributes (opt-in shared memory) are per device — a second GPU driven by the same
+    process must work and give the same bits as the first (plans are per device; launches go to the plan's device
+    whatever device is current)."""
+    x, t, y = cfg.model_inputs()
+    outs = []
+    for d in (0, 1):
+        m = su.create_model(**cfg.UNET_KW)
+        _load(m, cfg.UNET_SEED)
+        dev = th.device("cuda", d)
+        m.to(dev).eval()
+        c = su.create_classifier(**cfg.CLASSIFIER_KW)
+        _load(c, cfg.CLF_SEED)
+        c.to(dev).eval()
+        with th.no_grad():                      # current device stays cuda:0 on purpose
+            o = m(x.to(dev), t.to(dev), y.to(dev))
+            g = ClassifierGuidance(c, 1.0)(x.to(dev), t.to(dev), y=y.to(dev))
+        th.cuda.synchronize(dev)
+        outs.append((o.cpu(), g.cpu()))
+    assert th.equal(outs[0][0], outs[1][0]) and th.equal(outs[0][1], outs[1][1])
+    assert H.rel_err(outs[1][0], th.from_numpy(G["unet_out"])) < TOL
