@@ -23,6 +23,7 @@
 //              ONE 4-D TMA store {64ch, BW, BH, BI}: full-line writes, clipping of overhanging patches for free.
 //              Slow path (fp32 NCHW output / Cout not a multiple of 64): direct per-thread stores.
 #include "common.cuh"
+#include <stdlib.h>
 #include "../../include/gd_b200.h"
 
 namespace gd {
@@ -82,6 +83,8 @@ struct ConvArgs {
   int stats_ld;  // n_pad / 4
   int stats_per_tile;  // 1: one partial row per 128-pixel tile (tile inside one image); 4: one per 32-pixel quarter
   int debug;    // 0 = normal; 1 = epilogue skipped (barriers only); 2 = TMEM loads only (timing experiments)
+  int quad;     // pair kernels: 1 = clusters of FOUR CTAs (two pairs on consecutive pixel-tile pairs of the same N tile):
+                // every CTA loads a QUARTER of the weight tile and multicasts it to its counterpart in the other pair
   // fused GroupNorm (+FiLM, +SiLU, + nearest x2) on the main operand (kGn kernels only)
   int gn_mode, gn_silu;
   const __half* gn_src;  // raw a0
@@ -279,13 +282,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base_u32 = smem_u32(smem);
-  const uint32_t rank = kTwo ? cluster_ctarank() : 0u;
+  const uint32_t crank = kTwo ? cluster_ctarank() : 0u;  // rank in the cluster (2 CTAs, or 4 in quad mode)
+  const uint32_t rank = crank & 1u;                      // rank within the CTA pair
+  const uint32_t pair_in_cluster = crank >> 1;           // 0, or 0 / 1 in quad mode
+  const uint32_t lead_rank = crank & ~1u;                // cluster rank of this pair's leader (MMA issuer)
   const bool lead_cta = rank == 0;
-  // work items: (pixel tile | pixel-tile pair, n tile); both CTAs of a pair walk the same list
-  const int m_units = kTwo ? (p.m_tiles + 1) / 2 : p.m_tiles;
+  const bool quad = kTwo && p.quad != 0;
+  const uint16_t pair_mask = static_cast<uint16_t>(0x3u << (2u * pair_in_cluster));
+  // work items: (pixel tile | pixel-tile pair | two pixel-tile pairs, n tile); all CTAs of a cluster walk the same list
+  const int m_per = kTwo ? (quad ? 4 : 2) : 1;
+  const int m_units = (p.m_tiles + m_per - 1) / m_per;
   const int total_tiles = m_units * p.n_tiles;
-  const int work0 = kTwo ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-  const int work_step = kTwo ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int work0 = static_cast<int>(blockIdx.x) / m_per;
+  const int work_step = static_cast<int>(gridDim.x) / m_per;
+  // pixel tile of this CTA inside work item `tile`
+  auto m_tile_of = [&](int tile) {
+    return kTwo ? m_per * (tile / p.n_tiles) + 2 * static_cast<int>(pair_in_cluster) + static_cast<int>(rank)
+                : tile / p.n_tiles;
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a0);
@@ -302,7 +316,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     }
     for (int s = 0; s < p.n_b; ++s) {
       mbar_init(&full_b[s], 1);
-      mbar_init(&empty_b[s], 1);
+      mbar_init(&empty_b[s], quad ? 2 : 1);  // quad: a weight slot is refilled for BOTH pairs -> both must have read it
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
@@ -348,18 +362,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     // The whole warp walks the loop (warp-uniform control flow keeps addresses and coordinates in uniform
     // registers); one elected lane issues the copies.
     const int n_tiles = p.n_tiles, bn = p.bn;
-    const uint32_t full_a0_cluster = kTwo ? mapa_u32(&full_a[0], 0) : 0u;  // the leader's barriers
-    const uint32_t full_b0_cluster = kTwo ? mapa_u32(&full_b[0], 0) : 0u;
+    const uint32_t full_a0_cluster = kTwo ? mapa_u32(&full_a[0], lead_rank) : 0u;  // the pair leader's barriers
+    const uint32_t full_b0_cluster = kTwo ? mapa_u32(&full_b[0], lead_rank) : 0u;
     const uint32_t halo_bytes = static_cast<uint32_t>(a_slot);
+    // quad mode: this CTA fetches rows [q_row, q_row + b_rows/2) of its pair-half of the weight tile and multicasts
+    // them to the CTA of the same pair rank in the other pair (cluster ranks rank and rank + 2)
+    const int q_rows = b_rows >> 1;
+    const uint16_t mc_mask = static_cast<uint16_t>((1u << rank) | (1u << (rank + 2u)));
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
     uint32_t hs_phase = 0;
     for (int tile = work0; tile < total_tiles; tile += work_step) {
       const int n_tile = tile % n_tiles;
-      const int m_tile = kTwo ? 2 * (tile / n_tiles) + static_cast<int>(rank) : tile / n_tiles;
+      const int m_tile = m_tile_of(tile);
       int n0, y0, x0;
       tile_coords(p, m_tile, n0, y0, x0);
-      const int b_row0 = n_tile * bn + (kTwo ? static_cast<int>(rank) * b_rows : 0);
+      const int b_row0 = n_tile * bn + (kTwo ? static_cast<int>(rank) * b_rows : 0) +
+                         (quad ? static_cast<int>(pair_in_cluster) * q_rows : 0);
       for (int src = 0; src < 2; ++src) {
         const bool main_src = src == 0;
         const CUtensorMap* ma = main_src ? &map_a0 : &map_a1;
@@ -421,8 +440,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
               if (elect_one()) {
                 uint8_t* dst = b_ring + sb * b_tile_bytes;
                 if (kTwo) {
+                  // the pair leader's barrier expects the bytes landing in BOTH CTAs of the pair, whoever sends them
                   if (lead_cta) mbar_arrive_expect_tx(&full_b[sb], static_cast<uint32_t>(2 * b_tile_bytes));
-                  tma_load_2d_2sm(dst, &map_b, full_b0_cluster + static_cast<uint32_t>(sb) * 8u, kcol + t * kstep, b_row0);
+                  if (quad)
+                    tma_load_2d_2sm_mc(dst + static_cast<int>(pair_in_cluster) * q_rows * (kBK * 2), &map_b,
+                                       full_b0_cluster + static_cast<uint32_t>(sb) * 8u, kcol + t * kstep, b_row0, mc_mask);
+                  else
+                    tma_load_2d_2sm(dst, &map_b, full_b0_cluster + static_cast<uint32_t>(sb) * 8u, kcol + t * kstep, b_row0);
                 } else {
                   mbar_arrive_expect_tx(&full_b[sb], static_cast<uint32_t>(b_tile_bytes));
                   tma_load_2d(dst, &map_b, &full_b[sb], kcol + t * kstep, b_row0);
@@ -480,13 +504,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
               }
               // free the weight slot (in both CTAs of a pair) once these MMAs have read it; after a group's last
               // tap also the activation slot, after the tile's last tap signal the accumulator
-              if (kTwo) umma_commit_2sm(&empty_b[sb], 0x3);
+              if (kTwo) umma_commit_2sm(&empty_b[sb], quad ? static_cast<uint16_t>(0xF) : pair_mask);
               else umma_commit(&empty_b[sb]);
               if (t == nt - 1) {
-                if (kTwo) umma_commit_2sm(&empty_a[sa], 0x3);
+                if (kTwo) umma_commit_2sm(&empty_a[sa], pair_mask);
                 else umma_commit(&empty_a[sa]);
                 if (grp == groups_total - 1) {
-                  if (kTwo) umma_commit_2sm(&tmem_full[acc], 0x3);
+                  if (kTwo) umma_commit_2sm(&tmem_full[acc], pair_mask);
                   else umma_commit(&tmem_full[acc]);
                 }
               }
@@ -522,7 +546,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     const int tw = warp - 2;
     const int cch = lane & 7, sub = lane >> 3;
     const uint32_t a_ring_u32 = smem_base_u32 + static_cast<uint32_t>(kBarrierBytes + kBiasBytes);
-    const uint32_t full_a0_cluster = kTwo ? mapa_u32(&full_a[0], 0) : 0u;
+    const uint32_t full_a0_cluster = kTwo ? mapa_u32(&full_a[0], lead_rank) : 0u;
     const bool up = p.gn_mode == GD_CONV_GN_UPSAMPLE2;
     const int hs = up ? (p.h >> 1) : p.h, ws = up ? (p.w >> 1) : p.w;
     const size_t img_stride = static_cast<size_t>(hs) * ws * p.gn_ld;
@@ -566,10 +590,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     constexpr int kHalf = kGnIters / 2;
     // source pointer (this lane's channel chunk of the tile's first pixel), affine table row and validity mask of a tile
     auto tile_state = [&](int tile, const __half*& img, const float4*& coef, uint32_t& vmask) {
-      const int m_tile = kTwo ? 2 * (tile / p.n_tiles) + static_cast<int>(rank) : tile / p.n_tiles;
+      const int m_tile = m_tile_of(tile);
       int n0, y0, x0;
       tile_coords(p, m_tile, n0, y0, x0);
-      const bool img_ok = n0 < p.n_img;  // (an odd tile count leaves the last pair half empty)
+      const bool img_ok = n0 < p.n_img;  // (a tile count that is not a multiple of the cluster leaves CTAs without a tile)
       const int n_c = img_ok ? n0 : p.n_img - 1;
       // (only lanes whose pixel lies inside the image dereference img + rel[i])
       img = p.gn_src + static_cast<size_t>(n_c) * img_stride + cch * 8 +
@@ -735,7 +759,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     uint64_t* rbar = &res_bar[group];
     // hand a drained accumulator back to the MMA issuer (pair mode: the issuer lives in the leader CTA)
     auto release_accumulator = [&](uint64_t* bar) {
-      if (kTwo) mbar_arrive_cluster(mapa_u32(bar, 0));
+      if (kTwo) mbar_arrive_cluster(mapa_u32(bar, lead_rank));
       else mbar_arrive(bar);
     };
     const int patch_px = p.bh * p.bw;
@@ -755,7 +779,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     uint32_t acc_phase = 0;
     for (int tile = work0; tile < total_tiles; tile += work_step) {
       const int n_tile = tile % p.n_tiles;
-      const int m_tile = kTwo ? 2 * (tile / p.n_tiles) + static_cast<int>(rank) : tile / p.n_tiles;
+      const int m_tile = m_tile_of(tile);
       int n0, y0, x0;
       tile_coords(p, m_tile, n0, y0, x0);
       EpiCtx e;
@@ -978,6 +1002,17 @@ int g_disable_tma_epi = 0;
 int g_two_cta_mode = 1;
 int g_halo_mode = 1;
 int g_gn_na = 0;  // experiments: force the activation-ring depth of the fused-GroupNorm kernels
+// Clusters of four CTAs with multicast weight tiles (GD_B200_QUAD=1 / gd_debug_set(8, 1)).  OFF by default: it is
+// correct (the conv parity tests pass with it) but MEASURED slower — alone 1 498 -> 1 451 TFLOP/s (3x3 256->256 @256^2),
+// 1 069 -> 1 027 (128->128), 1 555 -> 1 499 (512->512 @64^2), and 155.5 -> 156.4 ms per batch-64 step
+// (profiles/quad_ab_r02.log): halving the L2 -> SM weight stream buys nothing because the mainloop is bound by the
+// tensor pipe at the power-capped clock (ncu: 99.3 % tensor-pipe active), while the lock-step of two pairs on one
+// weight ring and the 4-CTA cluster placement cost a few percent.
+int g_quad_mode = [] {
+  const char* e = getenv("GD_B200_QUAD");
+  return e ? atoi(e) : 0;
+}();
+int g_max_quads[2] = {-1, -1};  // co-resident 4-CTA clusters per kernel variant (cudaOccupancyMaxActiveClusters)
 
 }  // namespace
 
@@ -988,6 +1023,7 @@ void conv_debug_set(int key, int value) {
   if (key == 3) g_two_cta_mode = value;
   if (key == 4) g_halo_mode = value;
   if (key == 7) g_gn_na = value;
+  if (key == 8) g_quad_mode = value;
 }
 
 // N tile: the largest divisor of n_pad (multiple of 16, <= 256) that still yields enough tiles to fill the SMs;
@@ -1102,6 +1138,7 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
 
   ConvArgs p;
   p.debug = g_debug_epilogue;
+  p.quad = 0;
   p.n_img = d->n;
   p.h = d->h;
   p.w = d->w;
@@ -1213,7 +1250,14 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
   } else {
     ma1 = ma0;
   }
-  rc = encode_weight_map(&mb, d->wpack, k_total, d->n_pad, two_cta ? bn / 2 : bn);
+  // quad mode: clusters of 4 = two CTA pairs on consecutive pixel-tile pairs of the same N tile; every CTA fetches a
+  // quarter of the weight tile and multicasts it to the other pair, which halves the L2 -> SM weight stream (the
+  // largest operand stream of the mainloop: 590 KB of weights against 245 KB of activations per 128 x 256 tile).
+  // Needs whole 8-row swizzle groups per quarter and at least one work item per cluster slot to be worth the lock-step.
+  const bool quad = two_cta && g_quad_mode != 0 && (bn / 4) % 8 == 0 && m_tiles >= 8 &&
+                    ((m_tiles + 3) / 4) * (d->n_pad / bn) >= g_num_sms / 8;
+  p.quad = quad ? 1 : 0;
+  rc = encode_weight_map(&mb, d->wpack, k_total, d->n_pad, quad ? bn / 4 : (two_cta ? bn / 2 : bn));
   if (rc) return rc;
   mout = ma0;
   mres = ma0;
@@ -1246,18 +1290,36 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
   }
   const int threads = gn ? kThreadsGn : kThreads;
   if (two_cta) {
-    // one cluster of 2 CTAs per pixel-tile pair; persistent over (pair, n tile) work items
-    const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
-    const int max_clusters = g_num_sms / 2;
-    const int clusters = pairs < max_clusters ? pairs : max_clusters;
+    // one cluster of 2 (or 4) CTAs per pixel-tile pair (or two pairs); persistent over (m unit, n tile) work items
+    const int csize = quad ? 4 : 2;
+    const int items = ((p.m_tiles + csize - 1) / csize) * p.n_tiles;
+    int max_clusters = g_num_sms / csize;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * clusters);
     cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = reinterpret_cast<cudaStream_t>(stream);
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.x = csize;
+    if (quad) {
+      // how many 4-CTA clusters the GPU can hold at once (GPC boundaries may leave SMs unused): ask the driver once
+      int& cached = g_max_quads[gn ? 1 : 0];
+      if (cached < 0) {
+        cfg.gridDim = dim3(4 * max_clusters);
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        int n = 0;
+        cudaError_t e = gn ? cudaOccupancyMaxActiveClusters(&n, conv_igemm_kernel<true, true>, &cfg)
+                           : cudaOccupancyMaxActiveClusters(&n, conv_igemm_kernel<true, false>, &cfg);
+        cached = (e == cudaSuccess && n > 0) ? n : max_clusters;
+        (void)cudaGetLastError();
+      }
+      if (cached < max_clusters) max_clusters = cached;
+    }
+    const int clusters = items < max_clusters ? items : max_clusters;
+    cfg.gridDim = dim3(csize * clusters);
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;

@@ -13,7 +13,8 @@ extern "C" {
  * TMA-store epilogue, key 3 = 0 disables CTA-pair (cta_group::2) mode, key 4 = 0 disables halo reuse (every tap
  * loads its own activation tile), key 5 = 0 disables the tcgen05 attention forward (mma.sync kernel for every length),
  * key 6 = 1 launches the frequent kernels with programmatic dependent launch (default 0: measured slower, DESIGN.md 4.2;
- * also GD_B200_PDL=1), key 7 = force the activation-ring depth of the fused-GroupNorm conv kernels (0 = heuristic). */
+ * also GD_B200_PDL=1), key 7 = force the activation-ring depth of the fused-GroupNorm conv kernels (0 = heuristic), key 8 = 0 disables
+ * the 4-CTA-cluster mode (weight tiles multicast to two CTA pairs). */
 void gd_debug_set(int key, int value);
 /* Measurement hook (profiles/bw_probe.py): stream `bytes` from src to dst. structure 0 = one-shot flat grid, -k = 256-thread
  * CTAs owning a contiguous region walked in k rounds of 8 loads/stores per thread, k>0 =

@@ -45,6 +45,14 @@ for na in (int(v) for v in os.environ.get("GN_NA", "").split(",") if v):
     print(f"  activation ring depth {na}: fused {t:.3f} ms ({fl / t / 1e9:.0f} TF)")
 L.load().gd_debug_set(7, 0)
 t_f = timed(lambda: H.conv_igemm(x, cin, 0, pack, b, cout, n, hw, hw, out_buf=out, gn=gn))
+if os.environ.get("QUAD_AB"):
+    for q in (0, 1, 0, 1):
+        L.load().gd_debug_set(8, q)
+        normed_ = H.gn_apply(x, cin, st, gamma, beta, film=film, silu=True)
+        tf_ = timed(lambda: H.conv_igemm(x, cin, 0, pack, b, cout, n, hw, hw, out_buf=out, gn=gn))
+        tc_ = timed(lambda: H.conv_igemm(normed_, cin, 0, pack, b, cout, n, hw, hw, out_buf=out))
+        print(f"  quad={q}: fused {tf_:.3f} ms ({fl / tf_ / 1e9:.0f} TF) | plain {tc_:.3f} ms ({fl / tc_ / 1e9:.0f} TF)")
+    L.load().gd_debug_set(8, 1)
 normed = H.gn_apply(x, cin, st, gamma, beta, film=film, silu=True)
 t_c = timed(lambda: H.conv_igemm(normed, cin, 0, pack, b, cout, n, hw, hw, out_buf=out))
 t_a = timed(lambda: H.gn_apply(x, cin, st, gamma, beta, film=film, silu=True))
