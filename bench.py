@@ -498,6 +498,14 @@ def run_gpu_arm(args):
         dist_util.setup_dist("nccl")
     dev = th.device("cuda", local)
     B, S = args.batch, args.image_size
+    if world > 1:
+        # warm-up of the collective itself: NCCL builds its communicator (rings, NVLS buffers) lazily inside the first
+        # call — a one-time cost of ~1.5 s at 8 ranks that belongs to process start-up, not to a sampling batch
+        w_in = th.zeros(16, dtype=th.uint8, device=dev)
+        w_out = th.zeros(16 * world, dtype=th.uint8, device=dev)
+        for _ in range(2):
+            dist.all_gather_into_tensor(w_out, w_in)
+        th.cuda.synchronize()
     th.manual_seed(dist_util.rank_seed(args.seed, rank))
     diffusion, model_fn, cond_fn = build_cfg2(S, dev)
 
