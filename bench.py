@@ -549,6 +549,9 @@ def run_gpu_arm(args):
     full = None
     if not args.no_full_loop:
         gbuf = dist_util.GatherBuffer(B, 3, S, S, dev)
+        # warm-up of the output stage at its real size (NCCL sets up the channels / protocol of a message size on first
+        # use: 0.7 - 1.5 s for the first 50 - 100 MB gather of a process, a one-time cost)
+        gbuf.pack_and_gather(th.zeros(shape, device=dev), y)
         if world > 1:
             dist.barrier()
         th.cuda.synchronize()
