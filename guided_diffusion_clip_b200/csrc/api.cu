@@ -25,6 +25,16 @@ bool pdl_enabled() {
   }
   return g_pdl != 0;
 }
+// the same attribute for the TINY kernels between two convs only (statistics finalize / affine table): their launch
+// latency is a visible share of a small-batch step (GD_B200_PDL_SMALL=1; measured in profiles/pdl_small_r02.log)
+static int g_pdl_small = -1;
+bool pdl_small_enabled() {
+  if (g_pdl_small < 0) {
+    const char* e = getenv("GD_B200_PDL_SMALL");
+    g_pdl_small = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return g_pdl_small != 0 || pdl_enabled();
+}
 void conv_debug_set(int key, int value);
 void attn_debug_set(int value);
 }  // namespace gd

@@ -72,6 +72,27 @@ __device__ __forceinline__ void fmul2(float& d0, float& d1, float a0, float a1, 
       : "=f"(d0), "=f"(d1)
       : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
+// 2^a for a PAIR of scores on the FMA / integer pipes instead of the MUFU (which is the bound of the softmax: one
+// ex2 per score at 16 per clock and SM).  Cody-Waite with the round-to-nearest magic number: x = a + 1.5*2^23 carries
+// n = rint(a) in its low mantissa bits, r = a - n lies in [-0.5, 0.5], 2^r is a degree-4 polynomial (relative error
+// 4.5e-5, an order of magnitude below the fp16 rounding of P) and 2^n is added to the exponent field with one shift-add
+// (the magic number's own bits shift out).  a is clamped at -120: 2^-120 rounds to the same fp16 zero as ex2(-inf).
+__device__ __forceinline__ void ex2_poly2(float a0, float a1, float& p0, float& p1) {
+  constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23
+  a0 = fmaxf(a0, -120.0f);
+  a1 = fmaxf(a1, -120.0f);
+  float x0, x1, n0, n1, r0, r1;
+  fadd2(x0, x1, a0, a1, kMagic, kMagic);
+  fadd2(n0, n1, x0, x1, -kMagic, -kMagic);
+  ffma2(r0, r1, n0, n1, -1.0f, -1.0f, a0, a1);
+  float q0, q1;
+  ffma2(q0, q1, r0, r1, 0.009618129f, 0.009618129f, 0.055504109f, 0.055504109f);
+  ffma2(q0, q1, q0, q1, r0, r1, 0.240226507f, 0.240226507f);
+  ffma2(q0, q1, q0, q1, r0, r1, 0.693147181f, 0.693147181f);
+  ffma2(q0, q1, q0, q1, r0, r1, 1.0f, 1.0f);
+  p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(x0) << 23));
+  p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(x1) << 23));
+}
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -97,6 +118,8 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// kPolyMask: which of the 16 score pairs of every 32-column chunk take the polynomial exponential (bit i = pair i)
+template <uint32_t kPolyMask>
 __global__ void __launch_bounds__(kTcThreads, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __half* __restrict__ out, int ld_out,
                    float* __restrict__ lse, int t, int t_valid, int heads, int order) {
@@ -303,7 +326,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __half* __restri
         for (int i = 0; i < 16; ++i) {
           float a0, a1;
           ffma2(a0, a1, __uint_as_float(v[c][2 * i]), __uint_as_float(v[c][2 * i + 1]), sc, sc, nmsc, nmsc);
-          const float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
+          float p0, p1;
+          if ((kPolyMask >> i) & 1u) {
+            ex2_poly2(a0, a1, p0, p1);
+          } else {
+            p0 = ex2_approx(a0);
+            p1 = ex2_approx(a1);
+          }
           fadd2(rs[c][0], rs[c][1], rs[c][0], rs[c][1], p0, p1);
           h[i] = pack_h2(p0, p1);
         }
@@ -379,10 +408,19 @@ EncodeTiledFn encode_fn() {
 }
 
 int g_attn_tc_enabled = 1;
+// Share of the exponentials computed with the polynomial on the FMA pipe (index into the instantiated masks).  Measured
+// (profiles/attn_sweep.py, r02, 8 heads x T = 1024 at batch 64): 0/16 637.5, 4/16 663.3, 6/16 638.0, 8/16 609.0 TFLOP/s —
+// the softmax is co-limited by issue slots (the polynomial costs ~5.5 slots per score against 1.5 for the MUFU path),
+// so only a quarter of the scores is worth moving.
+int g_attn_poly = 1;
 
 }  // namespace
 
-void attn_debug_set(int value) { g_attn_tc_enabled = value; }
+// 0 / 1: mma.sync or tcgen05 forward; 10 + k: select the polynomial-exponential share k (0: none, 1: 4/16, 2: 6/16, 3: 8/16)
+void attn_debug_set(int value) {
+  if (value >= 10) g_attn_poly = value - 10;
+  else g_attn_tc_enabled = value;
+}
 
 // true when the tcgen05 kernel covers this call (otherwise the caller runs the mma.sync kernel)
 bool attn_fwd_tc_applicable(const void* qkv, int ld_qkv, const void* out, int ld_out, int t) {
@@ -404,13 +442,20 @@ int attn_fwd_tc_launch(const void* qkv, int ld_qkv, void* out, int ld_out, float
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   GD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(qkv) failed: %d (heads=%d ld=%d n=%d t=%d)", (int)r, heads, ld_qkv,
              n, t);
+  auto k0 = attn_fwd_tc_kernel<0x0000u>;
+  auto k1 = attn_fwd_tc_kernel<0x1111u>;   // 4 of 16 pairs
+  auto k2 = attn_fwd_tc_kernel<0x4925u>;   // 6 of 16
+  auto k3 = attn_fwd_tc_kernel<0x5555u>;   // 8 of 16
   static unsigned long long configured_on[2] = {0, 0};
   if (gd::first_use_on_device(configured_on)) {
-    GD_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    GD_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    for (auto k : {k0, k1, k2, k3}) {
+      GD_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+      GD_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    }
   }
   dim3 grid(t / kBQ, heads, n);
-  GD_CHECK_CUDA(launch_pdl(attn_fwd_tc_kernel, grid, dim3(kTcThreads), kSmemBytes, stream, map,
+  auto kern = g_attn_poly == 0 ? k0 : g_attn_poly == 1 ? k1 : g_attn_poly == 3 ? k3 : k2;
+  GD_CHECK_CUDA(launch_pdl(kern, grid, dim3(kTcThreads), kSmemBytes, stream, map,
                            reinterpret_cast<__half*>(out), ld_out, lse, t, t_valid, heads, order));
   count_launch(1);
   return 0;

@@ -43,6 +43,7 @@ void set_error(const char* fmt, ...);
 // the step gets SLOWER with the attribute on -- 166.6 -> 169.8 ms at batch 64, 22.0 -> 22.4 ms at batch 8 -- so it is
 // OFF by default; GD_B200_PDL=1 (or gd_debug_set(6, 1)) turns it on.  Without the attribute griddepcontrol.* are no-ops.
 bool pdl_enabled();
+bool pdl_small_enabled();
 // Function attributes (opt-in dynamic shared memory) are per DEVICE: true the first time this call site runs on the
 // current device (one process may drive several GPUs), false afterwards.  `seen` is a zero-initialised static bitmap.
 inline bool first_use_on_device(unsigned long long (&seen)[2]) {
@@ -64,8 +65,8 @@ __device__ __forceinline__ void pdl_enter() {
 }
 
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
-                              Args... args) {
+inline cudaError_t launch_pdl_if(bool enabled, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                 cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -73,10 +74,21 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  attr[0].val.programmaticStreamSerializationAllowed = enabled ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args... args) {
+  return launch_pdl_if(pdl_enabled(), kernel, grid, block, smem, st, args...);
+}
+// tiny kernels between two convolutions (see pdl_small_enabled)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl_small(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                    Args... args) {
+  return launch_pdl_if(pdl_small_enabled(), kernel, grid, block, smem, st, args...);
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -646,11 +646,11 @@ extern "C" int gd_groupnorm_finalize_partials(const float* p0, int32_t c0, int32
   GD_REQUIRE(ld0 >= c0 / 4 && (p1 == nullptr || ld1 >= c1 / 4), "gd_groupnorm_finalize_partials: bad leading dimension");
   const double inv_count = 1.0 / (static_cast<double>(hw) * static_cast<double>(c / kGroups));
   if (rows_per_image >= 128)
-    GD_CHECK_CUDA(launch_pdl(gn_finalize_partials_kernel<4>, dim3(kGroups * n), dim3(128), 0,
+    GD_CHECK_CUDA(launch_pdl_small(gn_finalize_partials_kernel<4>, dim3(kGroups * n), dim3(128), 0,
                              reinterpret_cast<cudaStream_t>(stream), p0, c0, ld0, p1, c1, ld1, rows_per_image, n,
                              inv_count, eps, mean_rstd, gamma, beta, film, film_ld, coef_out));
   else
-    GD_CHECK_CUDA(launch_pdl(gn_finalize_partials_kernel<1>, dim3((kGroups * n + 3) / 4), dim3(128), 0,
+    GD_CHECK_CUDA(launch_pdl_small(gn_finalize_partials_kernel<1>, dim3((kGroups * n + 3) / 4), dim3(128), 0,
                              reinterpret_cast<cudaStream_t>(stream), p0, c0, ld0, p1, c1, ld1, rows_per_image, n,
                              inv_count, eps, mean_rstd, gamma, beta, film, film_ld, coef_out));
   count_launch(1);
@@ -662,7 +662,7 @@ extern "C" int gd_groupnorm_coef(const float* mean_rstd, const float* gamma, con
   GD_REQUIRE(mean_rstd && gamma && beta && coef_out && n > 0, "gd_groupnorm_coef: bad arguments");
   GD_REQUIRE(c > 0 && c % 32 == 0 && (film == nullptr || film_ld >= 2 * c), "gd_groupnorm_coef: bad channel count %d / film stride %d",
              c, film_ld);
-  GD_CHECK_CUDA(launch_pdl(gn_coef_kernel, dim3((n * c + 255) / 256), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
+  GD_CHECK_CUDA(launch_pdl_small(gn_coef_kernel, dim3((n * c + 255) / 256), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
                            mean_rstd, gamma, beta, film, film_ld, n, c, coef_out));
   count_launch(1);
   return 0;
@@ -691,7 +691,7 @@ extern "C" int gd_groupnorm_stats(const void* x, int32_t ld, int32_t n, int32_t 
   GD_CHECK_CUDA(launch_pdl(gn_stats_kernel, dim3(g.chunks, n), dim3(g.threads), g.threads * 16 * sizeof(float), st,
                            reinterpret_cast<const __half*>(x), ld, hw, c, g.c8, g.rep, g.px_per_chunk, partial_ws));
   const float inv_count = 1.0f / (static_cast<float>(hw) * static_cast<float>(c / kGroups));
-  GD_CHECK_CUDA(launch_pdl(gn_finalize_kernel, dim3(n), dim3(kGroups), 0, st, partial_ws, g.chunks, inv_count, eps, 0,
+  GD_CHECK_CUDA(launch_pdl_small(gn_finalize_kernel, dim3(n), dim3(kGroups), 0, st, partial_ws, g.chunks, inv_count, eps, 0,
                            mean_rstd));
   count_launch(2);
   return 0;
@@ -758,7 +758,7 @@ extern "C" int gd_groupnorm_bwd(const void* x, int32_t ld, const float* mean_rst
                  reinterpret_cast<const __half*>(dy), ld_dy, h, w, c, g.c8, g.rep, g.px_per_chunk, partial_ws);
   GD_CHECK_CUDA(cudaGetLastError());
   const float inv_count = 1.0f / (static_cast<float>(h * w) * static_cast<float>(c / kGroups));
-  GD_CHECK_CUDA(launch_pdl(gn_finalize_kernel, dim3(n), dim3(kGroups), 0, st, partial_ws, g.chunks, inv_count, 0.f, 1,
+  GD_CHECK_CUDA(launch_pdl_small(gn_finalize_kernel, dim3(n), dim3(kGroups), 0, st, partial_ws, g.chunks, inv_count, 0.f, 1,
                            gsum));
   GD_GN_DISPATCH(gn_bwd_apply_kernel, silu, spatial_mode,
                  dim3(ga.chunks, n), dim3(ga.threads), 0, st, reinterpret_cast<const __half*>(x), ld, mean_rstd, gamma, beta,

@@ -51,6 +51,12 @@ def main():
             row[name + "_ms"] = round(ms, 4)
             row[name + "_tflops"] = round(flop / ms / 1e9, 1)
         lib.gd_debug_set(5, 1)
+        for k, share in ((0, "0/16"), (1, "4/16"), (2, "6/16"), (3, "8/16")):  # exponentials moved to the FMA pipe
+            lib.gd_debug_set(5, 10 + k)
+            ms = timeit(fn)
+            row[f"poly_{share}_ms"] = round(ms, 4)
+            row[f"poly_{share}_tflops"] = round(flop / ms / 1e9, 1)
+        lib.gd_debug_set(5, 11)
         print(json.dumps(row), flush=True)
 
 
