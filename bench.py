@@ -522,14 +522,18 @@ def run_gpu_arm(args):
     dx = th.empty(shape, device=dev)
     dt = th.empty((B,), dtype=th.int64, device=dev)
 
+    host = [host_x, host_out]
+
     def e2e_step(k):
+        # x_t comes from pinned host memory and x_{t-1} goes back to pinned host memory every step; the two host buffers
+        # swap roles (the result of step k is the input of step k + 1) instead of being copied on the host
+        src, dst = host[k & 1], host[(k + 1) & 1]
         host_t.fill_(T - 1 - (k % T))
-        dx.copy_(host_x, non_blocking=True)
+        dx.copy_(src, non_blocking=True)
         dt.copy_(host_t, non_blocking=True)
         out = diffusion.p_sample(model_fn, dx, dt, cond_fn=cond_fn, model_kwargs=kwargs)
-        host_out.copy_(out["sample"], non_blocking=True)
+        dst.copy_(out["sample"], non_blocking=True)
         th.cuda.current_stream().synchronize()
-        host_x.copy_(host_out)
 
     for k in range(3):
         e2e_step(k)

@@ -267,9 +267,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   uint64_t* tmem_full = empty_b + kMaxB;
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* res_bar = tmem_empty + 2;  // one per epilogue group
-  uint64_t* main_done = res_bar + 2;   // kGn: hand-shakes between the two producers of the activation ring
-  uint64_t* skip_done = main_done + 1;
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(skip_done + 1);
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(res_bar + 2);
   float* s_stat = reinterpret_cast<float*>(smem + kBarrierBytes);  // [2 groups][4 quarters][16] parked GN partial sums
   uint8_t* a_ring = smem + kBarrierBytes + kBiasBytes;
   const int b_rows = kTwo ? (p.bn >> 1) : p.bn;  // weight rows this CTA stages per K block
@@ -324,8 +322,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     }
     mbar_init(&res_bar[0], 1);
     mbar_init(&res_bar[1], 1);
-    mbar_init(main_done, kGnWarps);
-    mbar_init(skip_done, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -371,7 +367,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     const uint16_t mc_mask = static_cast<uint16_t>((1u << rank) | (1u << (rank + 2u)));
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
-    uint32_t hs_phase = 0;
     for (int tile = work0; tile < total_tiles; tile += work_step) {
       const int n_tile = tile % n_tiles;
       const int m_tile = m_tile_of(tile);
@@ -379,15 +374,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       tile_coords(p, m_tile, n0, y0, x0);
       const int b_row0 = n_tile * bn + (kTwo ? static_cast<int>(rank) * b_rows : 0) +
                          (quad ? static_cast<int>(pair_in_cluster) * q_rows : 0);
-      for (int src = 0; src < 2; ++src) {
-        const bool main_src = src == 0;
-        const CUtensorMap* ma = main_src ? &map_a0 : &map_a1;
-        const int nblk = main_src ? kb0_per_tap : nblk1;
-        const int ngrp = main_src ? ngrp0 : 1;
-        const int nt = main_src ? nt0 : 1;
-        const uint32_t a_bytes = (main_src && halo) ? halo_bytes : static_cast<uint32_t>(kATileBytes);
-        for (int cb = 0; cb < nblk; ++cb) {
-          for (int g = 0; g < ngrp; ++g) {
+      // K schedule (shared with the MMA issuer and the transform warps): per 64-channel block of the main operand its
+      // groups (3 kx halo groups, 9 taps, or the single tap of a 1x1), then THIS block's share of the fused 1x1-skip
+      // operand's blocks — the skip operand is spread evenly over the main blocks instead of trailing the tile: a run of
+      // one-tap skip blocks needs 16 KB of activations + 16 KB of weights per 512 tensor cycles (64 B/clk per SM, more
+      // than L2 delivers to 148 SMs), interleaved the stream stays below 48 B/clk (K = 2816: 1 294 -> see DESIGN 4.1.1).
+      for (int cb = 0; cb < kb0_per_tap; ++cb) {
+        const int s_lo = cb * nblk1 / kb0_per_tap, s_hi = (cb + 1) * nblk1 / kb0_per_tap;
+        const int n_items = ngrp0 + (s_hi - s_lo);
+        for (int it = 0; it < n_items; ++it) {
+          const bool main_src = it < ngrp0;
+          const int g = it;                      // main operand: group index
+          const int skb = s_lo + (it - ngrp0);   // skip operand: block index
+          const CUtensorMap* ma = main_src ? &map_a0 : &map_a1;
+          const int nt = main_src ? nt0 : 1;
+          const uint32_t a_bytes = (main_src && halo) ? halo_bytes : static_cast<uint32_t>(kATileBytes);
+          const int a_ch = (main_src ? cb : skb) * kBK;
+          {
             int cx = x0, cy = y0, kcol, kstep = 0;
             if (main_src && halo) {  // group = kx; taps ky = 0..2 -> weight columns (ky*3 + kx)*C0
               cx = x0 + g - 1;
@@ -401,34 +404,28 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
               }
               kcol = g * c0_total + cb * kBK;
             } else {
-              kcol = p.kb0 * kBK + cb * kBK;
+              kcol = p.kb0 * kBK + skb * kBK;
             }
-            // kGn: the transform warps fill the main operand's slots, this warp only the fused 1x1-skip operand's.
-            // Two producers on one ring must not pass each other (a parity wait that falls two phases behind a
-            // barrier returns early and the slot would be overwritten before it was consumed): before its first skip
-            // slot of a tile this warp waits until every transform warp has acquired the tile's last main slot
-            // (main_done), and it announces when it has acquired the tile's last skip slot (skip_done).
-            if (!(kGn && main_src)) {
-              if (kGn && cb == 0) mbar_wait(main_done, hs_phase);
+            // kGn: the transform warps own the WHOLE activation ring — they write the main operand's slots and issue
+            // the TMA loads of the fused 1x1-skip operand's slots themselves, in ring order.  (Two producers taking
+            // turns on one ring can pass each other: a parity wait that falls two phases behind a barrier returns
+            // early and a slot is overwritten before it was consumed.  Hand-shake barriers between this warp and the
+            // transform warps fixed that but tied the transform's look-ahead to this warp's, which the weight ring
+            // keeps at 4 taps.)  This warp then only streams weights.
+            if (!kGn) {
               mbar_wait(&empty_a[sa], pa ^ 1);
               __syncwarp();
               if (elect_one()) {
                 uint8_t* dst = a_ring + sa * a_slot;
                 if (kTwo) {
                   // both CTAs' loads complete on the LEADER's barrier, which expects the bytes of the whole pair
-                  if (lead_cta) {
-                    mbar_arrive_expect_tx(&full_a[sa], 2 * a_bytes);
-                    if (kGn) mbar_arrive_count(&full_a[sa], 2 * kGnWarps - 1);  // stands in for the transform warps
-                  }
-                  tma_load_4d_2sm(dst, ma, full_a0_cluster + static_cast<uint32_t>(sa) * 8u, cb * kBK, cx, cy, n0);
+                  if (lead_cta) mbar_arrive_expect_tx(&full_a[sa], 2 * a_bytes);
+                  tma_load_4d_2sm(dst, ma, full_a0_cluster + static_cast<uint32_t>(sa) * 8u, a_ch, cx, cy, n0);
                 } else {
                   mbar_arrive_expect_tx(&full_a[sa], a_bytes);
-                  if (kGn) mbar_arrive_count(&full_a[sa], kGnWarps - 1);
-                  tma_load_4d(dst, ma, &full_a[sa], cb * kBK, cx, cy, n0);
+                  tma_load_4d(dst, ma, &full_a[sa], a_ch, cx, cy, n0);
                 }
-                if (kGn && cb == nblk - 1) mbar_arrive(skip_done);
               }
-              if (kGn && cb == nblk - 1) hs_phase ^= 1;
             }
             if (++sa == n_a) {
               sa = 0;
@@ -470,8 +467,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       const uint32_t idesc = umma_idesc_f16(kTwo ? 2 * kBM : kBM, static_cast<uint32_t>(p.bn));
       const uint32_t a_ring_u32 = smem_base_u32 + static_cast<uint32_t>(kBarrierBytes + kBiasBytes);
       const uint32_t b_ring_u32 = a_ring_u32 + static_cast<uint32_t>(n_a * a_slot);
-      const int groups_main = kb0_per_tap * ngrp0;
-      const int groups_total = groups_main + nblk1;
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int acc = 0;
@@ -480,8 +475,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
-        for (int grp = 0; grp < groups_total; ++grp) {
-          const int nt = grp < groups_main ? nt0 : 1;
+        // the K schedule of the producer: per main channel block its groups, then its share of the skip blocks
+        for (int cb = 0; cb < kb0_per_tap; ++cb) {
+        const int n_items = ngrp0 + ((cb + 1) * nblk1 / kb0_per_tap - cb * nblk1 / kb0_per_tap);
+        for (int it = 0; it < n_items; ++it) {
+          const int nt = it < ngrp0 ? nt0 : 1;
+          const bool last_item = cb == kb0_per_tap - 1 && it == n_items - 1;
           mbar_wait(&full_a[sa], pa);
           const uint32_t a_base = a_ring_u32 + static_cast<uint32_t>(sa * a_slot);
           for (int t = 0; t < nt; ++t) {
@@ -494,7 +493,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
 #pragma unroll
               for (int k = 0; k < kBK / 16; ++k) {
                 // advance 16 fp16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in (addr >> 4) units
-                const uint32_t accumulate = static_cast<uint32_t>((grp | t | k) != 0);
+                const uint32_t accumulate = static_cast<uint32_t>((cb | it | t | k) != 0);
                 if (kTwo)
                   umma_f16_2sm(d_tmem, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
                                accumulate);
@@ -509,7 +508,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
               if (t == nt - 1) {
                 if (kTwo) umma_commit_2sm(&empty_a[sa], pair_mask);
                 else umma_commit(&empty_a[sa]);
-                if (grp == groups_total - 1) {
+                if (last_item) {
                   if (kTwo) umma_commit_2sm(&tmem_full[acc], pair_mask);
                   else umma_commit(&tmem_full[acc]);
                 }
@@ -524,6 +523,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             sa = 0;
             pa ^= 1;
           }
+        }
         }
         if (++acc == 2) {
           acc = 0;
@@ -581,7 +581,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     const bool has7 = pidx0 + 24 * 7 < kGnHaloW * kGnHaloH;  // only the last iteration can fall off the 180-pixel halo
     int sa = 0;
     uint32_t pa = 0;
-    uint32_t hs_phase = 0;
+    uint8_t* a_ring_ptr = a_ring;
     // Software pipeline at HALF-pass granularity with one set of registers: a lane's 8 chunks form two halves; while
     // half A of channel block cb is normalised and stored, the loads of half B are in flight, and while B is processed
     // the loads of half A of the NEXT channel block (or of the next tile's first block) are in flight — the L2 latency
@@ -589,9 +589,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     uint32_t raw[kGnIters][4];
     constexpr int kHalf = kGnIters / 2;
     // source pointer (this lane's channel chunk of the tile's first pixel), affine table row and validity mask of a tile
-    auto tile_state = [&](int tile, const __half*& img, const float4*& coef, uint32_t& vmask) {
+    auto tile_state = [&](int tile, const __half*& img, const float4*& coef, uint32_t& vmask, int& n0, int& y0,
+                          int& x0) {
       const int m_tile = m_tile_of(tile);
-      int n0, y0, x0;
       tile_coords(p, m_tile, n0, y0, x0);
       const bool img_ok = n0 < p.n_img;  // (a tile count that is not a multiple of the cluster leaves CTAs without a tile)
       const int n_c = img_ok ? n0 : p.n_img - 1;
@@ -656,10 +656,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     const __half* img = p.gn_src;
     const float4* coef = reinterpret_cast<const float4*>(p.gn_coef);
     uint32_t vmask = 0;
+    int t_n0 = 0, t_y0 = 0, t_x0 = 0;  // origin of the current tile (for the skip operand's TMA boxes)
     float4 cn0, cn1, cn2, cn3;  // affine (a[8], b[8]) of the NEXT channel block, prefetched
     cn0 = cn1 = cn2 = cn3 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (work0 < total_tiles) {
-      tile_state(work0, img, coef, vmask);
+      tile_state(work0, img, coef, vmask, t_n0, t_y0, t_x0);
       issue_half(0, img, vmask, 0);
       cn0 = __ldg(coef), cn1 = __ldg(coef + 1), cn2 = __ldg(coef + 2), cn3 = __ldg(coef + 3);
     }
@@ -690,7 +691,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           sa = 0;
           pa ^= 1;
         }
-        if (nblk1 > 0 && cb == kb0_per_tap - 1 && lane == 0) mbar_arrive(main_done);  // last main slot acquired
         const uint32_t slot0 = a_ring_u32 + static_cast<uint32_t>(s0 * a_slot);
         const uint32_t slot1 = a_ring_u32 + static_cast<uint32_t>(s1 * a_slot);
         const uint32_t slot2 = a_ring_u32 + static_cast<uint32_t>(s2 * a_slot);
@@ -699,10 +699,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         const __half* img_n = img;
         const float4* coef_n = coef;
         uint32_t vmask_n = vmask;
+        int n0_n = t_n0, y0_n = t_y0, x0_n = t_x0;
         int cb_n = cb + 1;
         if (cb_n == kb0_per_tap) {
           cb_n = 0;
-          if (tile + work_step < total_tiles) tile_state(tile + work_step, img_n, coef_n, vmask_n);
+          if (tile + work_step < total_tiles) tile_state(tile + work_step, img_n, coef_n, vmask_n, n0_n, y0_n, x0_n);
           else vmask_n = 0;  // nothing left: no loads (the table row stays a valid address)
         }
         issue_half(0, img_n, vmask_n, cb_n);
@@ -724,22 +725,40 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             mbar_arrive(&full_a[s2]);
           }
         }
-        img = img_n;
-        coef = coef_n;
-        vmask = vmask_n;
-      }
-      // The fused 1x1-skip operand's slots are filled by the TMA producer.  Two producers on one ring must not pass
-      // each other (a parity wait that falls two phases behind a barrier returns early): this side announces that it
-      // has acquired the tile's last main slot (main_done, see above) and, before touching the next tile's slots, waits
-      // until the TMA producer has acquired this tile's last skip slot (skip_done).
-      if (nblk1 > 0) {
-        for (int s1 = 0; s1 < nblk1; ++s1)
+        // This block's share of the fused 1x1-skip operand (raw, one tap per block): plain TMA boxes into the next ring
+        // slots, issued by the first transform warp in ring order — the transform warps are the ring's only producer.
+        const int s_lo = cb * nblk1 / kb0_per_tap, s_hi = (cb + 1) * nblk1 / kb0_per_tap;
+        for (int skb = s_lo; skb < s_hi; ++skb) {
+          if (tw == 0) {
+            mbar_wait(&empty_a[sa], pa ^ 1);
+            __syncwarp();
+            if (elect_one()) {
+              uint8_t* dst = a_ring_ptr + sa * a_slot;
+              if (kTwo) {
+                // both CTAs' boxes complete on the pair leader's barrier; its other arrivals stand in for the warps
+                if (lead_cta) {
+                  mbar_arrive_expect_tx(&full_a[sa], 2 * kATileBytes);
+                  mbar_arrive_count(&full_a[sa], 2 * kGnWarps - 1);
+                }
+                tma_load_4d_2sm(dst, &map_a1, full_a0_cluster + static_cast<uint32_t>(sa) * 8u, skb * kBK, t_x0, t_y0, t_n0);
+              } else {
+                mbar_arrive_expect_tx(&full_a[sa], kATileBytes);
+                mbar_arrive_count(&full_a[sa], kGnWarps - 1);
+                tma_load_4d(dst, &map_a1, &full_a[sa], skb * kBK, t_x0, t_y0, t_n0);
+              }
+            }
+          }
           if (++sa == n_a) {
             sa = 0;
             pa ^= 1;
           }
-        mbar_wait(skip_done, hs_phase);
-        hs_phase ^= 1;
+        }
+        img = img_n;
+        coef = coef_n;
+        vmask = vmask_n;
+        t_n0 = n0_n;
+        t_y0 = y0_n;
+        t_x0 = x0_n;
       }
     }
   }
