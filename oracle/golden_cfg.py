@@ -359,6 +359,17 @@ def fullsize_noise(name: str):
     return th.randn(1, 3, c["image"], c["image"])
 
 
+FS_TRAJ_STEPS = 10  # first reverse steps of the 250-step guided chain of configs[1] at FULL size (batch 1)
+
+
+def fullsize_traj_noise():
+    """The CPU-generator draws of the reference loop for the full-size trajectory: randn(shape), then one randn_like per
+    step (gaussian_diffusion.py:516, 430)."""
+    th.manual_seed(FS_SEED + 30)
+    shape = (1, 3, 256, 256)
+    return th.randn(*shape), [th.randn(*shape) for _ in range(FS_TRAJ_STEPS)]
+
+
 def fs_pack(a):
     """fixture storage: fp16 mantissa at a per-array power-of-two scale (5e-4 relative, far inside the 2e-2 budget)."""
     import numpy as np

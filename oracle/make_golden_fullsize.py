@@ -131,7 +131,44 @@ def run_case(name):
           flush=True)
 
 
+def run_traj():
+    """north_star: "short 10-step trajectories must match within the same stated bound" — at the REAL widths: the first
+    10 reverse steps of the 250-step classifier-guided chain of configs[1] through the reference's own
+    p_sample_loop_progressive (batch 1, fp32, CPU-generator noise), recording x after 5 and 10 steps."""
+    t0 = time.time()
+    unet, clf, _ = build_models("cfg2")
+    c = cfg.FULLSIZE_CASES["cfg2"]
+    d = rsu.create_gaussian_diffusion(**c["diffusion"])
+    y = th.tensor([c["label"]])
+
+    def model_fn(x_, t_, y=None):
+        return unet(x_, t_, y)
+
+    def cond_fn(x_, t_, y=None):
+        with th.enable_grad():
+            x_in = x_.detach().requires_grad_(True)
+            log_probs = F.log_softmax(clf(x_in, t_), dim=-1)
+            return th.autograd.grad(log_probs[range(len(x_in)), y.view(-1)].sum(), x_in)[0] * c["scale"]
+
+    th.manual_seed(cfg.FS_SEED + 30)
+    out = {}
+    gen = d.p_sample_loop_progressive(model_fn, (1, 3, 256, 256), model_kwargs={"y": y}, cond_fn=cond_fn, device="cpu",
+                                      denoise_start_point=-1)
+    for k, o in enumerate(gen):
+        if k + 1 in (5, cfg.FS_TRAJ_STEPS):
+            out[f"sample{k + 1}"], out[f"sample{k + 1}_exp"] = cfg.fs_pack(o["sample"].numpy())
+        if k + 1 == cfg.FS_TRAJ_STEPS:
+            break
+    path = os.path.join(OUT, "fullsize_traj_cfg2.npz")
+    np.savez_compressed(path, **out)
+    print(f"traj cfg2: {time.time() - t0:.1f} s, {os.path.getsize(path) / 1e6:.2f} MB", flush=True)
+
+
 if __name__ == "__main__":
     th.set_num_threads(os.cpu_count())
-    for nm in (sys.argv[1:] or list(cfg.FULLSIZE_CASES)):
-        run_case(nm)
+    names = sys.argv[1:] or (list(cfg.FULLSIZE_CASES) + ["traj"])
+    for nm in names:
+        if nm == "traj":
+            run_traj()
+        else:
+            run_case(nm)

@@ -133,3 +133,35 @@ def test_oracle_matches_reference_at_full_size_cfg2(golden_dir):
     e1, e2 = H.rel_err(eps, G["eps"]), H.rel_err(grad, G["grad"])
     print(f"oracle vs reference at full size: eps {e1:.3e} grad {e2:.3e}")
     assert e1 < 2e-3 and e2 < 2e-3  # fp32 vs fp32; the fixture is stored with an fp16 mantissa (5e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("graph", ["1", "0"])
+def test_fullsize_ten_step_guided_trajectory_matches_reference(lib, golden_dir, monkeypatch, graph):
+    """north_star: "short 10-step trajectories must match within the same stated bound" — here at the REAL widths of
+    configs[1]: the first 10 reverse steps of the 250-step classifier-guided chain (UNet-256 + classifier-256, batch 1)
+    against the reference's own p_sample_loop_progressive (fixture fullsize_traj_cfg2.npz), the reference's
+    CPU-generator noise replayed step by step; graphed (one CUDA-graph replay per step) and eager launch paths."""
+    monkeypatch.setenv("GD_B200_NO_GRAPH", "0" if graph == "1" else "1")
+    dev = th.device("cuda", 0)
+    z = np.load(os.path.join(golden_dir, "fullsize_traj_cfg2.npz"))
+    ref = {k: th.from_numpy(cfg.fs_unpack(z[k], z[k + "_exp"])).to(dev) for k in ("sample5", "sample10")}
+    model, d, cond = _build("cfg2", dev)
+    c = cfg.FULLSIZE_CASES["cfg2"]
+    y = th.tensor([c["label"]], device=dev)
+    init, zs = cfg.fullsize_traj_noise()
+    mf = ModelFn(model, True)
+    img = init.to(dev)
+    errs = {}
+    with th.no_grad():
+        for k in range(cfg.FS_TRAJ_STEPS):
+            t = th.full((1,), d.num_timesteps - 1 - k, dtype=th.int64, device=dev)
+            img = d._sample_step(mf, img, t, True, None, cond, {"y": y}, False, 0.0, noise=zs[k].to(dev))["sample"]
+            if k + 1 in (5, 10):
+                errs[k + 1] = H.rel_err(img, ref[f"sample{k + 1}"])
+    print(f"FULLSIZE 10-step guided trajectory (graph={graph}): after 5 steps {errs[5]:.3e}, after 10 steps {errs[10]:.3e}")
+    gp = os.path.join(os.path.dirname(golden_dir), "..", "gpurun_out")
+    if os.path.isdir(gp):
+        with open(os.path.join(gp, "fullsize_parity.txt"), "a") as f:
+            f.write(f"traj_cfg2 graph={graph} step5={errs[5]:.3e} step10={errs[10]:.3e}\n")
+    assert max(errs.values()) < TOL
