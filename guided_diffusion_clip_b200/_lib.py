@@ -37,6 +37,7 @@ class ConvDesc(C.Structure):
         ("bn", i32), ("out_scale", f32),
         ("stats_out", vp),
         ("gn_mode", i32), ("gn_silu", i32), ("gn_coef", vp),
+        ("splitk_ws", vp), ("splitk_ws_bytes", i64),
     ]
 
 
@@ -67,6 +68,7 @@ SIGNATURES = {
     "gd_conv_igemm": (C.c_int, [C.POINTER(ConvDesc), vp]),
     "gd_conv_stats_rows": (i64, [i32, i32, i32, C.POINTER(i32)]),
     "gd_conv_gn_fusable": (C.c_int, [i32, i32]),
+    "gd_conv_splitk_ws_bytes": (i64, [C.POINTER(ConvDesc)]),
     "gd_groupnorm_finalize_partials": (C.c_int, [vp, i32, i32, vp, i32, i32, i32, i32, i32, f32, vp, vp, vp, vp, i32, vp,
                                                  vp]),
     "gd_groupnorm_coef": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, vp, vp]),

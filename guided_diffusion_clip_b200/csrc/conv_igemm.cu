@@ -92,6 +92,12 @@ struct ConvArgs {
   const __half* gn_src1;  // a1 (fused 1x1-skip operand), read by the same warps
   int gn_ld1;
   const float* gn_coef;  // [n][c0/8][16]: a[8], b[8] per 8-channel chunk
+  // split-K (few pixel tiles, long K: the 8x8 / 16x16 layers at small batch): work item = (pixel unit, n tile, split);
+  // split s accumulates main channel blocks [s*cb_split, (s+1)*cb_split) (with their share of the skip operand) and
+  // stores its raw fp32 accumulators to ws[s][m_tiles*128][ws_ld]; conv_splitk_reduce_kernel finishes the epilogue
+  int ksplit, cb_split;
+  float* ws;
+  int ws_ld;
 };
 
 __device__ __forceinline__ void tile_coords(const ConvArgs& p, int m_tile, int& n0, int& y0, int& x0) {
@@ -290,14 +296,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   // work items: (pixel tile | pixel-tile pair | two pixel-tile pairs, n tile); all CTAs of a cluster walk the same list
   const int m_per = kTwo ? (quad ? 4 : 2) : 1;
   const int m_units = (p.m_tiles + m_per - 1) / m_per;
-  const int total_tiles = m_units * p.n_tiles;
+  const int mn_tiles = m_units * p.n_tiles;
+  const int total_tiles = mn_tiles * p.ksplit;  // split-K: the split index is the slowest digit of the work item
   const int work0 = static_cast<int>(blockIdx.x) / m_per;
   const int work_step = static_cast<int>(gridDim.x) / m_per;
   // pixel tile of this CTA inside work item `tile`
   auto m_tile_of = [&](int tile) {
-    return kTwo ? m_per * (tile / p.n_tiles) + 2 * static_cast<int>(pair_in_cluster) + static_cast<int>(rank)
-                : tile / p.n_tiles;
+    const int unit = (tile / p.n_tiles) % m_units;
+    return kTwo ? m_per * unit + 2 * static_cast<int>(pair_in_cluster) + static_cast<int>(rank) : unit;
   };
+  const int cb_split = p.cb_split;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a0);
@@ -379,7 +387,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       // operand's blocks — the skip operand is spread evenly over the main blocks instead of trailing the tile: a run of
       // one-tap skip blocks needs 16 KB of activations + 16 KB of weights per 512 tensor cycles (64 B/clk per SM, more
       // than L2 delivers to 148 SMs), interleaved the stream stays below 48 B/clk (K = 2816: 1 294 -> see DESIGN 4.1.1).
-      for (int cb = 0; cb < kb0_per_tap; ++cb) {
+      const int cb_lo = (tile / mn_tiles) * cb_split;
+      const int cb_hi = cb_lo + cb_split < kb0_per_tap ? cb_lo + cb_split : kb0_per_tap;
+      for (int cb = cb_lo; cb < cb_hi; ++cb) {
         const int s_lo = cb * nblk1 / kb0_per_tap, s_hi = (cb + 1) * nblk1 / kb0_per_tap;
         const int n_items = ngrp0 + (s_hi - s_lo);
         for (int it = 0; it < n_items; ++it) {
@@ -476,11 +486,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
         // the K schedule of the producer: per main channel block its groups, then its share of the skip blocks
-        for (int cb = 0; cb < kb0_per_tap; ++cb) {
+        const int cb_lo = (tile / mn_tiles) * cb_split;
+        const int cb_hi = cb_lo + cb_split < kb0_per_tap ? cb_lo + cb_split : kb0_per_tap;
+        for (int cb = cb_lo; cb < cb_hi; ++cb) {
         const int n_items = ngrp0 + ((cb + 1) * nblk1 / kb0_per_tap - cb * nblk1 / kb0_per_tap);
         for (int it = 0; it < n_items; ++it) {
           const int nt = it < ngrp0 ? nt0 : 1;
-          const bool last_item = cb == kb0_per_tap - 1 && it == n_items - 1;
+          const bool last_item = cb == cb_hi - 1 && it == n_items - 1;
           mbar_wait(&full_a[sa], pa);
           const uint32_t a_base = a_ring_u32 + static_cast<uint32_t>(sa * a_slot);
           for (int t = 0; t < nt; ++t) {
@@ -493,7 +505,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
 #pragma unroll
               for (int k = 0; k < kBK / 16; ++k) {
                 // advance 16 fp16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in (addr >> 4) units
-                const uint32_t accumulate = static_cast<uint32_t>((cb | it | t | k) != 0);
+                const uint32_t accumulate = static_cast<uint32_t>(((cb - cb_lo) | it | t | k) != 0);
                 if (kTwo)
                   umma_f16_2sm(d_tmem, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
                                accumulate);
@@ -823,6 +835,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
 
       if (p.debug == 1) {
         // timing experiment: no epilogue work at all
+      } else if (p.ksplit > 1) {
+        // split-K: raw fp32 accumulators -> this split's slab of the workspace (row = pixel-tile row, 128 B per thread
+        // and sub-tile: whole sectors); bias, residual, fp16 rounding and statistics happen in the reduce kernel
+        float* wrow = p.ws + (static_cast<size_t>((tile / mn_tiles) * p.m_tiles + m_tile) * kBM + row) * p.ws_ld + col_base;
+        for (int j = group; j < nsub; j += 2) {
+          uint32_t v[32];
+          tmem_ld_x32(t_row + static_cast<uint32_t>(j * 32), v);
+          tmem_ld_wait();
+          if (m_tile < p.m_tiles) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<float4*>(wrow + j * 32 + 4 * q) =
+                  make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                              __uint_as_float(v[4 * q + 3]));
+          }
+        }
       } else if (!p.tma_epi) {
         for (int j = group; j < nsub; j += 2)
           epi_chunk_direct<32>(p, t_row + static_cast<uint32_t>(j * 32), col_base + j * 32, e);
@@ -964,6 +992,77 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   }
 }
 
+// Second half of a split-K convolution: out = fp16(sum over splits of the fp32 partial accumulators + bias (+ residual))
+// and, where the conv was asked for them, the GroupNorm partial sums in exactly the row layout the fused epilogue emits
+// (one row per 32-pixel quarter, or one per 128-pixel tile when the tile lies inside one image), taken from the fp32
+// values like epi_compute32.  grid = (row blocks, 64-channel slabs), 8 warps: warp = 8-channel chunk, lane = pixel row.
+// Fixed summation order (splits ascending, butterfly over lanes, quarters ascending) -> bitwise reproducible.
+__global__ void __launch_bounds__(256) conv_splitk_reduce_kernel(const ConvArgs p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nq = p.stats_per_tile == 1 ? 4 : 1;  // quarters handled by one block
+  const int m_tile = nq == 4 ? static_cast<int>(blockIdx.x) : static_cast<int>(blockIdx.x >> 2);
+  const int q0 = nq == 4 ? 0 : static_cast<int>(blockIdx.x & 3);
+  const int col = static_cast<int>(blockIdx.y) * 64 + warp * 8;
+  int n0, y0, x0;
+  tile_coords(p, m_tile, n0, y0, x0);
+  const int patch_px = p.bh * p.bw;
+  const size_t split_stride = static_cast<size_t>(p.m_tiles) * kBM * p.ws_ld;
+  float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+  if (p.bias != nullptr) {
+    b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+    b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col) + 1);
+  }
+  float cs[4] = {0.f, 0.f, 0.f, 0.f};  // sums of the two 4-channel chunks, then their sums of squares
+  for (int qi = 0; qi < nq; ++qi) {
+    const int row = (q0 + qi) * 32 + lane;
+    const int i_local = row / patch_px;
+    const int rem = row - i_local * patch_px;
+    const int y_local = rem / p.bw;
+    const int img = n0 + i_local, y = y0 + y_local, x = x0 + (rem - y_local * p.bw);
+    const bool valid = img < p.n_img && y < p.h && x < p.w;
+    const float* wp = p.ws + (static_cast<size_t>(m_tile) * kBM + row) * p.ws_ld + col;
+    float4 a0 = b0, a1 = b1;
+    for (int s = 0; s < p.ksplit; ++s) {
+      const float4 u0 = *reinterpret_cast<const float4*>(wp + s * split_stride);
+      const float4 u1 = *reinterpret_cast<const float4*>(wp + s * split_stride + 4);
+      a0.x += u0.x; a0.y += u0.y; a0.z += u0.z; a0.w += u0.w;
+      a1.x += u1.x; a1.y += u1.y; a1.z += u1.z; a1.w += u1.w;
+    }
+    float f[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    float qs[4] = {0.f, 0.f, 0.f, 0.f};
+    if (valid) {
+      const size_t pix = (static_cast<size_t>(img) * p.h + y) * p.w + x;
+      if (p.res_mode == GD_RES_SAME) {
+        float t[8];
+        half8_to_float(ld_half8(p.res + pix * p.ld_res + col), t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += t[j];
+      }
+      st_half8(reinterpret_cast<__half*>(p.out) + pix * p.ld_out + col, float_to_half8(f));
+      qs[0] = (f[0] + f[1]) + (f[2] + f[3]);
+      qs[1] = (f[4] + f[5]) + (f[6] + f[7]);
+      qs[2] = fmaf(f[3], f[3], fmaf(f[2], f[2], fmaf(f[1], f[1], f[0] * f[0])));
+      qs[3] = fmaf(f[7], f[7], fmaf(f[6], f[6], fmaf(f[5], f[5], f[4] * f[4])));
+    }
+    if (p.stats != nullptr) {
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) qs[i] += __shfl_xor_sync(0xffffffffu, qs[i], off);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) cs[i] += qs[i];
+    }
+  }
+  if (p.stats != nullptr && lane < 4) {
+    const int prow = nq == 4 ? m_tile : m_tile * 4 + q0;
+    float* sp = p.stats + static_cast<size_t>(prow) * p.stats_ld * 2;
+    // lane 0/1: sums of chunk 0/1, lane 2/3: their sums of squares
+    const float val = lane == 0 ? cs[0] : (lane == 1 ? cs[1] : (lane == 2 ? cs[2] : cs[3]));
+    sp[((col >> 2) + (lane & 1)) * 2 + (lane >> 1)] = val;
+  }
+}
+
 // --------------------------------------------------------------------------------------------
 // host side
 // --------------------------------------------------------------------------------------------
@@ -1079,7 +1178,67 @@ bool patch_shape(int h, int w, int& bw, int& bh, int& bi) {
   return bi >= 1 && bi <= 256 && bw * bh * bi == 128;
 }
 
+// split-K applies to 3x3 convs with the aligned fp16 NHWC output whose (pixel unit, n tile) work items leave at least
+// half of the GPU idle; the caller lends a workspace (gd_conv_desc.splitk_ws)
+int g_splitk_mode = -1;  // -1: read GD_B200_SPLITK (default on)
+// SMs a persistent conv grid leaves free (GD_B200_CONV_SM_RESERVE): a conv CTA owns its SM outright (all shared memory,
+// kGn: all registers), so while a full-width conv runs nothing of another stream can start.  In a guided step the
+// classifier and the UNet are two branches of one graph; a few free SMs let one branch's latency-bound small kernels
+// proceed under the other's long convolutions.
+int g_sm_reserve = -1;
+int conv_sms() {
+  if (g_sm_reserve < 0) {
+    const char* e = getenv("GD_B200_CONV_SM_RESERVE");
+    g_sm_reserve = e != nullptr ? atoi(e) : 0;
+    if (g_sm_reserve < 0 || g_sm_reserve > g_num_sms / 2) g_sm_reserve = 0;
+  }
+  return g_num_sms - g_sm_reserve;
+}
+bool splitk_static_ok(const gd_conv_desc* d) {
+  if (g_splitk_mode < 0) {
+    const char* e = getenv("GD_B200_SPLITK");
+    g_splitk_mode = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return g_splitk_mode != 0 && d->gn_mode == GD_CONV_GN_OFF && d->taps == 9 && d->c0 >= 128 &&
+         d->out_mode == GD_OUT_NHWC_F16 && d->cout % 64 == 0 && d->n_pad == d->cout && d->ld_out % 8 == 0 &&
+         reinterpret_cast<uintptr_t>(d->out) % 16 == 0 && (d->out_scale == 1.0f || d->out_scale == 0.0f) &&
+         (d->res_mode == GD_RES_NONE ||
+          (d->res_mode == GD_RES_SAME && d->ld_res % 8 == 0 && reinterpret_cast<uintptr_t>(d->res) % 16 == 0)) &&
+         reinterpret_cast<uintptr_t>(d->bias) % 16 == 0;
+}
+// number of splits for `items` work items on `slots` CTA (pair) slots, at most kmax
+int splitk_pick(int items, int slots, int kb0_per_tap, long long per_split_bytes, long long ws_bytes) {
+  int ks = items > 0 ? slots / items : 1;
+  if (ks > 8) ks = 8;
+  if (ks > kb0_per_tap) ks = kb0_per_tap;
+  if (per_split_bytes > 0 && ks > ws_bytes / per_split_bytes) ks = static_cast<int>(ws_bytes / per_split_bytes);
+  if (ks < 2) return 1;
+  const int cbs = (kb0_per_tap + ks - 1) / ks;
+  return (kb0_per_tap + cbs - 1) / cbs;  // no empty split
+}
+
 }  // namespace gd
+
+extern "C" int64_t gd_conv_splitk_ws_bytes(const gd_conv_desc* d) {
+  using namespace gd;
+  if (d == nullptr || d->n <= 0 || d->h <= 0 || d->w <= 0 || d->c0 <= 0 || !splitk_static_ok(d)) return 0;
+  int bw, bh, bi;
+  if (!patch_shape(d->h, d->w, bw, bh, bi)) return 0;
+  if (g_num_sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      return 0;
+  }
+  const int m_tiles = ((d->w + bw - 1) / bw) * ((d->h + bh - 1) / bh) * ((d->n + bi - 1) / bi);
+  const bool two = m_tiles >= 2;
+  const int units = two ? (m_tiles + 1) / 2 : m_tiles;
+  const int slots = two ? g_num_sms / 2 : g_num_sms;
+  const long long per_split = static_cast<long long>(m_tiles) * kBM * d->n_pad * 4;
+  // upper bound over the N tilings the launch may choose (at least one n tile)
+  const int ks = splitk_pick(units, slots, d->c0 / 64, per_split, 1ll << 62);
+  return ks >= 2 ? ks * per_split : 0;
+}
 
 extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
   using namespace gd;
@@ -1254,6 +1413,28 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
   p.gn_src1 = reinterpret_cast<const __half*>(d->a1);
   p.gn_ld1 = d->a1 ? d->ld1 : 0;
   p.gn_coef = d->gn_coef;
+  p.ksplit = 1;
+  p.cb_split = p.kb0_per_tap;
+  p.ws = nullptr;
+  p.ws_ld = d->n_pad;
+  ConvArgs p_reduce;
+  if (d->splitk_ws != nullptr && d->splitk_ws_bytes > 0 && bn % 32 == 0 && g_debug_epilogue == 0 &&
+      reinterpret_cast<uintptr_t>(d->splitk_ws) % 16 == 0 && splitk_static_ok(d)) {
+    const int units = two_cta ? (m_tiles + 1) / 2 : m_tiles;
+    const long long per_split = static_cast<long long>(m_tiles) * kBM * d->n_pad * 4;
+    const int ks = splitk_pick(units * p.n_tiles, two_cta ? g_num_sms / 2 : g_num_sms, p.kb0_per_tap, per_split,
+                               d->splitk_ws_bytes);
+    if (ks >= 2) {
+      p.ksplit = ks;
+      p.cb_split = (p.kb0_per_tap + ks - 1) / ks;
+      p.ws = reinterpret_cast<float*>(d->splitk_ws);
+      p_reduce = p;  // the reduce kernel finishes the epilogue: bias, residual, fp16 output, statistics
+      p.tma_epi = 0;
+      p.stats = nullptr;
+      p.bias = nullptr;
+      p.res_mode = GD_RES_NONE;
+    }
+  }
 
   CUtensorMap ma0, ma1, mb, mout, mres;
   // (a fused-GroupNorm operand is read with plain loads; its tensor map is only a placeholder, encoded over the source
@@ -1273,7 +1454,7 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
   // quarter of the weight tile and multicasts it to the other pair, which halves the L2 -> SM weight stream (the
   // largest operand stream of the mainloop: 590 KB of weights against 245 KB of activations per 128 x 256 tile).
   // Needs whole 8-row swizzle groups per quarter and at least one work item per cluster slot to be worth the lock-step.
-  const bool quad = two_cta && g_quad_mode != 0 && (bn / 4) % 8 == 0 && m_tiles >= 8 &&
+  const bool quad = two_cta && p.ksplit == 1 && g_quad_mode != 0 && (bn / 4) % 8 == 0 && m_tiles >= 8 &&
                     ((m_tiles + 3) / 4) * (d->n_pad / bn) >= g_num_sms / 8;
   p.quad = quad ? 1 : 0;
   rc = encode_weight_map(&mb, d->wpack, k_total, d->n_pad, quad ? bn / 4 : (two_cta ? bn / 2 : bn));
@@ -1311,8 +1492,8 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
   if (two_cta) {
     // one cluster of 2 (or 4) CTAs per pixel-tile pair (or two pairs); persistent over (m unit, n tile) work items
     const int csize = quad ? 4 : 2;
-    const int items = ((p.m_tiles + csize - 1) / csize) * p.n_tiles;
-    int max_clusters = g_num_sms / csize;
+    const int items = ((p.m_tiles + csize - 1) / csize) * p.n_tiles * p.ksplit;
+    int max_clusters = conv_sms() / csize;
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem_bytes;
@@ -1348,8 +1529,8 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
     if (gn) GD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true, true>, ma0, ma1, mb, mout, mres, p));
     else GD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true, false>, ma0, ma1, mb, mout, mres, p));
   } else {
-    const int total_tiles = p.m_tiles * p.n_tiles;
-    const int grid = total_tiles < g_num_sms ? total_tiles : g_num_sms;
+    const int total_tiles = p.m_tiles * p.n_tiles * p.ksplit;
+    const int grid = total_tiles < conv_sms() ? total_tiles : conv_sms();
     if (gn)
       GD_CHECK_CUDA(launch_pdl(conv_igemm_kernel<false, true>, dim3(grid), dim3(threads), smem_bytes,
                                reinterpret_cast<cudaStream_t>(stream), ma0, ma1, mb, mout, mres, p));
@@ -1359,6 +1540,13 @@ extern "C" int gd_conv_igemm(const gd_conv_desc* d, void* stream) {
   }
   GD_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
+  if (p.ksplit > 1) {
+    const dim3 rgrid(static_cast<unsigned>(p.m_tiles * (p_reduce.stats_per_tile == 1 ? 1 : 4)),
+                     static_cast<unsigned>(d->cout / 64));
+    conv_splitk_reduce_kernel<<<rgrid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p_reduce);
+    GD_CHECK_CUDA(cudaGetLastError());
+    count_launch(1);
+  }
   return 0;
 }
 

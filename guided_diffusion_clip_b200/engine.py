@@ -79,6 +79,7 @@ class Program:
         self.calls: List[Tuple[object, tuple, str]] = []
         self.keep: List[object] = []
         self.device = device
+        self._measured: Optional[int] = None  # kernels launched by one run (counted by the library on the first run)
 
     def add(self, name: str, *args) -> None:
         fn = getattr(L.load(), name)
@@ -101,13 +102,18 @@ class Program:
                 except Exception as e:  # noqa: BLE001
                     raise L.GdError(f"launch #{i} {name} faulted: {e}") from e
             return
+        before = int(L.load().gd_launch_count()) if self._measured is None else 0
         for fn, args, name in self.calls:
             rc = fn(*args, stream)
             if rc != 0:
                 L.check(rc, name)
+        if self._measured is None:
+            self._measured = int(L.load().gd_launch_count()) - before
 
     @property
     def launches(self) -> int:
+        if self._measured is not None:  # exact (a split-K conv is two launches, decided at launch time)
+            return self._measured
         per = {"gd_groupnorm_stats": 2, "gd_groupnorm_bwd": 3, "gd_attention_bwd": 3, "gd_attnpool_fwd": 6,
                "gd_attnpool_bwd": 4}
         return sum(per.get(name, 1) for _, _, name in self.calls)
@@ -195,6 +201,7 @@ class Emitter:
         self._gn_ws_floats = 0
         self._producers: Dict[tuple, tuple] = {}   # (buffer ptr, channel offset, C) -> (ConvDesc, n, h, w)
         self._stats_bufs: Dict[int, th.Tensor] = {}  # id(ConvDesc) -> fused GroupNorm partials of that conv
+        self._splitk_ws: Optional[th.Tensor] = None  # split-K workspace shared by the plan's (serialised) convs
 
     # ---- buffers ------------------------------------------------------------------------------
     def scratch(self, role: str, n, h, w, c) -> View:
@@ -268,6 +275,14 @@ class Emitter:
             d.gn_mode, d.gn_silu = gn["mode"], int(gn.get("silu", True))
             d.gn_coef = gn["coef"].data_ptr()
             self.keep.append(gn["coef"])
+        need = int(L.load().gd_conv_splitk_ws_bytes(C.byref(d))) if os.environ.get("GD_B200_SPLITK", "1") != "0" else 0
+        if need > 0:
+            # few pixel tiles, long K (8x8 / 16x16 layers at small batch): lend the launch a workspace to split K over
+            # the idle SMs.  One workspace per plan: its launches are serialised on one stream.
+            if self._splitk_ws is None or self._splitk_ws.numel() * 4 < need:
+                self._splitk_ws = th.empty((need + 3) // 4, dtype=th.float32, device=self.device)
+            self.keep.append(self._splitk_ws)
+            d.splitk_ws, d.splitk_ws_bytes = self._splitk_ws.data_ptr(), self._splitk_ws.numel() * 4
         self.keep += [wpack, bias, d]
         self.prog.add("gd_conv_igemm", C.byref(d))
         self.last_scale_slot = ("desc", d, None)

@@ -80,11 +80,22 @@ typedef struct gd_conv_desc {
    * The optional 1x1 source a1 stays raw. */
   int32_t gn_mode, gn_silu;
   const float* gn_coef;
+  /* Optional split-K workspace (16-byte aligned device memory the launch may scribble on; NULL = never split).
+   * A 3x3 conv whose (pixel tile, N tile) work items leave at least half of the SMs idle — the 8x8 / 16x16 layers of
+   * unet.py:552-609 at small per-GPU batch, K up to 18 432 — is cut along K into up to 8 splits that accumulate into
+   * fp32 slabs of this workspace; a second launch sums them in a fixed order and finishes the epilogue (bias,
+   * residual GD_RES_SAME, fp16 output, stats_out).  gd_conv_splitk_ws_bytes(desc) = the most this conv can use
+   * (0: it never splits); a smaller workspace just means fewer splits. */
+  void* splitk_ws;
+  int64_t splitk_ws_bytes;
 } gd_conv_desc;
 enum { GD_CONV_GN_OFF = 0, GD_CONV_GN_SAME = 1, GD_CONV_GN_UPSAMPLE2 = 2 };
 /* 1 if a 3x3 conv over h x w images can normalise its operand on the fly (16 x 8 pixel tiles of one image). */
 int gd_conv_gn_fusable(int32_t h, int32_t w);
 int gd_conv_igemm(const gd_conv_desc* desc, void* stream);
+/* Upper bound of the split-K workspace gd_conv_igemm(desc) can use on the current device (pointer fields other than
+ * NULL-ness of res / bias alignment are not dereferenced); 0 if this conv never splits. */
+int64_t gd_conv_splitk_ws_bytes(const gd_conv_desc* desc);
 /* Geometry of the fused statistics: number of row blocks the conv writes (rows of stats_out), and how many
  * consecutive rows belong to one image (rows_per_image * n == rows).  Returns 0 rows if the geometry is ineligible. */
 int64_t gd_conv_stats_rows(int32_t n, int32_t h, int32_t w, int32_t* rows_per_image);

@@ -27,7 +27,7 @@ def nhwc_half(x_nchw: th.Tensor, ld: int = None, off: int = 0) -> th.Tensor:
 
 def conv_igemm(a0_buf, c0, off0, wpack, bias, cout, n, h, w, *, taps=9, a1_buf=None, c1=0, off1=0, res_buf=None,
                res_off=0, res_mode=L.RES_NONE, out_mode=L.OUT_NHWC_F16, ld_out=None, out_off=0, out_scale=1.0, bn=0,
-               stats_out=None, out_buf=None, gn=None):
+               stats_out=None, out_buf=None, gn=None, splitk_ws=None):
     """gn = dict(mode, silu, coef): GroupNorm fused into the main operand (a0 is the raw tensor; coef from gn_coef)."""
     lib = L.load()
     d = L.ConvDesc()
@@ -52,6 +52,8 @@ def conv_igemm(a0_buf, c0, off0, wpack, bias, cout, n, h, w, *, taps=9, a1_buf=N
     if gn is not None:
         d.gn_mode, d.gn_silu = gn["mode"], int(gn.get("silu", True))
         d.gn_coef = gn["coef"].data_ptr()
+    if splitk_ws is not None:
+        d.splitk_ws, d.splitk_ws_bytes = splitk_ws.data_ptr(), splitk_ws.numel() * splitk_ws.element_size()
     L.check(lib.gd_conv_igemm(C.byref(d), stream()), "gd_conv_igemm")
     return out
 

@@ -367,3 +367,97 @@ def test_conv_fused_groupnorm_rejects_ineligible_geometry(lib):
     with pytest.raises(L.GdError, match="fusable"):
         H.conv_igemm(x_buf, 64, 0, pack_conv3x3(th.zeros(64, 64, 3, 3)).cuda(), None, 64, 2, 8, 8,
                      gn=dict(mode=L.CONV_GN_SAME, coef=th.zeros(2, 8, 16, device="cuda")))
+
+
+SPLITK_CASES = [
+    # n, h, w, cin, cout, c1, res: few pixel tiles, long K (the 8x8 / 16x16 layers at per-GPU batch 8, unet.py:552-609)
+    (8, 8, 8, 512, 512, 0, False),     # classifier 8x8: 2 pair tiles x 4 N tiles -> 8 splits of one channel block
+    (8, 8, 8, 1024, 1024, 0, True),    # UNet 8x8 with residual
+    (3, 8, 8, 320, 128, 0, True),      # odd batch (half-empty tile, masked rows), 5 channel blocks -> uneven splits
+    (1, 8, 8, 256, 256, 0, False),     # one pixel tile: single-CTA kernel
+    (4, 16, 16, 512, 256, 0, True),    # one image per tile, two tiles per image: one partial row per tile
+    (2, 8, 8, 256, 256, 128, False),   # fused 1x1-skip operand split along with the main channel blocks
+    (5, 16, 8, 128, 128, 0, False),    # 8-pixel-wide halo tiles
+]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,c1,res", SPLITK_CASES)
+def test_conv_split_k_matches_unsplit_and_torch(lib, n, h, w, cin, cout, c1, res):
+    """gd_conv_desc.splitk_ws: K split over idle SMs + fixed-order fp32 reduction.  Output within fp16 rounding of the
+    unsplit launch and of torch; fused GroupNorm partials give the same statistics; replays are bit-identical."""
+    import ctypes as C
+    x = _h(_rand((n, cin, h, w), 50))
+    wt = _h(_rand((cout, cin, 3, 3), 51, (cin * 9) ** -0.5))
+    b = _rand((cout,), 52, 0.3)
+    ref = F.conv2d(x, wt, b, padding=1)
+    kw = {}
+    w1 = None
+    if c1:
+        s = _h(_rand((n, c1, h, w), 53))
+        w1 = _h(_rand((cout, c1, 1, 1), 54, c1 ** -0.5))
+        ref = ref + F.conv2d(s, w1)
+        kw.update(a1_buf=H.nhwc_half(s), c1=c1)
+    if res:
+        r = _h(_rand((n, cout, h, w), 55))
+        ref = ref + r
+        kw.update(res_buf=H.nhwc_half(r), res_mode=L.RES_SAME)
+    pack = pack_conv3x3(wt, w1)
+    rpi = C.c_int32(0)
+    rows = int(lib.gd_conv_stats_rows(n, h, w, C.byref(rpi)))
+    xb = H.nhwc_half(x)
+
+    d = L.ConvDesc()
+    d.a0, d.c0, d.ld0, d.taps, d.n, d.h, d.w = xb.data_ptr(), cin, cin, 9, n, h, w
+    d.k_total, d.n_pad, d.cout, d.out_mode, d.ld_out = pack.shape[1], cout, cout, L.OUT_NHWC_F16, cout
+    d.out = xb.data_ptr()  # only alignment is inspected
+    d.bias = b.data_ptr()
+    need = int(lib.gd_conv_splitk_ws_bytes(C.byref(d)))
+    assert need > 0, "this geometry is expected to split"
+    outs, stats = [], []
+    for ws_bytes in (0, need, need, need // 2):
+        st = th.zeros((rows, cout // 4, 2), dtype=th.float32, device="cuda")
+        ws = th.full((ws_bytes // 4,), float("nan"), dtype=th.float32, device="cuda") if ws_bytes else None
+        lib.gd_launch_count_reset()
+        o = H.conv_igemm(xb, cin, 0, pack, b, cout, n, h, w, stats_out=st, splitk_ws=ws, **kw)
+        th.cuda.synchronize()
+        launches = int(lib.gd_launch_count())
+        assert launches == (2 if ws_bytes == need else launches)  # the full workspace must split
+        outs.append(o)
+        stats.append(st)
+    assert int(lib.gd_launch_count()) >= 1
+    err = H.rel_err(outs[1].permute(0, 3, 1, 2), ref)
+    err01 = H.rel_err(outs[1].float(), outs[0].float())
+    print(f"split-K n={n} {h}x{w} {cin}(+{c1})->{cout} res={res}: vs torch {err:.3e}, vs unsplit {err01:.3e}")
+    assert err < TOL and err01 < 2e-3
+    assert H.rel_err(outs[3].permute(0, 3, 1, 2), ref) < TOL   # a smaller workspace: fewer splits (or none), same result
+    assert th.equal(outs[1], outs[2]) and th.equal(stats[1], stats[2])  # fixed summation order
+    for st in (stats[1], stats[3]):
+        out_a = th.zeros((n, 32, 2), dtype=th.float32, device="cuda")
+        out_b = th.zeros((n, 32, 2), dtype=th.float32, device="cuda")
+        for src, dst in ((stats[0], out_a), (st, out_b)):
+            L.check(lib.gd_groupnorm_finalize_partials(H.vp(src), cout, cout // 4, None, 0, 0, rpi.value, n, h * w,
+                                                       C.c_float(1e-5), H.vp(dst), None, None, None, 0, None, H.stream()))
+        th.cuda.synchronize()
+        g = outs[1].float().permute(0, 3, 1, 2).reshape(n, 32, -1)
+        assert float((out_b[..., 0] - g.mean(-1)).abs().max()) < 3e-4
+        assert H.rel_err(out_b[..., 1], (g.var(-1, unbiased=False) + 1e-5).rsqrt()) < 3e-4
+        assert H.rel_err(out_b, out_a) < 3e-4
+
+
+def test_conv_split_k_is_not_used_for_large_grids(lib):
+    """Enough pixel tiles to fill the GPU: the workspace is ignored (one launch)."""
+    import ctypes as C
+    n, h, w, c = 8, 64, 64, 128
+    x = _h(_rand((n, c, h, w), 60))
+    wt = _h(_rand((c, c, 3, 3), 61, (c * 9) ** -0.5))
+    xb = H.nhwc_half(x)
+    d = L.ConvDesc()
+    d.a0, d.c0, d.ld0, d.taps, d.n, d.h, d.w = xb.data_ptr(), c, c, 9, n, h, w
+    d.k_total, d.n_pad, d.cout, d.out_mode, d.ld_out, d.out = 9 * c, c, c, L.OUT_NHWC_F16, c, xb.data_ptr()
+    assert int(lib.gd_conv_splitk_ws_bytes(C.byref(d))) == 0
+    ws = th.empty(1 << 20, dtype=th.float32, device="cuda")
+    lib.gd_launch_count_reset()
+    out = H.conv_igemm(xb, c, 0, pack_conv3x3(wt), None, c, n, h, w, splitk_ws=ws)
+    th.cuda.synchronize()
+    assert int(lib.gd_launch_count()) == 1
+    assert H.rel_err(out.permute(0, 3, 1, 2), F.conv2d(x, wt, None, padding=1)) < TOL
