@@ -1126,6 +1126,11 @@ int g_gn_na = 0;  // experiments: force the activation-ring depth of the fused-G
 // (profiles/quad_ab_r02.log): halving the L2 -> SM weight stream buys nothing because the mainloop is bound by the
 // tensor pipe at the power-capped clock (ncu: 99.3 % tensor-pipe active), while the lock-step of two pairs on one
 // weight ring and the 4-CTA cluster placement cost a few percent.
+// Split-K is OPT-IN (GD_B200_SPLITK=1, devtools key 9): the number of splits follows the number of pixel tiles, i.e. the
+// batch, and with it the fp32 summation order — a sample's bits would depend on the batch it is computed in, which every
+// other kernel here avoids (tests/test_gpu_models.py::test_full_size_guided_step_properties) — for a measured 0-2.6 %
+// of the batch-8 step (profiles/splitk_ab_r02.log).
+int g_splitk_mode = -1;  // -1: read GD_B200_SPLITK
 int g_quad_mode = [] {
   const char* e = getenv("GD_B200_QUAD");
   return e ? atoi(e) : 0;
@@ -1142,6 +1147,7 @@ void conv_debug_set(int key, int value) {
   if (key == 4) g_halo_mode = value;
   if (key == 7) g_gn_na = value;
   if (key == 8) g_quad_mode = value;
+  if (key == 9) g_splitk_mode = value ? 1 : 0;
 }
 
 // N tile: the largest divisor of n_pad (multiple of 16, <= 256) that still yields enough tiles to fill the SMs;
@@ -1180,7 +1186,6 @@ bool patch_shape(int h, int w, int& bw, int& bh, int& bi) {
 
 // split-K applies to 3x3 convs with the aligned fp16 NHWC output whose (pixel unit, n tile) work items leave at least
 // half of the GPU idle; the caller lends a workspace (gd_conv_desc.splitk_ws)
-int g_splitk_mode = -1;  // -1: read GD_B200_SPLITK (default on)
 // SMs a persistent conv grid leaves free (GD_B200_CONV_SM_RESERVE): a conv CTA owns its SM outright (all shared memory,
 // kGn: all registers), so while a full-width conv runs nothing of another stream can start.  In a guided step the
 // classifier and the UNet are two branches of one graph; a few free SMs let one branch's latency-bound small kernels
@@ -1197,7 +1202,7 @@ int conv_sms() {
 bool splitk_static_ok(const gd_conv_desc* d) {
   if (g_splitk_mode < 0) {
     const char* e = getenv("GD_B200_SPLITK");
-    g_splitk_mode = (e != nullptr && e[0] == '0') ? 0 : 1;
+    g_splitk_mode = (e != nullptr && e[0] == '1') ? 1 : 0;
   }
   return g_splitk_mode != 0 && d->gn_mode == GD_CONV_GN_OFF && d->taps == 9 && d->c0 >= 128 &&
          d->out_mode == GD_OUT_NHWC_F16 && d->cout % 64 == 0 && d->n_pad == d->cout && d->ld_out % 8 == 0 &&

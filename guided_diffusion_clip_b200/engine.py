@@ -275,10 +275,11 @@ class Emitter:
             d.gn_mode, d.gn_silu = gn["mode"], int(gn.get("silu", True))
             d.gn_coef = gn["coef"].data_ptr()
             self.keep.append(gn["coef"])
-        need = int(L.load().gd_conv_splitk_ws_bytes(C.byref(d))) if os.environ.get("GD_B200_SPLITK", "1") != "0" else 0
+        need = int(L.load().gd_conv_splitk_ws_bytes(C.byref(d))) if os.environ.get("GD_B200_SPLITK", "0") == "1" else 0
         if need > 0:
             # few pixel tiles, long K (8x8 / 16x16 layers at small batch): lend the launch a workspace to split K over
-            # the idle SMs.  One workspace per plan: its launches are serialised on one stream.
+            # the idle SMs.  One workspace per plan: its launches are serialised on one stream.  Opt-in
+            # (GD_B200_SPLITK=1): the split count follows the batch, which costs bit-for-bit batch invariance.
             if self._splitk_ws is None or self._splitk_ws.numel() * 4 < need:
                 self._splitk_ws = th.empty((need + 3) // 4, dtype=th.float32, device=self.device)
             self.keep.append(self._splitk_ws)

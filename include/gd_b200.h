@@ -81,6 +81,8 @@ typedef struct gd_conv_desc {
   int32_t gn_mode, gn_silu;
   const float* gn_coef;
   /* Optional split-K workspace (16-byte aligned device memory the launch may scribble on; NULL = never split).
+   * OPT-IN: honoured only when the process runs with GD_B200_SPLITK=1 — the number of splits follows the batch, so a
+   * sample's low-order bits then depend on the batch it is computed in (every other path is batch-invariant bit for bit).
    * A 3x3 conv whose (pixel tile, N tile) work items leave at least half of the SMs idle — the 8x8 / 16x16 layers of
    * unet.py:552-609 at small per-GPU batch, K up to 18 432 — is cut along K into up to 8 splits that accumulate into
    * fp32 slabs of this workspace; a second launch sums them in a fixed order and finishes the epilogue (bias,

@@ -14,7 +14,8 @@ extern "C" {
  * loads its own activation tile), key 5 = 0 disables the tcgen05 attention forward (mma.sync kernel for every length),
  * key 6 = 1 launches the frequent kernels with programmatic dependent launch (default 0: measured slower, DESIGN.md 4.2;
  * also GD_B200_PDL=1), key 7 = force the activation-ring depth of the fused-GroupNorm conv kernels (0 = heuristic), key 8 = 0 disables
- * the 4-CTA-cluster mode (weight tiles multicast to two CTA pairs). */
+ * the 4-CTA-cluster mode (weight tiles multicast to two CTA pairs), key 9 = 1 enables split-K for convs that were lent a
+ * workspace (gd_conv_desc.splitk_ws; default 0, also GD_B200_SPLITK=1). */
 void gd_debug_set(int key, int value);
 /* Measurement hook (profiles/bw_probe.py): stream `bytes` from src to dst. structure 0 = one-shot flat grid, -k = 256-thread
  * CTAs owning a contiguous region walked in k rounds of 8 loads/stores per thread, k>0 =
