@@ -559,22 +559,29 @@ def run_gpu_arm(args):
         if world > 1:
             dist.barrier()
         th.cuda.synchronize()
-        f0, f1, f2 = (th.cuda.Event(enable_timing=True) for _ in range(3))
+        f0, fl, f1, f2 = (th.cuda.Event(enable_timing=True) for _ in range(4))
         f0.record()
         with th.no_grad():
             final = diffusion.p_sample_loop(model_fn, shape, cond_fn=cond_fn, model_kwargs=kwargs, device=dev)
+        fl.record()
+        if world > 1:
+            # the gather is a rendezvous: a rank that finished its 250 steps early waits here for the slowest one.  The
+            # barrier separates that wait (rank_skew_ms) from the cost of the output stage itself (gather_ms); the
+            # whole-job time f0 -> f2 contains both, as it does for the reference's driver.
+            dist.barrier()
         f1.record()
         imgs, labs = gbuf.pack_and_gather(final, y)
         f2.record()
         th.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        loop_ms = th.tensor([f0.elapsed_time(f2), f1.elapsed_time(f2)], device=dev)
+        loop_ms = th.tensor([f0.elapsed_time(f2), f1.elapsed_time(f2), fl.elapsed_time(f1)], device=dev)
         if world > 1:
             dist.all_reduce(loop_ms, op=dist.ReduceOp.MAX)
         ok = bool(th.isfinite(final).all()) and len(imgs) == world and imgs[0].dtype == th.uint8
         full = {"steps": T, "seconds": float(loop_ms[0]) / 1e3, "value": world * B / (float(loop_ms[0]) / 1e3),
                 "unit": "samples/s", "ms_per_step": float(loop_ms[0]) / T, "gather_ms": float(loop_ms[1]),
+                "rank_skew_ms": float(loop_ms[2]),
                 "gathered_samples": int(sum(int(i.shape[0]) for i in imgs)), "ok": ok,
                 "what": "diffusion.p_sample_loop (250 steps) + uint8 NHWC pack into the gather buffer + all_gather of "
                         "samples and labels, device-timed, max over ranks"}
