@@ -110,6 +110,51 @@ def test_fullsize_guided_step_matches_reference(lib, golden_dir, name):
     th.cuda.empty_cache()
 
 
+@pytest.mark.gpu
+def test_fullsize_guided_step_with_split_k_matches_reference(lib, golden_dir, monkeypatch):
+    """The opt-in split-K path (GD_B200_SPLITK=1) inside the real model: at batch 1 every plain 3x3 conv with few pixel
+    tiles (the 8x8 layers, K up to 18 432, with residuals, fused skip operands and fused GroupNorm statistics, and the
+    classifier's data-gradient convs) is split over the idle SMs.
+    Same fixture, same tolerance as the default path; the launch count proves the split ran."""
+    if not hasattr(lib, "gd_debug_set"):
+        pytest.skip("library built without GD_B200_DEVTOOLS")
+    name = "cfg2"
+    dev = th.device("cuda", 0)
+    c = cfg.FULLSIZE_CASES[name]
+    G = _fixture(golden_dir, name)
+    monkeypatch.setenv("GD_B200_SPLITK", "1")   # the planner lends workspaces ...
+    lib.gd_debug_set(9, 1)                       # ... and the library (which read the variable at start-up) honours them
+    try:
+        model, d, cond = _build(name, dev)
+        x = cfg.fullsize_inputs(name)[0].to(dev)
+        y = th.tensor([c["label"]], device=dev)
+        t_model = th.tensor([int(G["t_model"])], device=dev)
+        with th.no_grad():
+            lib.gd_launch_count_reset()
+            eps = model(x, t_model, y)
+            launches = int(lib.gd_launch_count())
+            grad = cond(x, t_model, y=y)
+            th.cuda.synchronize()
+            lib.gd_debug_set(9, 0)  # same plan, workspaces ignored: the unsplit launch count
+            lib.gd_launch_count_reset()
+            eps0 = model(x, t_model, y)
+            launches0 = int(lib.gd_launch_count())
+        th.cuda.synchronize()
+    finally:
+        lib.gd_debug_set(9, 0)
+    e1, e2 = H.rel_err(eps, G["eps"].to(dev)), H.rel_err(grad, G["grad"].to(dev))
+    print(f"FULLSIZE {name} split-K: eps {e1:.3e} grad {e2:.3e} ({launches} UNet launches)")
+    gp = os.path.join(os.path.dirname(golden_dir), "..", "gpurun_out")
+    if os.path.isdir(gp):
+        with open(os.path.join(gp, "fullsize_parity.txt"), "a") as f:
+            f.write(f"{name}_splitk eps={e1:.3e} grad={e2:.3e} unet_launches={launches}\n")
+    assert e1 < TOL and e2 < TOL and H.rel_err(eps0, G["eps"].to(dev)) < TOL
+    assert launches >= launches0 + 10, f"no conv was split ({launches} launches with, {launches0} without)"
+    assert not th.equal(eps, eps0)  # a different summation order, not a silently ignored workspace
+    del model, cond
+    th.cuda.empty_cache()
+
+
 def test_oracle_matches_reference_at_full_size_cfg2(golden_dir):
     """CPU: the oracle restatement against the reference's configs[1] fixture at the REAL widths (UNet-256 forward +
     classifier-256 gradient, batch 1, ~20 s of host time) — pins oracle/oracle_models.py where the bench runs."""
