@@ -169,38 +169,63 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// The same with a suspend-time hint (ns): the thread may sleep in hardware until the phase completes OR the hint
+// expires, instead of returning after the (short) default time limit.  Completion still wakes it at once; what the hint
+// removes is the polling itself — in the fused conv a quarter of all issued warp instructions were try_wait / clock /
+// compare / branch of spinning producer, MMA and epilogue warps (ncu source page), issue slots and power the
+// transform warps of the same SM partitions need.
+constexpr uint32_t kMbarSuspendNs = 20000;
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(kMbarSuspendNs)
+      : "memory");
+  return ok != 0;
+}
 // acquire at cluster scope: the data the barrier guards was written by the OTHER CTA of a pair (generic-proxy stores
 // followed by a release.cluster arrive)
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(kMbarSuspendNs)
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must surface as a trap (launch failure), never as a hung GPU.
+// Bounded wait: a protocol bug must surface as a trap (launch failure), never as a hung GPU.  The clock is only read
+// every 1024 unsuccessful polls (with the hint a poll is rare; without it the loop must stay cheap).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
-      printf("gd: mbarrier wait timeout block %d thread %d parity %u\n", blockIdx.x, threadIdx.x, parity);
-      __trap();
+  long long t0 = 0;
+  for (uint32_t spins = 1; !mbar_try_wait_hint(bar, parity); ++spins) {
+    if ((spins & 1023u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+        printf("gd: mbarrier wait timeout block %d thread %d parity %u\n", blockIdx.x, threadIdx.x, parity);
+        __trap();
+      }
     }
   }
 }
 
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait_cluster(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait_cluster(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("gd: mbarrier (cluster) wait timeout block %d thread %d parity %u\n", blockIdx.x, threadIdx.x, parity);
-      __trap();
+  long long t0 = 0;
+  for (uint32_t spins = 1; !mbar_try_wait_cluster(bar, parity); ++spins) {
+    if ((spins & 1023u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 4000000000LL) {
+        printf("gd: mbarrier (cluster) wait timeout block %d thread %d parity %u\n", blockIdx.x, threadIdx.x, parity);
+        __trap();
+      }
     }
   }
 }
@@ -402,7 +427,16 @@ __device__ __forceinline__ Half8 float_to_half8(const float (&f)[8]) {
   for (int i = 0; i < 4; ++i) v.h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
   return v;
 }
-__device__ __forceinline__ Half8 ld_half8(const __half* p) { return *reinterpret_cast<const Half8*>(p); }
+// 16-byte accesses go through uint4: copying the struct itself is member-wise (__half2 has user-provided copy
+// operations), which the compiler lowers to FOUR 32-bit accesses — for the 64-byte-pitch staging tiles in shared memory
+// that is a 4-way bank conflict per store (ncu: 134 M wavefronts instead of 34 M in the dominant conv), in global memory
+// four partial-sector stores per lane.
+__device__ __forceinline__ Half8 ld_half8(const __half* p) {
+  const uint4 t = *reinterpret_cast<const uint4*>(p);
+  Half8 v;
+  *reinterpret_cast<uint4*>(&v) = t;
+  return v;
+}
 // streaming 16-byte load: read-only path, do not allocate in L1 (the GroupNorm kernels touch every byte exactly once)
 __device__ __forceinline__ Half8 ld_half8_stream(const __half* p) {
   uint32_t a, b, c, d;
@@ -414,7 +448,19 @@ __device__ __forceinline__ Half8 ld_half8_stream(const __half* p) {
   w[0] = a; w[1] = b; w[2] = c; w[3] = d;
   return v;
 }
-__device__ __forceinline__ void st_half8(__half* p, const Half8& v) { *reinterpret_cast<Half8*>(p) = v; }
+__device__ __forceinline__ void st_half8(__half* p, const Half8& v) {
+  *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(&v);
+}
+// the same for any 16-byte aligned address (shared-memory staging tiles)
+__device__ __forceinline__ void st_half8_at(void* p, const Half8& v) {
+  *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(&v);
+}
+__device__ __forceinline__ Half8 ld_half8_at(const void* p) {
+  const uint4 t = *reinterpret_cast<const uint4*>(p);
+  Half8 v;
+  *reinterpret_cast<uint4*>(&v) = t;
+  return v;
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

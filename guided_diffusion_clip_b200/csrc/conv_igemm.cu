@@ -171,7 +171,7 @@ __device__ __forceinline__ void epi_compute32(const uint32_t (&v)[32], const flo
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] += t[j];
     }
-    *reinterpret_cast<Half8*>(sw64(so, row, q)) = float_to_half8(f);
+    st_half8_at(sw64(so, row, q), float_to_half8(f));  // one STS.128: conflict-free with the 64-byte swizzle
     if (kStats) {
       cs[2 * q] = (f[0] + f[1]) + (f[2] + f[3]);
       cs[2 * q + 1] = (f[4] + f[5]) + (f[6] + f[7]);
@@ -872,7 +872,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             mbar_wait(rbar, res_phase);
             res_phase ^= 1;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) rv[q] = *reinterpret_cast<const Half8*>(sw64(sr, res_row, q));
+            for (int q = 0; q < 4; ++q) rv[q] = ld_half8_at(sw64(sr, res_row, q));
           } else if (p.res_mode == GD_RES_AVGPOOL2 && e.valid && p.debug == 0) {
             // residual lives at double resolution (unet.py:136,241): direct global reads, fp32 average -> fp16
             float racc[32];

@@ -29,7 +29,8 @@ ORDER = [("conv_gn_256_256_b64", ["conv_igemm_kernel"]), ("conv_gn_128_128_b64",
          ("conv_plain_128_128_b64", ["conv_igemm_kernel"]),
          ("gn_bwd_128_b64", ["gn_bwd_stats_kernel", "gn_finalize_kernel", "gn_bwd_apply_kernel"]),
          ("gn_apply_pool_256_b64", ["gn_apply_kernel"]), ("posterior_b64", ["posterior_kernel"]),
-         ("attn_fwd_tc_b64", ["attn_fwd_tc_kernel"])]
+         ("attn_fwd_tc_b64", ["attn_fwd_tc_kernel"]), ("conv_gn_512_256_b64", ["conv_igemm_kernel"]),
+         ("conv_gn_256_256_skip512_b64", ["conv_igemm_kernel"]), ("conv_gn_256_256_res_b64", ["conv_igemm_kernel"])]
 launches = [r for r in data if len(r) == len(hdr)]
 pos, summary, lines = 0, {}, []
 for key, kernels in ORDER:
@@ -58,7 +59,7 @@ for key, kernels in ORDER:
             if v is not None:
                 ent[nm] = v
     summary[key] = ent
-    lines.append(f"{key:26s} {ent['duration_us']:9.1f} us  dram {ent['dram_bytes_per_launch'] / 1e6:9.1f} MB  "
+    lines.append(f"{key:30s} {ent['duration_us']:9.1f} us  dram {ent['dram_bytes_per_launch'] / 1e6:9.1f} MB  "
                  f"({ent['dram_bytes_per_launch'] / max(ent['duration_us'], 1e-9) / 1e3:7.1f} GB/s)  tensor pipe "
                  f"{ent.get('tensor_pipe_active_pct', float('nan')):5.1f} %  dram {ent.get('dram_throughput_pct', float('nan')):5.1f} %  "
                  f"regs {ent.get('registers', 0):.0f}")

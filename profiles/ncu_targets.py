@@ -25,12 +25,17 @@ g = th.Generator().manual_seed(0)
 dev = "cuda"
 
 
-def conv_case(cin, cout, hw, gn):
+def conv_case(cin, cout, hw, gn, c1=0, res=False):
     x = th.randn((B, hw, hw, cin), generator=g).half().to(dev)
-    pack = pack_conv3x3((th.randn((cout, cin, 3, 3), generator=g) * (cin * 9) ** -0.5).to(dev))
+    w1 = (th.randn((cout, c1, 1, 1), generator=g) * c1 ** -0.5).to(dev) if c1 else None
+    pack = pack_conv3x3((th.randn((cout, cin, 3, 3), generator=g) * (cin * 9) ** -0.5).to(dev), w1)
     bias = th.zeros(cout, device=dev)
     out = th.empty((B, hw, hw, cout), dtype=th.float16, device=dev)
     kw = {}
+    if c1:  # the fused 1x1 skip_connection operand of an up ResBlock's second conv (unet.py:222, 256)
+        kw.update(a1_buf=th.randn((B, hw, hw, c1), generator=g).half().to(dev), c1=c1)
+    if res:  # identity residual (unet.py:256 with skip_connection = Identity)
+        kw.update(res_buf=th.randn((B, hw, hw, cout), generator=g).half().to(dev), res_mode=L.RES_SAME)
     if gn:
         st = H.gn_stats(x, cin)
         film = (0.1 * th.randn((B, 2 * cin), generator=g)).to(dev)
@@ -79,6 +84,9 @@ TARGETS = [
     ("gn_apply_pool_256_b64", gn_apply_pool_case(256, 256)),
     ("posterior_b64", posterior_case(256)),
     ("attn_fwd_tc_b64", attn_case(8, 1024)),
+    ("conv_gn_512_256_b64", conv_case(512, 256, 256, True)),                 # K = 4608, the largest time share of the UNet
+    ("conv_gn_256_256_skip512_b64", conv_case(256, 256, 256, True, c1=512)),  # K = 2816: fused 1x1-skip operand
+    ("conv_gn_256_256_res_b64", conv_case(256, 256, 256, True, res=True)),    # identity residual staged through shared memory
 ]
 
 if __name__ == "__main__":
